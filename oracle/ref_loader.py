@@ -1,0 +1,121 @@
+"""Loads the REAL Python reference (read-only, /root/reference) -- TEST INFRASTRUCTURE ONLY.
+
+The reference needs `gymnasium`, which is not installed in this image; a minimal stub of the
+few names it touches (Env, spaces.Box/Discrete/Tuple, envs.registration.register) is injected
+into sys.modules when the real package is absent.  Nothing here is available on the GPU box
+(no /root/reference there): callers must check `available()` and skip.
+
+`injected_dice(stream)` replays an explicit dice stream through the reference by patching
+numpy.random.randint, which is the only RNG call the reference env makes
+(gym_narde/envs/narde_env.py:29,112-113).
+"""
+from __future__ import annotations
+
+import contextlib
+import importlib
+import os
+import sys
+import types
+from unittest import mock
+
+import numpy as np
+
+REF_ROOT = os.environ.get("NARDE_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "gym_narde", "envs", "narde.py"))
+
+
+def _install_gymnasium_stub():
+    try:
+        import gymnasium  # noqa: F401
+        return
+    except Exception:
+        pass
+    gym = types.ModuleType("gymnasium")
+
+    class Env:
+        metadata = {}
+
+        def __init__(self, *a, **k):
+            pass
+
+        @property
+        def unwrapped(self):
+            return self
+
+    class _Space:
+        def sample(self):
+            raise NotImplementedError
+
+    class Box(_Space):
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+        def sample(self):
+            return np.random.randint(self.low, self.high + 1, size=self.shape).astype(self.dtype)
+
+    class Discrete(_Space):
+        def __init__(self, n):
+            self.n = n
+
+        def sample(self):
+            return int(np.random.randint(0, self.n))
+
+    class Tuple(_Space):
+        def __init__(self, spaces):
+            self.spaces = tuple(spaces)
+
+        def sample(self):
+            return tuple(s.sample() for s in self.spaces)
+
+    spaces = types.ModuleType("gymnasium.spaces")
+    spaces.Box, spaces.Discrete, spaces.Tuple = Box, Discrete, Tuple
+    envs = types.ModuleType("gymnasium.envs")
+    registration = types.ModuleType("gymnasium.envs.registration")
+    _registry = {}
+
+    def register(id, entry_point=None, **kw):
+        _registry[id] = (entry_point, kw)
+
+    registration.register = register
+    registration.registry = _registry
+    envs.registration = registration
+    gym.Env, gym.spaces, gym.envs = Env, spaces, envs
+    gym.register = register
+    sys.modules["gymnasium"] = gym
+    sys.modules["gymnasium.spaces"] = spaces
+    sys.modules["gymnasium.envs"] = envs
+    sys.modules["gymnasium.envs.registration"] = registration
+
+
+_cache = {}
+
+
+def load():
+    """Returns (narde_module, narde_env_module) of the real reference."""
+    if "mods" in _cache:
+        return _cache["mods"]
+    if not available():
+        raise RuntimeError("reference not present at %s" % REF_ROOT)
+    _install_gymnasium_stub()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    narde = importlib.import_module("gym_narde.envs.narde")
+    narde_env = importlib.import_module("gym_narde.envs.narde_env")
+    _cache["mods"] = (narde, narde_env)
+    return _cache["mods"]
+
+
+@contextlib.contextmanager
+def injected_dice(stream):
+    """Patch numpy.random.randint so the reference env consumes `stream` (ints 1..6) verbatim."""
+    it = iter(stream)
+
+    def fake_randint(low, high=None, size=None, dtype=int):
+        assert size is None
+        return int(next(it))
+
+    with mock.patch("numpy.random.randint", side_effect=fake_randint):
+        yield
