@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- legal-move-enumerated Narde env steps/s on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port on host cores)
+
+Workload (config.workload): BASELINE config 4's per-GPU shard -- 131072 lock-step environments per
+GPU (1M environments at 8 GPUs), full-rules random self-play: per env turn = Philox dice ->
+full legal-turn enumeration (written to HBM) -> uniform action -> apply -> termination/reward ->
+auto-reset -> Box(198) observation.  One "step" = one fused kernel launch over all envs of the GPU.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "legal-move-enumerated env steps/sec"
+UNIT = "env_steps/s"
+SEED = 0x5EED
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (C restatement of the reference's algorithm) on the host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, env_base, n_envs, n_steps = args
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    n, a, e = O.selfplay(seed, env_base, n_envs, n_steps)
+    return n, a, e, time.perf_counter() - t0
+
+
+def cpu_selfplay(cores, envs_per_core, steps):
+    """Full-rules random self-play on `cores` processes; returns (env_steps/s, total steps, mean A)."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    O.build()
+    jobs = [(SEED, c * envs_per_core, envs_per_core, steps) for c in range(cores)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    acts = sum(r[1] for r in res)
+    return total / wall, total, acts / max(total, 1), wall
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference algorithm's CPU implementation on all host cores.  The
+    reference is pure Python and cannot travel to the GPU box (no /root/reference there), so this
+    arm times the oracle port (oracle/narde_oracle.c), as the tier contract prescribes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    envs_per_core, sub_steps = 64, 100      # one "step" = 64*100 env turns per core (bounded sample)
+    for _ in range(max(args.warmup, 1)):
+        cpu_selfplay(cores, envs_per_core, 10)
+    vals, tot, A = [], 0, 0.0
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, n, a, wall = cpu_selfplay(cores, envs_per_core, sub_steps)
+        vals.append(v)
+        tot += n
+        A = a
+        t_all += wall
+    value = tot / t_all
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "full-rules random self-play (same dice/action stream as the CUDA arm)",
+                   "envs_per_core": envs_per_core, "turns_per_env_per_step": sub_steps, "mean_legal_actions": A},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d procs x %d envs x %d turns per step, %d steps" % (cores, envs_per_core, sub_steps, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0 and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+
+    from gym_narde_b200 import VecNardeEnv, _cabi
+
+    E, K, W = args.envs_per_gpu, args.steps, args.warmup
+    env = VecNardeEnv(E, seed=SEED, max_actions=args.cap, env_base=rank * E, device=dev)
+    env.reset()
+    for _ in range(args.burn_in):           # de-correlate game phases: steady-state self-play mix
+        env.step()
+    torch.cuda.synchronize()
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, n_steps):
+        """Per-step CUDA events on the launching stream; L2 flushed (untimed) between steps."""
+        evs = []
+        for _ in range(n_steps):
+            if flush is not None:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    # ---- device-resident arm: `value` ----
+    for _ in range(W):
+        env.step()
+    stats0 = env.stats.clone()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    ms = timed_loop(lambda: env.step(), K)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    clocks = sampler.stop()
+    dstats = (env.stats - stats0).cpu().tolist()
+    total_ms = sum(ms)
+    A = dstats[5] / float(E * K)
+
+    # ---- end-to-end arm: host action indices in (pinned) -> step -> reward/done out (pinned) ----
+    h_idx = torch.randint(0, 1 << 20, (E,), dtype=torch.int32).pin_memory()
+    d_idx = torch.zeros(E, dtype=torch.int32, device=dev)
+    h_rew = torch.zeros(E, dtype=torch.float32).pin_memory()
+    h_done = torch.zeros(E, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        d_idx.copy_(h_idx, non_blocking=True)               # H2D: this step's inputs (action indices)
+        obs, rew, term, trunc, info = env.step(d_idx)        # public API call
+        h_rew.copy_(rew, non_blocking=True)                  # D2H: this step's results
+        h_done.copy_(env.done, non_blocking=True)
+
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    ms_e2e = timed_loop(e2e_step, K)
+    barrier()
+    total_e2e = sum(ms_e2e)
+
+    # ---- config 2 side measurement (4096 lock-step envs, same kernel) ----
+    small = VecNardeEnv(4096, seed=SEED, max_actions=args.cap, env_base=0, device=dev)
+    small.reset()
+    for _ in range(args.burn_in):
+        small.step()
+    torch.cuda.synchronize()
+    ms_small = timed_loop(lambda: small.step(), min(K, 50))
+
+    # ---- reduce over ranks (MAX time), gather episode stats with NCCL ----
+    tmax = torch.tensor([total_ms, total_e2e], dtype=torch.float64, device=dev)
+    st = env.stats.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(gathered, st)                        # config 4: allgather of episode stats
+        st_all = torch.stack(gathered)
+    else:
+        st_all = st[None]
+    total_ms_max, total_e2e_max = tmax.cpu().tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        units = world * E * K
+        value = units / (total_ms_max * 1e-3)
+        e2e_value = units / (total_e2e_max * 1e-3)
+        bytes_per_unit = 871 + 8 * A                         # B_step(A)
+        kernel_ms = total_ms / K                             # rank-0 kernel: one launch per step
+        achieved = E * bytes_per_unit / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "step_full_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8/u32 bit arithmetic (obs f32)", "data": "synthetic",
+            "config": {"workload": "config4 shard: %d lock-step envs/GPU full-rules random self-play (1M envs at 8 GPUs)" % E,
+                       "envs_per_gpu": E, "action_capacity": args.cap, "burn_in_steps": args.burn_in,
+                       "mean_legal_actions": A, "max_legal_actions": int(st_all[:, 6].max().item()),
+                       "l2": "flushed between timed steps (256 MiB fill, untimed)" if flush is not None else "not flushed",
+                       "parallelism": "env-sharded x%d, no data-path collective" % world},
+            "roofline": {"bound": "hbm", "kernel": "k_step_full", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 5 * E,
+                    "ms_per_step": total_e2e_max / K,
+                    "note": "VecNardeEnv.step(action_idx): pinned int32 action indices H2D, reward f32 + done u8 D2H every step; Box(198) stays in HBM for the device-resident policy"},
+            "gpu_launches": K, "wall_ms": wall_ms, "clocks": clocks,
+            "config2_4096_envs": {"value": 4096 * len(ms_small) / (sum(ms_small) * 1e-3), "unit": UNIT,
+                                  "ms_per_step": sum(ms_small) / len(ms_small)},
+            "episode_stats": {k: int(v) for k, v in zip(_cabi.STAT_NAMES, st_all.sum(0).tolist())},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            v, n, a, wall = cpu_selfplay(cores, 64, 150)
+            v, n, a, wall = cpu_selfplay(cores, 64, max(150, int(150 * 12.0 / max(wall, 1e-3))))
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d procs x 64 envs, %d env turns total in %.1f s (oracle/narde_oracle.c o_selfplay)" % (cores, n, wall)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=131072)
+    ap.add_argument("--cap", type=int, default=64)
+    ap.add_argument("--burn-in", type=int, default=300)
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+// narde_env.cuh -- per-environment bodies of the C-ABI entry points (include/narde_b200.h).
+// The CUDA kernels (narde_kernels.cu) wrap these with coalesced state loads/stores; the
+// test-only host harness (tests/hostsim/) wraps the same bodies in plain loops.
+#pragma once
+#include "narde_core.cuh"
+
+namespace narde {
+
+enum : int {
+  F_REWARD_MOVER12 = 1,
+  F_AUTORESET = 2,
+  F_HALF_MOVES_ONLY = 4,
+  DONE_TERMINATED = 1,
+  DONE_TRUNCATED = 2,
+};
+
+// ---- reset (narde_env.py:105-120) ---------------------------------------------------------
+NHD State reset_env(uint64_t seed, uint32_t env, uint64_t step) {
+  return initial_state(opening_player(seed, env, step));
+}
+
+// ---- Tier R1 -------------------------------------------------------------------------------
+struct MoveWriter {
+  uint8_t* out;
+  int n;
+  NHD void operator()(int from, int to) {
+    out[2 * n] = (uint8_t)from;
+    out[2 * n + 1] = (uint8_t)to;
+    n++;
+  }
+};
+
+NHD int half_moves_env(const State& s, const uint8_t* dice4, int player_override, uint8_t* moves) {
+  int player = player_override ? player_override : s.turn();
+  bool first_turn = (s.flags() & (player == 1 ? FLAG_FIRST_W : FLAG_FIRST_B)) != 0;
+  Pos P = decode_pos(s, player);
+  int nroll = 0;
+  uint8_t roll[4];
+  for (int k = 0; k < 4; k++)
+    if (dice4[k] != 0) roll[nroll++] = dice4[k];
+  MoveWriter mw = {moves, 0};
+  return half_moves_list(P, roll, nroll, first_turn, mw);
+}
+
+// ---- Tier R2 -------------------------------------------------------------------------------
+NHD void step_ref_env(State& s, int d1, int d2, int code1, int code2, int max_episode_steps,
+                      int* reward, int* done_bits) {
+  if (s.flags() & FLAG_DONE) {  // terminated envs are left untouched
+    *reward = 0;
+    *done_bits = DONE_TERMINATED;
+    return;
+  }
+  int dn;
+  step_reference(s, d1, d2, code1, code2, reward, &dn);
+  int bits = dn ? DONE_TERMINATED : 0;
+  if (!dn && max_episode_steps > 0 && (int)s.steps() >= max_episode_steps) bits |= DONE_TRUNCATED;
+  *done_bits = bits;
+}
+
+// ---- Tier N: fused full-rules step ---------------------------------------------------------
+struct StepFullArgs {
+  int64_t env_base;
+  uint64_t seed, step;
+  const uint8_t* dice_in;
+  const int32_t* action_idx;
+  int cap;
+  uint64_t* actions;
+  int32_t* counts;
+  uint8_t* dice_out;
+  uint64_t* chosen;
+  float* reward;
+  uint8_t* done;
+  int flags;
+  int max_episode_steps;
+};
+
+struct StepFullLocal {  // per-env contributions to the stats vector
+  int count;
+  int finished, white_win, black_win, mars, ep_len, overflow;
+};
+
+NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal& L) {
+  L.count = 0;
+  L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
+  uint32_t env = (uint32_t)(A.env_base + i);
+  if (s.flags() & FLAG_DONE) {  // only reachable without auto-reset: a finished env idles
+    if (A.counts) A.counts[i] = 0;
+    if (A.dice_out) A.dice_out[2 * i] = A.dice_out[2 * i + 1] = 0;
+    if (A.chosen) A.chosen[i] = ACT_EMPTY;
+    if (A.reward) A.reward[i] = 0.0f;
+    if (A.done) A.done[i] = DONE_TERMINATED;
+    return;
+  }
+  U4 rnd = turn_random(A.seed, env, A.step);
+  int d1, d2;
+  if (A.dice_in) {
+    d1 = A.dice_in[2 * i];
+    d2 = A.dice_in[2 * i + 1];
+  } else {
+    d1 = die_from_word(rnd.x);
+    d2 = die_from_word(rnd.y);
+  }
+  int player = s.turn();
+  bool first_turn = (s.flags() & (player == 1 ? FLAG_FIRST_W : FLAG_FIRST_B)) != 0;
+  Pos P = decode_pos(s, player);
+
+  int count;
+  uint64_t* slice = A.actions ? A.actions + (int64_t)i * A.cap : nullptr;
+  if (slice) {
+    StoreSink sk = {slice, A.cap, 1, 0};
+    count = enumerate_turn(P, d1, d2, first_turn, sk);
+  } else {
+    CountSink ck;
+    count = enumerate_turn(P, d1, d2, first_turn, ck);
+  }
+  L.count = count;
+  L.overflow = (slice && count > A.cap) ? 1 : 0;
+
+  uint64_t act = ACT_EMPTY;
+  if (count > 0) {
+    int idx;
+    if (A.action_idx) {
+      idx = A.action_idx[i];
+      if (idx < 0) idx = 0;
+      if (idx >= count) idx = count - 1;
+    } else {
+      idx = (int)mulhi32(rnd.z, (uint32_t)count);
+    }
+    if (slice && idx < A.cap) {
+      act = slice[idx];
+    } else {  // not stored: enumerate again and pick the idx-th
+      PickSink pk = {idx, 0, ACT_EMPTY};
+      enumerate_turn(P, d1, d2, first_turn, pk);
+      act = pk.picked;
+    }
+    apply_action(s, player, act);
+  }
+  float rew;
+  int dn;
+  finish_turn(s, player, (A.flags & F_REWARD_MOVER12) ? 1 : 0, &rew, &dn);
+  int bits = dn ? DONE_TERMINATED : 0;
+  if (!dn && A.max_episode_steps > 0 && (int)s.steps() >= A.max_episode_steps) bits |= DONE_TRUNCATED;
+  if (bits) {
+    L.finished = 1;
+    L.ep_len = (int)s.steps();
+    if (dn) {
+      if (player == 1)
+        L.white_win = 1;
+      else
+        L.black_win = 1;
+      int loser_off = player == 1 ? s.off_b() : s.off_w();
+      L.mars = loser_off == 0 ? 1 : 0;
+    }
+    if (A.flags & F_AUTORESET) s = reset_env(A.seed, env, A.step);
+  }
+  if (A.counts) A.counts[i] = count;
+  if (A.dice_out) {
+    A.dice_out[2 * i] = (uint8_t)d1;
+    A.dice_out[2 * i + 1] = (uint8_t)d2;
+  }
+  if (A.chosen) A.chosen[i] = act;
+  if (A.reward) A.reward[i] = rew;
+  if (A.done) A.done[i] = (uint8_t)bits;
+}
+
+// ---- narde_enumerate body -------------------------------------------------------------------
+NHD int enumerate_env(const State& s, int d1, int d2, int cap, uint64_t* slice) {
+  int player = s.turn();
+  bool first_turn = (s.flags() & (player == 1 ? FLAG_FIRST_W : FLAG_FIRST_B)) != 0;
+  Pos P = decode_pos(s, player);
+  StoreSink sk = {slice, cap, 1, 0};
+  return enumerate_turn(P, d1, d2, first_turn, sk);
+}
+
+// ---- narde_apply_actions body ---------------------------------------------------------------
+NHD void apply_actions_env(State& s, uint64_t act, int flags, float* reward, int* done_bits) {
+  if (s.flags() & FLAG_DONE) {
+    *reward = 0.0f;
+    *done_bits = DONE_TERMINATED;
+    return;
+  }
+  int player = s.turn();
+  apply_action(s, player, act);
+  if (flags & F_HALF_MOVES_ONLY) {  // Narde.execute_rotated_move only (narde.py:36-56)
+    *reward = 0.0f;
+    *done_bits = 0;
+    return;
+  }
+  int dn;
+  finish_turn(s, player, (flags & F_REWARD_MOVER12) ? 1 : 0, reward, &dn);
+  *done_bits = dn ? DONE_TERMINATED : 0;
+}
+
+}  // namespace narde

@@ -1,0 +1,335 @@
+// narde_kernels.cu -- sm_100a kernels + the C ABI of include/narde_b200.h.
+//
+// Layout in HBM: two SoA planes lo[N], hi[N] of 16-byte lanes (one uint4 per env per plane) so a
+// warp loads/stores 512 contiguous bytes per plane.  One thread owns one environment for the
+// integer rules work (registers only); Box(198) rows are written by the whole CTA from a
+// shared-memory copy of the CTA's states so that global stores are contiguous 16-byte lanes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/narde_b200.h"
+#include "narde_env.cuh"
+
+using namespace narde;
+
+namespace {
+
+constexpr int kThreads = 128;
+
+__device__ __forceinline__ State ld_state(const uint4* __restrict__ lo, const uint4* __restrict__ hi, int64_t i) {
+  uint4 a = lo[i], b = hi[i];
+  State s;
+  s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
+  s.w[4] = b.x; s.w[5] = b.y; s.meta = b.z; s.aux = b.w;
+  return s;
+}
+__device__ __forceinline__ void st_state(uint4* __restrict__ lo, uint4* __restrict__ hi, int64_t i, const State& s) {
+  lo[i] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+  hi[i] = make_uint4(s.w[4], s.w[5], s.meta, s.aux);
+}
+
+// CTA-cooperative Box(198) writer: sm[] holds the CTA's states, rows [row0, row0+rows).
+__device__ __forceinline__ void write_obs198_cta(const State* sm, int rows, int64_t row0, float* __restrict__ obs) {
+  float* base = obs + row0 * 198;
+  const int pairs = rows * 99;
+  if ((((uintptr_t)base) & 15u) == 0) {
+    // 16-byte lanes: two (x,y) pairs per store; pairs never straddle more than two rows
+    float4* b4 = reinterpret_cast<float4*>(base);
+    const int quads = pairs >> 1;
+    for (int g = threadIdx.x; g < quads; g += blockDim.x) {
+      int p0 = 2 * g, p1 = p0 + 1;
+      int e0 = p0 / 99, e1 = p1 / 99;
+      float4 v;
+      obs198_pair(sm[e0], p0 - e0 * 99, &v.x, &v.y);
+      obs198_pair(sm[e1], p1 - e1 * 99, &v.z, &v.w);
+      b4[g] = v;
+    }
+    if ((pairs & 1) && threadIdx.x == 0) {
+      int p = pairs - 1, e = p / 99;
+      float2 v;
+      obs198_pair(sm[e], p - e * 99, &v.x, &v.y);
+      reinterpret_cast<float2*>(base)[p] = v;
+    }
+  } else {
+    float2* b2 = reinterpret_cast<float2*>(base);
+    for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+      int e = p / 99;
+      float2 v;
+      obs198_pair(sm[e], p - e * 99, &v.x, &v.y);
+      b2[p] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_reset(uint4* lo, uint4* hi, const uint8_t* mask, int64_t n, int64_t env_base,
+                                                   uint64_t seed, uint64_t step) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask && !mask[i]) return;
+  st_state(lo, hi, i, reset_env(seed, (uint32_t)(env_base + i), step));
+}
+
+__global__ void __launch_bounds__(kThreads) k_half_moves(const uint4* lo, const uint4* hi, const uint8_t* dice, int64_t n,
+                                                        int player_override, uint8_t* moves, int32_t* counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  State s = ld_state(lo, hi, i);
+  uint32_t d4 = reinterpret_cast<const uint32_t*>(dice)[i];
+  uint8_t dd[4] = {(uint8_t)(d4 & 0xFF), (uint8_t)((d4 >> 8) & 0xFF), (uint8_t)((d4 >> 16) & 0xFF), (uint8_t)(d4 >> 24)};
+  counts[i] = half_moves_env(s, dd, player_override, moves + i * (NARDE_MAX_HALF_MOVES * 2));
+}
+
+__global__ void __launch_bounds__(kThreads) k_step_ref(uint4* lo, uint4* hi, const uint8_t* dice, const int32_t* codes, int64_t n,
+                                                      int max_episode_steps, int32_t* o24, int32_t* reward, uint8_t* done) {
+  __shared__ State sm[kThreads];
+  int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+  int64_t i = row0 + threadIdx.x;
+  if (i < n) {
+    State s = ld_state(lo, hi, i);
+    uint16_t d2 = reinterpret_cast<const uint16_t*>(dice)[i];
+    int2 c = reinterpret_cast<const int2*>(codes)[i];
+    int r, dn;
+    step_ref_env(s, d2 & 0xFF, d2 >> 8, c.x, c.y, max_episode_steps, &r, &dn);
+    st_state(lo, hi, i, s);
+    if (reward) reward[i] = r;
+    if (done) done[i] = (uint8_t)dn;
+    sm[threadIdx.x] = s;
+  }
+  if (!o24) return;
+  __syncthreads();
+  int rows = (int)min((int64_t)blockDim.x, n - row0);
+  // narde_env.py:24-25: 24 int32 per env, written as contiguous words by the CTA
+  int32_t* base = o24 + row0 * 24;
+  for (int j = threadIdx.x; j < rows * 24; j += blockDim.x) {
+    int e = j / 24, k = j - e * 24;
+    const State& s = sm[e];
+    int v = s.turn() == 1 ? s.point(k) : -s.point(k < 12 ? k + 12 : k - 12);
+    base[j] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_enumerate(const uint4* lo, const uint4* hi, const uint8_t* dice, int64_t n, int cap,
+                                                       uint64_t* actions, int32_t* counts, uint8_t* overflow) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  State s = ld_state(lo, hi, i);
+  uint16_t d2 = reinterpret_cast<const uint16_t*>(dice)[i];
+  int c = 0;
+  if (!(s.flags() & FLAG_DONE)) c = enumerate_env(s, d2 & 0xFF, d2 >> 8, cap, actions + i * (int64_t)cap);
+  counts[i] = c;
+  if (overflow) overflow[i] = c > cap ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, int64_t n, StepFullArgs A, float* obs198, int64_t* stats) {
+  __shared__ State sm[kThreads];
+  int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+  int64_t i = row0 + threadIdx.x;
+  StepFullLocal L;
+  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
+  if (i < n) {
+    State s = ld_state(lo, hi, i);
+    step_full_env(s, i, A, L);
+    st_state(lo, hi, i, s);
+    sm[threadIdx.x] = s;
+  }
+  if (stats) {
+    // warp-level reduction, one atomic per warp per slot that is non-zero
+    unsigned full = 0xFFFFFFFFu;
+    int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
+    int mx = L.count, ov = L.overflow;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(full, v[k], o);
+      mx = max(mx, __shfl_xor_sync(full, mx, o));
+      ov += __shfl_xor_sync(full, ov, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++)
+        if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
+      if (mx) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)mx);
+      if (ov) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), (unsigned long long)ov);
+    }
+  }
+  if (!obs198) return;
+  __syncthreads();
+  int rows = (int)min((int64_t)blockDim.x, n - row0);
+  write_obs198_cta(sm, rows, row0, obs198);
+}
+
+__global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {
+  __shared__ State sm[kThreads];
+  int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+  int64_t i = row0 + threadIdx.x;
+  if (i < n) sm[threadIdx.x] = ld_state(lo, hi, i);
+  __syncthreads();
+  int rows = (int)min((int64_t)blockDim.x, n - row0);
+  write_obs198_cta(sm, rows, row0, obs198);
+}
+
+__global__ void __launch_bounds__(kThreads) k_obs24(const uint4* lo, const uint4* hi, int64_t n, int32_t* o24) {
+  __shared__ State sm[kThreads];
+  int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+  int64_t i = row0 + threadIdx.x;
+  if (i < n) sm[threadIdx.x] = ld_state(lo, hi, i);
+  __syncthreads();
+  int rows = (int)min((int64_t)blockDim.x, n - row0);
+  int32_t* base = o24 + row0 * 24;
+  for (int j = threadIdx.x; j < rows * 24; j += blockDim.x) {
+    int e = j / 24, k = j - e * 24;
+    const State& s = sm[e];
+    base[j] = s.turn() == 1 ? s.point(k) : -s.point(k < 12 ? k + 12 : k - 12);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_apply_actions(uint4* lo, uint4* hi, const uint64_t* acts, int64_t n, int flags,
+                                                           float* reward, uint8_t* done) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  State s = ld_state(lo, hi, i);
+  float r;
+  int dn;
+  apply_actions_env(s, acts[i], flags, &r, &dn);
+  st_state(lo, hi, i, s);
+  if (reward) reward[i] = r;
+  if (done) done[i] = (uint8_t)dn;
+}
+
+__global__ void __launch_bounds__(kThreads) k_roll_dice(int64_t n, int64_t env_base, uint64_t seed, uint64_t step, uint8_t* dice) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  U4 r = turn_random(seed, (uint32_t)(env_base + i), step);
+  reinterpret_cast<uint16_t*>(dice)[i] = (uint16_t)(die_from_word(r.x) | (die_from_word(r.y) << 8));
+}
+
+__global__ void __launch_bounds__(kThreads) k_block_rule(const int8_t* boards, int64_t n, uint8_t* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t own = 0, opp = 0;
+  for (int k = 0; k < 24; k++) {
+    int v = boards[i * 24 + k];
+    own |= (v > 0 ? 1u : 0u) << k;
+    opp |= (v < 0 ? 1u : 0u) << k;
+  }
+  out[i] = violates_block(own, opp) ? 1 : 0;
+}
+
+inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+inline int launch_status() { return (int)cudaGetLastError(); }
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int narde_abi_version(void) { return NARDE_ABI_VERSION; }
+const char* narde_build_arch(void) { return "sm_100a"; }
+
+int narde_reset_masked(void* lo, void* hi, const uint8_t* mask, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
+                       void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
+  k_reset<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, mask, n, env_base, seed, step);
+  return launch_status();
+}
+
+int narde_reset(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, void* stream) {
+  return narde_reset_masked(lo, hi, nullptr, n, env_base, seed, step, stream);
+}
+
+int narde_half_moves(const void* lo, const void* hi, const uint8_t* dice, int64_t n, int player_override, uint8_t* moves,
+                     int32_t* counts, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !lo || !hi || !dice || !moves || !counts || !aligned16(lo) || !aligned16(hi)) return -1;
+  if ((((uintptr_t)dice) & 3u) != 0) return -1;
+  k_half_moves<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, dice, n,
+                                                                   player_override, moves, counts);
+  return launch_status();
+}
+
+int narde_step_ref(void* lo, void* hi, const uint8_t* dice, const int32_t* codes, int64_t n, int32_t max_episode_steps,
+                   int32_t* obs24, int32_t* reward, uint8_t* done, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !lo || !hi || !dice || !codes || !aligned16(lo) || !aligned16(hi)) return -1;
+  if ((((uintptr_t)dice) & 1u) != 0 || (((uintptr_t)codes) & 7u) != 0) return -1;
+  k_step_ref<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, dice, codes, n,
+                                                                 max_episode_steps, obs24, reward, done);
+  return launch_status();
+}
+
+int narde_enumerate(const void* lo, const void* hi, const uint8_t* dice, int64_t n, int32_t cap, uint64_t* actions,
+                    int32_t* counts, uint8_t* overflow, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || cap < 0 || !lo || !hi || !dice || !counts || (cap > 0 && !actions) || !aligned16(lo) || !aligned16(hi))
+    return -1;
+  if ((((uintptr_t)dice) & 1u) != 0) return -1;
+  k_enumerate<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, dice, n, cap,
+                                                                  actions, counts, overflow);
+  return launch_status();
+}
+
+int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
+                    const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
+                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, int64_t* stats, int32_t flags,
+                    int32_t max_episode_steps, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || cap < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
+  if (obs198 && (((uintptr_t)obs198) & 7u) != 0) return -1;
+  if (n == 0) return 0;
+  StepFullArgs A;
+  A.env_base = env_base;
+  A.seed = seed;
+  A.step = step;
+  A.dice_in = dice_in;
+  A.action_idx = action_idx;
+  A.cap = cap;
+  A.actions = cap > 0 ? actions : nullptr;
+  A.counts = counts;
+  A.dice_out = dice_out;
+  A.chosen = chosen;
+  A.reward = reward;
+  A.done = done;
+  A.flags = flags;
+  A.max_episode_steps = max_episode_steps;
+  k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
+  return launch_status();
+}
+
+int narde_obs198(const void* lo, const void* hi, int64_t n, float* obs198, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !lo || !hi || !obs198 || !aligned16(lo) || !aligned16(hi) || (((uintptr_t)obs198) & 7u) != 0) return -1;
+  k_obs198<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, n, obs198);
+  return launch_status();
+}
+
+int narde_obs24(const void* lo, const void* hi, int64_t n, int32_t* obs24, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !lo || !hi || !obs24 || !aligned16(lo) || !aligned16(hi)) return -1;
+  k_obs24<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, n, obs24);
+  return launch_status();
+}
+
+int narde_apply_actions(void* lo, void* hi, const uint64_t* acts, int64_t n, int32_t flags, float* reward, uint8_t* done,
+                        void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !lo || !hi || !acts || !aligned16(lo) || !aligned16(hi)) return -1;
+  k_apply_actions<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, acts, n, flags, reward, done);
+  return launch_status();
+}
+
+int narde_roll_dice(int64_t n, int64_t env_base, uint64_t seed, uint64_t step, uint8_t* dice, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !dice || (((uintptr_t)dice) & 1u) != 0) return -1;
+  k_roll_dice<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(n, env_base, seed, step, dice);
+  return launch_status();
+}
+
+int narde_violates_block_rule(const int8_t* boards, int64_t n, uint8_t* out, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !boards || !out) return -1;
+  k_block_rule<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(boards, n, out);
+  return launch_status();
+}
+
+}  // extern "C"

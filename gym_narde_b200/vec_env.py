@@ -1,0 +1,141 @@
+"""VecNardeEnv -- N lock-step Narde games on one B200, same calls as the reference NardeEnv.
+
+Mirrors gym_narde/envs/narde_env.py (reset/step/observation/reward) over a batch:
+  rules="full"      README contract (Tier N): full legal-turn enumeration (max-dice, higher-die,
+                    per-turn head rule, doubles up to 4 half-moves), Box(198) observation,
+                    reward +1 iff WHITE wins (or the reference's mover 1/2 with reward="mover12").
+  rules="reference" the reference code's exact behaviour (Tier R): NardeEnv.step quirks included,
+                    int32[24] mover-perspective observation, reward 1/2 to the mover.
+All state lives in HBM as two [N,16] uint8 planes; every method enqueues hand-written sm_100a
+kernels through the C ABI (gym_narde_b200/_cabi.py).  There is no CPU path.
+"""
+from __future__ import annotations
+
+from . import _cabi
+
+
+class VecNardeEnv:
+    def __init__(self, num_envs, seed=0, rules="full", reward=None, max_actions=64, device="cuda",
+                 env_base=0, autoreset=True, max_episode_steps=1000, write_actions=True):
+        torch = _cabi.require_cuda()
+        _cabi.load()
+        if rules not in ("full", "reference"):
+            raise ValueError("rules must be 'full' or 'reference'")
+        self.torch = torch
+        self.num_envs = int(num_envs)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.rules = rules
+        self.reward_mode = reward or ("white01" if rules == "full" else "mover12")
+        if self.reward_mode not in ("white01", "mover12"):
+            raise ValueError("reward must be 'white01' or 'mover12'")
+        self.max_actions = int(max_actions)
+        self.device = torch.device(device)
+        self.env_base = int(env_base)
+        self.autoreset = bool(autoreset)
+        self.max_episode_steps = int(max_episode_steps)
+        self.write_actions = bool(write_actions)
+        self.step_count = 0  # Philox step counter (global, shared by all envs)
+        n, dev = self.num_envs, self.device
+        self.lo = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
+        self.hi = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
+        self.dice = torch.zeros((n, 2), dtype=torch.uint8, device=dev)
+        self.counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.chosen = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.actions = torch.zeros((n, self.max_actions), dtype=torch.int64, device=dev)
+        self.overflow = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.stats = torch.zeros(_cabi.NUM_STATS, dtype=torch.int64, device=dev)
+        if rules == "full":
+            self.obs = torch.zeros((n, 198), dtype=torch.float32, device=dev)
+            self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        else:
+            self.obs = torch.zeros((n, 24), dtype=torch.int32, device=dev)
+            self.reward = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    # -- gym-style API -----------------------------------------------------------------------
+    def reset(self, *, seed=None, options=None):
+        """NardeEnv.reset (narde_env.py:105-120) for every env; returns (obs, {})."""
+        if seed is not None:
+            self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.step_count = 0
+        _cabi.reset(self.lo, self.hi, self.env_base, self.seed, 0)
+        self.stats.zero_()
+        return self.observe(), {}
+
+    def observe(self):
+        if self.rules == "full":
+            _cabi.obs198(self.lo, self.hi, self.obs)
+        else:
+            _cabi.obs24(self.lo, self.hi, self.obs)
+        return self.obs
+
+    def roll(self):
+        """The dice the NEXT step will use (Philox stream); [N,2] uint8."""
+        _cabi.roll_dice(self.dice, self.env_base, self.seed, self.step_count + 1)
+        return self.dice
+
+    def get_valid_moves(self, dice4):
+        """Narde.get_valid_moves for every env (narde.py:58-92).  dice4: [N,4] uint8, 0-padded.
+        Returns (moves [N,96,2] uint8 with 255 = 'off', counts [N] int32)."""
+        t = self.torch
+        moves = t.zeros((self.num_envs, _cabi.MAX_HALF_MOVES, 2), dtype=t.uint8, device=self.device)
+        counts = t.zeros(self.num_envs, dtype=t.int32, device=self.device)
+        _cabi.half_moves(self.lo, self.hi, dice4, moves, counts)
+        return moves, counts
+
+    def get_valid_actions(self, dice=None):
+        """README get_valid_actions(roll): all legal full-turn actions per env.
+        Returns (actions [N,max_actions] int64 bit patterns, counts [N], overflow [N])."""
+        if dice is None:
+            dice = self.roll()
+        _cabi.enumerate_actions(self.lo, self.hi, dice, self.actions, self.counts, self.overflow)
+        return self.actions, self.counts, self.overflow
+
+    def step(self, actions=None, dice=None):
+        """One lock-step turn for all envs.
+
+        rules="full":      actions = int32 [N] indices into get_valid_actions (None = uniform random
+                           from the Philox stream); dice = optional [N,2] uint8 override.
+        rules="reference": actions = int32 [N,2] codes (from*24+to) exactly as NardeEnv.step takes
+                           them; dice default to the Philox stream.
+        Returns (obs, reward, terminated, truncated, info)."""
+        t = self.torch
+        self.step_count += 1
+        if self.rules == "full":
+            flags = (_cabi.REWARD_MOVER12 if self.reward_mode == "mover12" else 0) | (
+                _cabi.AUTORESET if self.autoreset else 0)
+            _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, self.step_count, dice_in=dice,
+                            action_idx=actions, actions=self.actions if self.write_actions else None,
+                            counts=self.counts, dice_out=self.dice, chosen=self.chosen, obs198=self.obs,
+                            reward=self.reward, done=self.done, stats=self.stats, flags=flags,
+                            max_episode_steps=self.max_episode_steps)
+        else:
+            if actions is None:
+                raise ValueError("rules='reference' needs action codes [N,2]")
+            if dice is None:
+                _cabi.roll_dice(self.dice, self.env_base, self.seed, self.step_count)
+                dice = self.dice
+            _cabi.step_ref(self.lo, self.hi, dice, actions, self.obs, self.reward, self.done,
+                           max_episode_steps=self.max_episode_steps)
+        terminated = (self.done & _cabi.TERMINATED) != 0
+        truncated = (self.done & _cabi.TRUNCATED) != 0
+        info = {"dice": self.dice, "counts": self.counts, "chosen": self.chosen}
+        return self.obs, self.reward, terminated, truncated, info
+
+    def episode_stats(self):
+        """Device-side counters as a dict (one D2H copy)."""
+        v = self.stats.cpu().tolist()
+        return dict(zip(_cabi.STAT_NAMES, v))
+
+    # -- checkpoint: the SoA planes + the Philox (seed, step) are the complete state -----------
+    def state_dict(self):
+        return {"lo": self.lo.clone(), "hi": self.hi.clone(), "seed": self.seed, "step_count": self.step_count,
+                "env_base": self.env_base, "rules": self.rules}
+
+    def load_state_dict(self, sd):
+        self.lo.copy_(sd["lo"])
+        self.hi.copy_(sd["hi"])
+        self.seed, self.step_count, self.env_base = sd["seed"], sd["step_count"], sd["env_base"]
+
+    def close(self):
+        pass

@@ -1,0 +1,135 @@
+/*
+ * narde_b200.h -- C ABI of the B200-native batched Narde environment path.
+ *
+ * Drop-in boundary for the reference's rules engine + env step
+ * (/root/reference/gym_narde/envs/narde.py, narde_env.py).  The reference
+ * is pure Python with no FFI; the binding a maintainer would add is the ctypes stub shown in
+ * INTEGRATION.md (the product's own host side, gym_narde_b200/_cabi.py, is exactly that stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a cudaError_t value (> 0) / -1 for bad arguments;
+ *     nothing is thrown across the ABI;
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); the library
+ *     allocates nothing and keeps no state;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream);
+ *   - n = number of environments in this shard; env_base = global id of the shard's first
+ *     environment (multi-GPU sharding: rank r owns [env_base, env_base + n)).
+ *
+ * State record (two SoA planes of 16-byte lanes, one lane per environment per plane):
+ *   lo[i] : int8 point counts 0..15            absolute (White) frame, +white / -black
+ *   hi[i] : int8 point counts 16..23 | u8 off_white | u8 off_black | i8 turn (+1 White, -1 Black)
+ *           | u8 flags (1 first_turn_white, 2 first_turn_black, 4 terminated)
+ *           | u16 episode_steps | u16 reserved
+ *   (replaces Narde.board/borne_off_* / first_turn_* , narde.py:21-29, + NardeEnv.current_player)
+ *
+ * Half-move encoding  : u8 from, u8 to (255 = bear off) in the MOVER's frame, as
+ *                       Narde.get_valid_moves returns them (narde.py:58-92).
+ * Turn-action encoding: u64 = 4 x u16 half-moves (from | to << 8), slot 0 played first,
+ *                       0xFFFF = unused slot.
+ */
+#ifndef NARDE_B200_H
+#define NARDE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NARDE_ABI_VERSION 1
+#define NARDE_MAX_HALF_MOVES 96 /* 4 dice x 24 points */
+
+/* narde_step_full flags */
+#define NARDE_REWARD_MOVER12 1   /* reward 1/2 to the mover (narde_env.py:134-141); default: README +1 iff WHITE wins */
+#define NARDE_AUTORESET 2        /* reset a finished environment in the same step (obs = first obs of the new game) */
+#define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
+
+/* done[] bits */
+#define NARDE_TERMINATED 1
+#define NARDE_TRUNCATED 2
+
+/* stats[] slots (int64, accumulated with atomics; caller zeroes) */
+#define NARDE_STAT_EPISODES 0
+#define NARDE_STAT_WHITE_WINS 1
+#define NARDE_STAT_BLACK_WINS 2
+#define NARDE_STAT_MARS 3
+#define NARDE_STAT_EPISODE_STEPS 4 /* sum of lengths of finished episodes */
+#define NARDE_STAT_LEGAL_ACTIONS 5 /* sum of legal turn actions over all stepped envs */
+#define NARDE_STAT_MAX_ACTIONS 6
+#define NARDE_STAT_OVERFLOWS 7
+#define NARDE_NUM_STATS 8
+
+int narde_abi_version(void);
+
+/* Which device the library was built for ("sm_100a") and a launch-free self check. */
+const char *narde_build_arch(void);
+
+/* NardeEnv.reset (narde_env.py:105-120) for n environments: fresh Narde() (narde.py:21-29) and
+ * the opening roll-off, dice from Philox4x32-10(key = seed, ctr = (env, step, 1 + attempt<<8)). */
+int narde_reset(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
+                void *stream);
+
+/* Same, but only environments with mask[i] != 0 are reset (mask may be NULL = all). */
+int narde_reset_masked(void *lo, void *hi, const uint8_t *mask, int64_t n, int64_t env_base,
+                       uint64_t seed, uint64_t step, void *stream);
+
+/* Narde.get_valid_moves(roll, current_player) (narde.py:58-92) for the player to move of each
+ * environment.  dice: [n,4] u8, 0-padded (1, 2 or 4 dice).  moves: [n,96,2] u8 in the
+ * reference's list order (die descending, point ascending, duplicates kept, head filter applied);
+ * counts: [n] i32.  player_override: 0 = use each state's turn, +1/-1 = force that perspective. */
+int narde_half_moves(const void *lo, const void *hi, const uint8_t *dice, int64_t n,
+                     int player_override, uint8_t *moves, int32_t *counts, void *stream);
+
+/* NardeEnv.step(action) (narde_env.py:27-103) with the dice supplied by the caller.
+ * dice: [n,2] u8 in roll order (the order matters: narde_env.py:77-83).  codes: [n,2] i32 action
+ * codes from*24+to.  Outputs: obs24 [n,24] i32 (narde_env.py:24-25), reward [n] i32 (0/1/2),
+ * done [n] u8 (NARDE_TERMINATED | NARDE_TRUNCATED).  max_episode_steps: 0 = no TimeLimit
+ * (gym_narde/__init__.py:6 registers 1000).  Terminated environments are left untouched. */
+int narde_step_ref(void *lo, void *hi, const uint8_t *dice, const int32_t *codes, int64_t n,
+                   int32_t max_episode_steps, int32_t *obs24, int32_t *reward, uint8_t *done,
+                   void *stream);
+
+/* README get_valid_actions(roll) (README.md:156-165) for every environment: all legal full-turn
+ * actions (max-dice rule, higher-die rule, per-turn head rule, doubles = up to 4 half-moves),
+ * de-duplicated by afterstate, in canonical order.  dice: [n,2] u8.  actions: [n,cap] u64;
+ * counts[i] = true number of legal actions (may exceed cap; then overflow[i] = 1 and only the
+ * first cap are stored).  overflow may be NULL. */
+int narde_enumerate(const void *lo, const void *hi, const uint8_t *dice, int64_t n, int32_t cap,
+                    uint64_t *actions, int32_t *counts, uint8_t *overflow, void *stream);
+
+/* One fused full-rules env step for n environments:
+ *   dice (dice_in [n,2] u8, or Philox(seed, env_base+i, step) when NULL) -> legal-turn
+ *   enumeration (written to actions/counts like narde_enumerate; actions may be NULL) -> action
+ *   choice (action_idx[i], clamped; NULL = Philox-uniform) -> apply -> termination / reward
+ *   -> player switch -> optional auto-reset -> Box(198) observation (README.md:44-102).
+ * Any of actions, counts, dice_out, obs198, reward, done, chosen, stats may be NULL. */
+int narde_step_full(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
+                    const uint8_t *dice_in, const int32_t *action_idx, int32_t cap,
+                    uint64_t *actions, int32_t *counts, uint8_t *dice_out, uint64_t *chosen,
+                    float *obs198, float *reward, uint8_t *done, int64_t *stats, int32_t flags,
+                    int32_t max_episode_steps, void *stream);
+
+/* Observations of the current states: Box(198) float32 (README.md:44-102) / the reference's
+ * mover-perspective int32[24] (narde_env.py:24-25). */
+int narde_obs198(const void *lo, const void *hi, int64_t n, float *obs198, void *stream);
+int narde_obs24(const void *lo, const void *hi, int64_t n, int32_t *obs24, void *stream);
+
+/* Apply caller-chosen turn actions (from narde_enumerate) without re-enumerating: afterstate
+ * transition + termination/reward/switch as in narde_step_full.  acts: [n] u64. */
+int narde_apply_actions(void *lo, void *hi, const uint64_t *acts, int64_t n, int32_t flags,
+                        float *reward, uint8_t *done, void *stream);
+
+/* The turn's dice for every environment from the counter-based stream the fused step uses:
+ * Philox4x32-10(key = seed, ctr = (env_base+i, step_lo, step_hi, 0)), die = 1 + ((w*6) >> 32) on
+ * words 0 and 1 (replaces np.random.randint(1,7) x2, narde_env.py:29).  dice: [n,2] u8. */
+int narde_roll_dice(int64_t n, int64_t env_base, uint64_t seed, uint64_t step, uint8_t *dice,
+                    void *stream);
+
+/* Narde._violates_block_rule(board) (narde.py:139-184) for n mover-frame boards: [n,24] int8 in,
+ * [n] u8 out. */
+int narde_violates_block_rule(const int8_t *boards, int64_t n, uint8_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -473,7 +473,8 @@ int o_full_step(o_env *e, int d1, int d2, int action_idx, int reward_mode, float
   int first_turn = player == 1 ? e->game.first_turn_white : e->game.first_turn_black;
   int mover_off = player == 1 ? e->game.borne_off_white : e->game.borne_off_black;
   int cap = 4096;
-  o_turn_action *acts = (o_turn_action *)malloc((size_t)cap * sizeof(o_turn_action));
+  static __thread o_turn_action *acts = 0; /* per-thread scratch, allocated once */
+  if (!acts) acts = (o_turn_action *)malloc((size_t)cap * sizeof(o_turn_action));
   int n = o_turn_enumerate(mover, mover_off, d1, d2, first_turn, cap, acts, 0);
   if (n > 0) {
     if (action_idx < 0) action_idx = 0;
@@ -482,7 +483,6 @@ int o_full_step(o_env *e, int d1, int d2, int action_idx, int reward_mode, float
     for (int k = 0; k < a->n_moves; k++)
       o_execute_rotated_move(&e->game, a->moves[2 * k], a->moves[2 * k + 1], player);
   }
-  free(acts);
   int32_t rew12 = 0;
   int dn = o_check_game_ended(e, &rew12);
   if (reward_mode == 1)
@@ -549,4 +549,64 @@ int o_opening_player(uint64_t seed, uint32_t env, uint64_t step) {
     }
   }
   return 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CPU baseline driver (bench.py cpu_baseline / --impl reference): full-rules random self-play of
+ * n_envs environments for n_steps lock-step turns, same Philox dice/action stream and auto-reset
+ * as the CUDA path, one Box(198) observation per env step.  Returns env steps executed.
+ * ---------------------------------------------------------------------------------------- */
+int64_t o_selfplay(uint64_t seed, uint32_t env_base, int n_envs, int n_steps, uint64_t step0,
+                   int64_t *sum_actions, int64_t *episodes, double *obs_checksum) {
+  o_env *envs = (o_env *)malloc((size_t)n_envs * sizeof(o_env));
+  float obs[198];
+  int64_t steps = 0, acts = 0, eps = 0;
+  double chk = 0.0;
+  for (int i = 0; i < n_envs; i++) {
+    o_game_init(&envs[i].game);
+    envs[i].current_player = o_opening_player(seed, env_base + (uint32_t)i, step0);
+  }
+  for (int t = 1; t <= n_steps; t++) {
+    for (int i = 0; i < n_envs; i++) {
+      int32_t d1, d2;
+      uint32_t w;
+      o_turn_dice(seed, env_base + (uint32_t)i, step0 + (uint64_t)t, &d1, &d2, &w);
+      /* count first (to map the action word to an index), then step */
+      int32_t mover[24];
+      o_env *e = &envs[i];
+      int pl = e->current_player;
+      o_get_perspective_board(&e->game, pl, mover);
+      float rew;
+      int32_t done;
+      /* o_full_step clamps the index; compute it from the count exactly like the CUDA path */
+      static __thread o_turn_action *scratch = 0;
+      if (!scratch) scratch = (o_turn_action *)malloc(4096 * sizeof(o_turn_action));
+      int n = o_turn_enumerate(mover, pl == 1 ? e->game.borne_off_white : e->game.borne_off_black, d1, d2,
+                               pl == 1 ? e->game.first_turn_white : e->game.first_turn_black, 4096, scratch, 0);
+      int idx = n ? (int)(((uint64_t)w * (uint64_t)n) >> 32) : 0;
+      if (n > 0) {
+        const o_turn_action *a = &scratch[idx];
+        for (int k = 0; k < a->n_moves; k++)
+          o_execute_rotated_move(&e->game, a->moves[2 * k], a->moves[2 * k + 1], pl);
+      }
+      int32_t r12;
+      done = o_check_game_ended(e, &r12);
+      rew = (done && pl == 1) ? 1.0f : 0.0f;
+      if (!done) e->current_player *= -1;
+      if (done) {
+        eps++;
+        o_game_init(&e->game);
+        e->current_player = o_opening_player(seed, env_base + (uint32_t)i, step0 + (uint64_t)t);
+      }
+      o_obs198(e->game.board, e->game.borne_off_white, e->game.borne_off_black, e->current_player, obs);
+      chk += obs[97] + obs[195] + rew;
+      acts += n;
+      steps++;
+    }
+  }
+  free(envs);
+  if (sum_actions) *sum_actions = acts;
+  if (episodes) *episodes = eps;
+  if (obs_checksum) *obs_checksum = chk;
+  return steps;
 }

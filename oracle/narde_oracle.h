@@ -87,6 +87,10 @@ void o_turn_dice(uint64_t seed, uint32_t env, uint64_t step, int32_t *d1, int32_
 /* opening roll-off: returns +1 (White starts) or -1 */
 int o_opening_player(uint64_t seed, uint32_t env, uint64_t step);
 
+/* CPU baseline driver: full-rules random self-play, same dice/action stream as the CUDA path. */
+int64_t o_selfplay(uint64_t seed, uint32_t env_base, int n_envs, int n_steps, uint64_t step0,
+                   int64_t *sum_actions, int64_t *episodes, double *obs_checksum);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,9 @@ def lib():
         L.o_turn_dice.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, i32p, i32p, C.POINTER(C.c_uint32)]
         L.o_opening_player.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
         L.o_opening_player.restype = C.c_int
+        L.o_selfplay.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.o_selfplay.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -225,3 +228,11 @@ def turn_dice(seed, env, step):
 
 def opening_player(seed, env, step):
     return int(lib().o_opening_player(int(seed), int(env), int(step)))
+
+
+def selfplay(seed, env_base, n_envs, n_steps, step0=0):
+    """Full-rules random self-play in C (CPU baseline).  Returns (env_steps, sum_actions, episodes)."""
+    a, e, c = C.c_int64(0), C.c_int64(0), C.c_double(0)
+    n = lib().o_selfplay(int(seed), int(env_base), int(n_envs), int(n_steps), int(step0), C.byref(a), C.byref(e),
+                         C.byref(c))
+    return int(n), int(a.value), int(e.value)

@@ -1,0 +1,138 @@
+// hostsim.cpp -- TEST-ONLY host build of the device core (gym_narde_b200/csrc/narde_core.cuh).
+//
+// The CUDA path's per-environment arithmetic is written as __host__ __device__ functions; this
+// file compiles the SAME source with g++ and wraps it in plain loops behind the C-ABI signatures
+// of include/narde_b200.h (prefix hs_, HOST pointers), so the rules logic can be checked against
+// the oracle in the GPU-less build container.  It is not a CPU fallback: the product package never
+// loads it (gym_narde_b200/_cabi.py only opens libnarde_b200.so and fails loudly without CUDA).
+#include <stdint.h>
+#include <string.h>
+
+#include "../../gym_narde_b200/csrc/narde_env.cuh"
+
+using namespace narde;
+
+static State load_state(const void* lo, const void* hi, int64_t i) {
+  State s;
+  const uint32_t* l = (const uint32_t*)lo + 4 * i;
+  const uint32_t* h = (const uint32_t*)hi + 4 * i;
+  s.w[0] = l[0]; s.w[1] = l[1]; s.w[2] = l[2]; s.w[3] = l[3];
+  s.w[4] = h[0]; s.w[5] = h[1]; s.meta = h[2]; s.aux = h[3];
+  return s;
+}
+static void store_state(void* lo, void* hi, int64_t i, const State& s) {
+  uint32_t* l = (uint32_t*)lo + 4 * i;
+  uint32_t* h = (uint32_t*)hi + 4 * i;
+  l[0] = s.w[0]; l[1] = s.w[1]; l[2] = s.w[2]; l[3] = s.w[3];
+  h[0] = s.w[4]; h[1] = s.w[5]; h[2] = s.meta; h[3] = s.aux;
+}
+
+extern "C" {
+
+int hs_reset_masked(void* lo, void* hi, const uint8_t* mask, int64_t n, int64_t env_base, uint64_t seed,
+                    uint64_t step, void*) {
+  for (int64_t i = 0; i < n; i++) {
+    if (mask && !mask[i]) continue;
+    store_state(lo, hi, i, reset_env(seed, (uint32_t)(env_base + i), step));
+  }
+  return 0;
+}
+int hs_reset(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, void* st) {
+  return hs_reset_masked(lo, hi, nullptr, n, env_base, seed, step, st);
+}
+
+int hs_half_moves(const void* lo, const void* hi, const uint8_t* dice, int64_t n, int player_override,
+                  uint8_t* moves, int32_t* counts, void*) {
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    counts[i] = half_moves_env(s, dice + 4 * i, player_override, moves + i * 96 * 2);
+  }
+  return 0;
+}
+
+int hs_step_ref(void* lo, void* hi, const uint8_t* dice, const int32_t* codes, int64_t n,
+                int32_t max_episode_steps, int32_t* o24, int32_t* reward, uint8_t* done, void*) {
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    int r, d;
+    step_ref_env(s, dice[2 * i], dice[2 * i + 1], codes[2 * i], codes[2 * i + 1], max_episode_steps, &r, &d);
+    store_state(lo, hi, i, s);
+    if (o24) obs24(s, s.turn(), o24 + 24 * i);
+    if (reward) reward[i] = r;
+    if (done) done[i] = (uint8_t)d;
+  }
+  return 0;
+}
+
+int hs_enumerate(const void* lo, const void* hi, const uint8_t* dice, int64_t n, int32_t cap, uint64_t* actions,
+                 int32_t* counts, uint8_t* overflow, void*) {
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    int c = enumerate_env(s, dice[2 * i], dice[2 * i + 1], cap, actions + i * (int64_t)cap);
+    counts[i] = c;
+    if (overflow) overflow[i] = c > cap;
+  }
+  return 0;
+}
+
+int hs_obs198(const void* lo, const void* hi, int64_t n, float* obs, void*) {
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    for (int k = 0; k < 99; k++) obs198_pair(s, k, obs + 198 * i + 2 * k, obs + 198 * i + 2 * k + 1);
+  }
+  return 0;
+}
+int hs_obs24(const void* lo, const void* hi, int64_t n, int32_t* o, void*) {
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    obs24(s, s.turn(), o + 24 * i);
+  }
+  return 0;
+}
+
+int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
+                 const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
+                 uint64_t* chosen, float* obs198, float* reward, uint8_t* done, int64_t* stats, int32_t flags,
+                 int32_t max_episode_steps, void*) {
+  StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
+                    chosen, reward, done, flags, max_episode_steps};
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    StepFullLocal L;
+    step_full_env(s, i, A, L);
+    store_state(lo, hi, i, s);
+    if (stats) {
+      stats[0] += L.finished; stats[1] += L.white_win; stats[2] += L.black_win; stats[3] += L.mars;
+      stats[4] += L.ep_len; stats[5] += L.count;
+      if (L.count > stats[6]) stats[6] = L.count;
+      stats[7] += L.overflow;
+    }
+    if (obs198)
+      for (int k = 0; k < 99; k++) obs198_pair(s, k, obs198 + 198 * i + 2 * k, obs198 + 198 * i + 2 * k + 1);
+  }
+  return 0;
+}
+
+int hs_apply_actions(void* lo, void* hi, const uint64_t* acts, int64_t n, int32_t flags, float* reward, uint8_t* done,
+                     void*) {
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    float r; int d;
+    apply_actions_env(s, acts[i], flags, &r, &d);
+    store_state(lo, hi, i, s);
+    if (reward) reward[i] = r;
+    if (done) done[i] = (uint8_t)d;
+  }
+  return 0;
+}
+
+// instrumentation for design decisions (tests/bench only)
+int hs_block_irrelevant(const void* lo, const void* hi, const uint8_t* dice, int64_t n, uint8_t* out) {
+  for (int64_t i = 0; i < n; i++) {
+    State s = load_state(lo, hi, i);
+    Pos P = decode_pos(s, s.turn());
+    out[i] = block_rule_irrelevant(P, dice[2 * i], dice[2 * i + 1]);
+  }
+  return 0;
+}
+}

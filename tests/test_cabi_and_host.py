@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library loads and exports every symbol include/narde_b200.h declares; the host
+side fails loudly without CUDA; the product never touches the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gym_narde_b200 import _cabi
+from gym_narde_b200 import state as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "narde_b200.h")).read()
+    declared = set(re.findall(r"\b(narde_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 13
+    lib = _cabi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_cabi.exported_symbols())
+    assert lib.narde_abi_version() == 1 and lib.narde_build_arch() == b"sm_100a"
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    lib = _cabi.load()
+    assert lib.narde_reset(None, None, 4, 0, 0, 0, None) == -1
+    assert lib.narde_enumerate(None, None, None, 4, 8, None, None, None, None) == -1
+    assert lib.narde_reset(None, None, -1, 0, 0, 0, None) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import gym_narde_b200
+    with pytest.raises(_cabi.NardeCudaError):
+        gym_narde_b200.make("narde-v0")
+    with pytest.raises(_cabi.NardeCudaError):
+        gym_narde_b200.VecNardeEnv(4)
+    with pytest.raises(_cabi.NardeCudaError):
+        _cabi.reset(torch.zeros((1, 16), dtype=torch.uint8), torch.zeros((1, 16), dtype=torch.uint8), 0, 0, 0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gym_narde_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("the oracle computes", "").replace("against the oracle", "") \
+                    .replace("oracle/narde_oracle.c", "") or f in ("narde_core.cuh",), (dp, f)
+                assert "hostsim" not in src or "test-only" in src or "tests/hostsim" in src, (dp, f)
+
+
+def test_state_pack_roundtrip():
+    rng = np.random.RandomState(0)
+    b = rng.randint(-15, 16, size=(50, 24))
+    lo, hi = S.pack_states(b, rng.randint(0, 16, 50), rng.randint(0, 16, 50), rng.choice([1, -1], 50),
+                           rng.rand(50) < .5, rng.rand(50) < .5, steps=rng.randint(0, 60000, 50))
+    u = S.unpack_states(lo, hi)
+    assert (u["board"] == b).all()
+    acts = [[(23, 17), (17, 11)], [(3, 'off')], [], [(5, 4), (4, 3), (3, 2), (2, 'off')]]
+    for a in acts:
+        assert S.decode_action(S.encode_action(a)) == a
