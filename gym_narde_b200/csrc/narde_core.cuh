@@ -26,6 +26,17 @@
 
 namespace narde {
 
+// Host-only work counters for design studies (tests/hostsim with -DNARDE_PROFILE); no-ops otherwise.
+#if defined(NARDE_PROFILE) && !defined(__CUDA_ARCH__)
+struct ProfCounters {
+  long long nd_env, nd_rows, nd_pairs, nd_block_env, dbl_env, dbl_nodes[4], dbl_block_env, dbl_order_search, dbl_second_pass;
+};
+extern ProfCounters g_prof;
+#define NPROF(x) (g_prof.x)
+#else
+#define NPROF(x) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // bit helpers
 // ------------------------------------------------------------------------------------------
@@ -160,8 +171,9 @@ NHD uint32_t msb4(uint32_t m) {  // bits 7,15,23,31 -> bits 0..3
 }
 
 // Decode the byte board into the mover frame of `player` (+1 / -1).
-NHD Pos decode_pos(const State& s, int player) {
-  uint32_t own16[6], ownb[6], oppb[6];
+// *ones (optional) receives the mask of points holding exactly one mover checker.
+NHD Pos decode_pos(const State& s, int player, uint32_t* ones = nullptr) {
+  uint32_t own16[6], ownb[6], oppb[6], oneb[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) {
     uint32_t w = s.w[k];
@@ -174,6 +186,11 @@ NHD Pos decode_pos(const State& s, int player) {
     own16[k] = nib16(mine);
     ownb[k] = msb4((mine + 0x7F7F7F7Fu) & 0x80808080u);
     oppb[k] = msb4((theirs + 0x7F7F7F7Fu) & 0x80808080u);
+    oneb[k] = msb4(~((mine ^ 0x01010101u) + 0x7F7F7F7Fu) & 0x80808080u);  // byte == 1
+  }
+  if (ones) {
+    uint32_t o = oneb[0] | (oneb[1] << 4) | (oneb[2] << 8) | (oneb[3] << 12) | (oneb[4] << 16) | (oneb[5] << 20);
+    *ones = player == 1 ? o : (((o >> 12) | (o << 12)) & 0xFFFFFFu);
   }
   // rotation by 12 points = 3 words (narde.py:16-17)
   Pos p;
@@ -453,7 +470,10 @@ NHD int enum_nondouble(const Pos& P, int a, int b, bool blockchk, Sink& sink) {
   uint32_t chain_present = 0;  // bit x: pair (x, x-a) was present
   uint64_t bo_present = 0;     // bit 6p+q: pair (p, q) with p, q < 6 was present
   uint32_t rows = (P.own | (S >> b)) & 0xFFFFFFu;
+  NPROF(nd_env++);
+  if (blockchk) NPROF(nd_block_env++);
   while (rows) {
+    NPROF(nd_rows++);
     int p = fls32(rows);
     rows &= ~(1u << p);
     int ta = p - a;
@@ -491,6 +511,7 @@ NHD int enum_nondouble(const Pos& P, int a, int b, bool blockchk, Sink& sink) {
     }
     uint32_t pres = m1 | m2;
     while (pres) {
+      NPROF(nd_pairs++);
       int q = fls32(pres);
       pres &= ~(1u << q);
       bool dup = false;
@@ -534,6 +555,7 @@ NHD int enum_nondouble(const Pos& P, int a, int b, bool blockchk, Sink& sink) {
 // Exhaustive ordering search (rare path).  src[0..k) sorted descending.  Finds the
 // lexicographically first legal ordering (trying higher sources first); writes it to order[].
 NHD bool dbl_order_search(const Pos& base, const int* src, int k, int d, int H, int* order) {
+  NPROF(dbl_order_search++);
   // iterative DFS over permutations, depth <= 4
   Pos st[5];
   int head[5];
@@ -599,6 +621,7 @@ struct DblLevel {
       Pos C = P;
       C.move(s, s - cx.d);
       src[K] = s;
+      NPROF(dbl_nodes[K]++);
       bool r = true, dk = true;
       uint64_t a2 = act_set(act, K, s, s - cx.d);
       if (cx.blockchk) {
@@ -649,7 +672,10 @@ NHD int enum_double(const Pos& P, int d, bool first_turn, bool blockchk, Sink& s
   cx.n = 0;
   int src[4];
   DblLevel<0, Sink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sink);
+  NPROF(dbl_env++);
+  if (blockchk) NPROF(dbl_block_env++);
   if (cx.n == 0 && cx.maxdepth > 0) {  // max-dice: fewer than 4 playable; re-emit at that depth
+    NPROF(dbl_second_pass++);
     cx.target = cx.maxdepth;
     DblLevel<0, Sink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sink);
   }

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "../../include/narde_b200.h"
+#include "narde_block.cuh"
 #include "narde_env.cuh"
 
 using namespace narde;
@@ -158,6 +159,70 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
   write_obs198_cta(sm, rows, row0, obs198);
 }
 
+// Fused full-rules step, CTA-cooperative (narde_block.cuh): the phases run with a CTA barrier
+// between them; everything between the state load and the Box(198) store stays in shared memory.
+template <int BLK>
+__global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int64_t n, StepFullArgs A, float* obs198,
+                                                      int64_t* stats) {
+  typedef BlockStep<BLK> BS;
+  __shared__ BlockShared<BLK> sh;
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * BLK;
+  const int64_t i = row0 + tid;
+  const bool valid = i < n;
+  State s;
+  if (valid) s = ld_state(lo, hi, i);
+  BS::ph_load(tid, sh, valid, s, i, A);
+  __syncthreads();
+  BS::ph_scan1(tid, sh);
+  __syncthreads();
+  BS::ph_scan2(tid, sh);
+  __syncthreads();
+  BS::ph_scan3(tid, sh);
+  BS::ph_item_bases(tid, sh);
+  __syncthreads();
+  BS::ph_rows(tid, sh);
+  __syncthreads();
+  BS::ph_nd_count(tid, sh);
+  __syncthreads();
+  BS::ph_scan1(tid, sh);
+  __syncthreads();
+  BS::ph_scan2(tid, sh);
+  __syncthreads();
+  BS::ph_scan3(tid, sh);
+  __syncthreads();
+  BS::ph_offsets(tid, sh);
+  __syncthreads();
+  BS::ph_emit(tid, sh, row0, A);
+  __syncthreads();
+  StepFullLocal L;
+  BS::ph_finish(tid, sh, valid, i, A, L);
+  if (valid) st_state(lo, hi, i, sh.st[tid]);
+  if (stats) {
+    unsigned full = 0xFFFFFFFFu;
+    int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
+    int mx = L.count, ov = L.overflow;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(full, v[k], o);
+      mx = max(mx, __shfl_xor_sync(full, mx, o));
+      ov += __shfl_xor_sync(full, ov, o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++)
+        if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
+      if (mx) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)mx);
+      if (ov) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), (unsigned long long)ov);
+    }
+  }
+  if (!obs198) return;
+  __syncthreads();
+  int rows = (int)min((int64_t)BLK, n - row0);
+  write_obs198_cta(sh.st, rows, row0, obs198);
+}
+
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {
   __shared__ State sm[kThreads];
   int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
@@ -292,7 +357,10 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.done = done;
   A.flags = flags;
   A.max_episode_steps = max_episode_steps;
-  k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
+  if (flags & NARDE_PER_THREAD_KERNEL)
+    k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
+  else
+    k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
   return launch_status();
 }
 

@@ -42,6 +42,7 @@ extern "C" {
 /* narde_step_full flags */
 #define NARDE_REWARD_MOVER12 1   /* reward 1/2 to the mover (narde_env.py:134-141); default: README +1 iff WHITE wins */
 #define NARDE_AUTORESET 2        /* reset a finished environment in the same step (obs = first obs of the new game) */
+#define NARDE_PER_THREAD_KERNEL 8 /* narde_step_full: use the thread-per-env kernel (A/B testing; same results) */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 
 /* done[] bits */

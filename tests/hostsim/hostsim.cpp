@@ -8,9 +8,15 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "../../gym_narde_b200/csrc/narde_block.cuh"
 #include "../../gym_narde_b200/csrc/narde_env.cuh"
 
 using namespace narde;
+#ifdef NARDE_PROFILE
+namespace narde { ProfCounters g_prof; }
+extern "C" void hs_prof_get(long long* out) { memcpy(out, &narde::g_prof, sizeof(narde::g_prof)); }
+extern "C" void hs_prof_reset() { memset(&narde::g_prof, 0, sizeof(narde::g_prof)); }
+#endif
 
 static State load_state(const void* lo, const void* hi, int64_t i) {
   State s;
@@ -110,6 +116,61 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
     if (obs198)
       for (int k = 0; k < 99; k++) obs198_pair(s, k, obs198 + 198 * i + 2 * k, obs198 + 198 * i + 2 * k + 1);
   }
+  return 0;
+}
+
+}  // extern "C"
+
+// CTA-cooperative step (narde_block.cuh) emulated phase by phase: every phase runs for all tids
+// of a block before the next one starts, which is what __syncthreads() guarantees on the GPU.
+template <int BLK>
+static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs& A, float* obs198, int64_t* stats) {
+  typedef BlockStep<BLK> BS;
+  static BlockShared<BLK> sh;
+  for (int64_t row0 = 0; row0 < n; row0 += BLK) {
+    for (int t = 0; t < BLK; t++) {
+      bool valid = row0 + t < n;
+      State s;
+      if (valid) s = load_state(lo, hi, row0 + t);
+      BS::ph_load(t, sh, valid, s, row0 + t, A);
+    }
+    for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
+    for (int t = 0; t < BLK; t++) { BS::ph_scan3(t, sh); BS::ph_item_bases(t, sh); }
+    for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_nd_count(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_scan3(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_offsets(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_emit(t, sh, row0, A);
+    for (int t = 0; t < BLK; t++) {
+      bool valid = row0 + t < n;
+      StepFullLocal L;
+      BS::ph_finish(t, sh, valid, row0 + t, A, L);
+      if (!valid) continue;
+      store_state(lo, hi, row0 + t, sh.st[t]);
+      if (stats) {
+        stats[0] += L.finished; stats[1] += L.white_win; stats[2] += L.black_win; stats[3] += L.mars;
+        stats[4] += L.ep_len; stats[5] += L.count;
+        if (L.count > stats[6]) stats[6] = L.count;
+        stats[7] += L.overflow;
+      }
+      if (obs198)
+        for (int k = 0; k < 99; k++)
+          obs198_pair(sh.st[t], k, obs198 + 198 * (row0 + t) + 2 * k, obs198 + 198 * (row0 + t) + 2 * k + 1);
+    }
+  }
+}
+
+extern "C" {
+int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
+                    const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
+                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, int64_t* stats, int32_t flags,
+                    int32_t max_episode_steps, void*) {
+  StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
+                    chosen, reward, done, flags, max_episode_steps};
+  step_full_v2_host<128>(lo, hi, n, A, obs198, stats);
   return 0;
 }
 

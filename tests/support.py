@@ -86,6 +86,8 @@ class HostSim:
         self.lib.hs_obs24(_p(lo), _p(hi), C.c_int64(n), _p(obs), None)
         return obs
 
+    per_thread = False  # True: the thread-per-env body (k_step_full); False: the CTA-cooperative phases
+
     def step_full(self, lo, hi, env_base=0, seed=0, step=0, dice_in=None, action_idx=None, cap=64, flags=0,
                   max_episode_steps=0, want_actions=True, want_obs=True):
         n = lo.shape[0]
@@ -103,7 +105,8 @@ class HostSim:
             "done": np.zeros(n, np.uint8),
             "stats": np.zeros(8, np.int64),
         }
-        self.lib.hs_step_full(_p(lo), _p(hi), C.c_int64(n), C.c_int64(env_base), C.c_uint64(seed), C.c_uint64(step),
+        fn = self.lib.hs_step_full if (self.per_thread or (flags & 8)) else self.lib.hs_step_full_v2
+        fn(_p(lo), _p(hi), C.c_int64(n), C.c_int64(env_base), C.c_uint64(seed), C.c_uint64(step),
                               _p(dice_in), _p(action_idx), C.c_int32(cap), _p(out["actions"]), _p(out["counts"]),
                               _p(out["dice"]), _p(out["chosen"]), _p(out["obs198"]), _p(out["reward"]),
                               _p(out["done"]), _p(out["stats"]), C.c_int32(flags), C.c_int32(max_episode_steps), None)
@@ -211,6 +214,8 @@ class CudaBackend:
         rew = t.zeros(n, dtype=t.float32, device=self.dev)
         done = t.zeros(n, dtype=t.uint8, device=self.dev)
         stats = t.zeros(8, dtype=t.int64, device=self.dev)
+        if getattr(self, "per_thread", False):
+            flags |= 8  # NARDE_PER_THREAD_KERNEL
         self.cabi.step_full(tlo, thi, env_base, seed, step,
                             dice_in=self._up(None if dice_in is None else np.asarray(dice_in, np.uint8)),
                             action_idx=self._up(None if action_idx is None else np.asarray(action_idx, np.int32)),

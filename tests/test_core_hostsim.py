@@ -69,3 +69,46 @@ def test_step_full_lockstep_mover_reward_no_autoreset(hostsim):
 def test_obs198(hostsim):
     lo, hi = P.pack_corpus(P.selfplay_corpus(10, 21))
     P.check_obs198(hostsim, lo, hi)
+
+
+def _v1_v2_equal(hostsim, lo, hi, **kw):
+    import numpy as np
+    outs = []
+    for per_thread in (True, False):
+        hostsim.per_thread = per_thread
+        l, h = lo.copy(), hi.copy()
+        o = hostsim.step_full(l, h, **kw)
+        outs.append((l, h, o))
+    hostsim.per_thread = False
+    (l1, h1, o1), (l2, h2, o2) = outs
+    assert (l1 == l2).all() and (h1 == h2).all()
+    for k in o1:
+        if o1[k] is None:
+            assert o2[k] is None
+            continue
+        if k == "actions":
+            cap = o1[k].shape[1]
+            m = np.arange(cap)[None, :] < np.minimum(o1["counts"], cap)[:, None]
+            assert (o1[k][m] == o2[k][m]).all()
+        else:
+            assert (o1[k] == o2[k]).all(), k
+    return o1
+
+
+def test_block_kernel_equals_per_thread_body(hostsim):
+    """The CTA-cooperative phases (narde_block.cuh) and the per-thread body (narde_env.cuh) must agree
+    bit for bit: synthetic block-rule-heavy boards, ragged batch sizes, given dice / given indices."""
+    import numpy as np
+    b, off, ft = P.synthetic_boards(3001, 31)
+    lo, hi, _, _ = P.pack_mover_boards(b, off, ft, 32)
+    dice = P.random_dice(3001, 33, 0.4)
+    o = _v1_v2_equal(hostsim, lo, hi, seed=5, step=9, dice_in=dice, cap=48, flags=0)
+    assert o["counts"].max() > 48
+    idx = np.random.RandomState(1).randint(-2, 80, size=3001).astype(np.int32)
+    _v1_v2_equal(hostsim, lo, hi, seed=5, step=9, dice_in=dice, action_idx=idx, cap=16, flags=1)
+    _v1_v2_equal(hostsim, lo, hi, seed=5, step=9, cap=0, flags=2, want_actions=False)
+    for n in (1, 127, 128, 129, 300):
+        _v1_v2_equal(hostsim, lo[:n].copy(), hi[:n].copy(), seed=n, step=3, cap=64, flags=2)
+    lo, hi = P.pack_corpus(P.selfplay_corpus(30, 41))
+    for step in range(1, 6):
+        _v1_v2_equal(hostsim, lo, hi, seed=77, step=step, cap=32, flags=2)

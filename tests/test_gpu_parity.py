@@ -167,3 +167,21 @@ def test_gpu_vec_env_api_and_policy_loop():
     codes = torch.randint(0, 576, (256, 2), dtype=torch.int32, device="cuda")
     obs, rew, term, trunc, info = ref.step(codes)
     assert obs.abs().sum(1).eq(30).all() and rew.dtype == torch.int32
+
+
+def test_gpu_block_kernel_equals_per_thread_kernel(cuda_backend):
+    """k_step_full_v2 (CTA-cooperative) and k_step_full (thread per env) agree bit for bit."""
+    from test_core_hostsim import _v1_v2_equal
+    b, off, ft = P.synthetic_boards(20001, 31)
+    lo, hi, _, _ = P.pack_mover_boards(b, off, ft, 32)
+    dice = P.random_dice(20001, 33, 0.4)
+    o = _v1_v2_equal(cuda_backend, lo, hi, seed=5, step=9, dice_in=dice, cap=48, flags=0)
+    assert o["counts"].max() > 48
+    idx = np.random.RandomState(1).randint(-2, 80, size=20001).astype(np.int32)
+    _v1_v2_equal(cuda_backend, lo, hi, seed=5, step=9, dice_in=dice, action_idx=idx, cap=16, flags=1)
+    _v1_v2_equal(cuda_backend, lo, hi, seed=5, step=9, cap=0, flags=2, want_actions=False)
+    for n in (1, 127, 128, 129, 300):
+        _v1_v2_equal(cuda_backend, lo[:n].copy(), hi[:n].copy(), seed=n, step=3, cap=64, flags=2)
+    lo, hi = P.pack_corpus(P.selfplay_corpus(60, 41))
+    for step in range(1, 6):
+        _v1_v2_equal(cuda_backend, lo, hi, seed=77, step=step, cap=32, flags=2)
