@@ -16,8 +16,6 @@ LIB_PATH = os.path.join(_HERE, "libnarde_b200.so")
 REWARD_MOVER12 = 1
 AUTORESET = 2
 HALF_MOVES_ONLY = 4
-TERMINATED = 1
-TRUNCATED = 2
 MAX_HALF_MOVES = 96
 NUM_STATS = 8
 STAT_NAMES = ("episodes", "white_wins", "black_wins", "mars", "episode_steps", "legal_actions",
@@ -31,10 +29,10 @@ _SIGNATURES = {
     "narde_reset": ([_vp, _vp, _i64, _i64, _u64, _u64, _vp], _int),
     "narde_reset_masked": ([_vp, _vp, _vp, _i64, _i64, _u64, _u64, _vp], _int),
     "narde_half_moves": ([_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp], _int),
-    "narde_step_ref": ([_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp], _int),
+    "narde_step_ref": ([_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_enumerate": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp], _int),
     "narde_step_full": ([_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                         _vp, _i32, _i32, _vp], _int),
+                         _vp, _vp, _i32, _i32, _vp], _int),
     "narde_obs198": ([_vp, _vp, _i64, _vp, _vp], _int),
     "narde_obs24": ([_vp, _vp, _i64, _vp, _vp], _int),
     "narde_apply_actions": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp], _int),
@@ -128,13 +126,14 @@ def half_moves(lo, hi, dice4, moves, counts, player_override=0):
     _check(rc, "narde_half_moves")
 
 
-def step_ref(lo, hi, dice, codes, obs24, reward, done, max_episode_steps=0):
+def step_ref(lo, hi, dice, codes, obs24, reward, done, max_episode_steps=0, truncated=None):
     import torch
 
     rc = load().narde_step_ref(_ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"),
                                _ptr(dice, torch.uint8, "dice"), _ptr(codes, torch.int32, "codes"), lo.shape[0],
                                max_episode_steps, _ptr(obs24, torch.int32, "obs24"),
-                               _ptr(reward, torch.int32, "reward"), _ptr(done, torch.uint8, "done"), _stream())
+                               _ptr(reward, torch.int32, "reward"), _ptr(done, torch.uint8, "done"),
+                               _ptr(truncated, torch.uint8, "truncated"), _stream())
     _check(rc, "narde_step_ref")
 
 
@@ -151,7 +150,7 @@ def enumerate_actions(lo, hi, dice, actions, counts, overflow=None):
 
 def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actions=None, counts=None,
               dice_out=None, chosen=None, obs198=None, reward=None, done=None, stats=None, flags=0,
-              max_episode_steps=0):
+              max_episode_steps=0, truncated=None):
     import torch
 
     cap = actions.shape[1] if actions is not None else 0
@@ -161,7 +160,8 @@ def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actio
         _ptr(actions, torch.int64, "actions"), _ptr(counts, torch.int32, "counts"),
         _ptr(dice_out, torch.uint8, "dice_out"), _ptr(chosen, torch.int64, "chosen"),
         _ptr(obs198, torch.float32, "obs198"), _ptr(reward, torch.float32, "reward"),
-        _ptr(done, torch.uint8, "done"), _ptr(stats, torch.int64, "stats"), flags, max_episode_steps, _stream())
+        _ptr(done, torch.uint8, "done"), _ptr(truncated, torch.uint8, "truncated"), _ptr(stats, torch.int64, "stats"),
+        flags, max_episode_steps, _stream())
     _check(rc, "narde_step_full")
 
 

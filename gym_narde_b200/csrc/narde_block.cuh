@@ -20,7 +20,7 @@
 
 namespace narde {
 
-enum : uint8_t { K_NONE = 0, K_DONE = 1, K_ND = 2, K_D = 3, K_SLOW = 4 };
+enum : uint8_t { K_NONE = 0, K_DONE = 1, K_ND = 2, K_D = 3 };
 
 template <int BLK>
 struct BlockShared {
@@ -32,7 +32,7 @@ struct BlockShared {
   uint32_t rnd[BLK];
   int32_t count[BLK];
   uint64_t chosen[BLK];
-  uint8_t a[BLK], b[BLK], kind[BLK], first[BLK], d1[BLK], d2[BLK];
+  uint8_t a[BLK], b[BLK], kind[BLK], first[BLK], d1[BLK], d2[BLK], blk[BLK];
   // item masks / bases: ND rows and doubles first sources
   uint32_t rowmask[BLK], dmask[BLK];
   uint32_t ibase[BLK + 1], dbase[BLK + 1];
@@ -145,14 +145,18 @@ struct BlockStep {
     sh.nlo0[tid] = (uint32_t)P.lo;
     sh.nlo1[tid] = (uint32_t)(P.lo >> 32);
     sh.nhi[tid] = P.hi;
-    if (!block_rule_irrelevant(P, d1, d2)) {
-      sh.kind[tid] = K_SLOW;
-      return;
-    }
+    // the 6-prime block rule can only matter for ~4% of positions; those take the exact
+    // (nibble-board) row arithmetic, everything else the mask-only fast path
+    bool blk = !block_rule_irrelevant(P, d1, d2);
+    sh.blk[tid] = blk ? 1 : 0;
     if (a != b) {
       sh.kind[tid] = K_ND;
       uint32_t Ca = cand_mask(P.own, P.opp, a, true);
       uint32_t S = cand_mask(P.own, P.opp, b, true);
+      if (blk) {
+        Ca = block_filter(P, Ca, a);
+        S = block_filter(P, S, b);
+      }
       uint32_t q_home = 0, outside = P.own & ~0x3Fu;
       if (outside == 0u) {
         q_home = S;
@@ -249,6 +253,23 @@ struct BlockStep {
       m2 &= sh.qhome[e];
     }
     if (p == 23) m2 &= ~(1u << 23);
+    if (sh.blk[e]) {  // exact path: every intermediate and final board is tested (narde.py:78-89)
+      Pos P = pos_of(sh, e);
+      m1 = 0;
+      if (sh.Ca[e] & bp) {
+        Pos P1 = P;
+        P1.move(p, ta);
+        m1 = block_filter(P1, cand_mask(P1.own, P1.opp, b, p != 23), b);
+      }
+      uint32_t keep = 0;
+      for (uint32_t mm = m2 & ~m1; mm; mm &= mm - 1) {
+        int q = ctz32(mm);
+        Pos Q = P;
+        Q.move(q, q - b);
+        if (!violates_block(after_mask(Q, p, ta), Q.opp)) keep |= 1u << q;
+      }
+      m2 = keep | (m2 & m1);
+    }
     *m1_out = m1;
     *m2_out = m2;
   }
@@ -327,6 +348,49 @@ struct BlockStep {
     }
   }
 
+  // exact (block-rule aware) variants: the sequential walker of narde_core.cuh restricted to
+  // highest source s1
+  struct OffsetSink {
+    uint64_t* slice;
+    int cap;
+    uint32_t k, idx;
+    uint64_t* chosen;
+    NHD void operator()(uint64_t a) {
+      if (slice && (int)k < cap) slice[k] = a;
+      if (k == idx) *chosen = a;
+      k++;
+    }
+  };
+  static NHD uint32_t dbl_count_exact(const Pos& P, int d, int H, int s1) {
+    DblCtx cx;
+    cx.d = d;
+    cx.H = H;
+    cx.target = 4;
+    cx.blockchk = true;
+    cx.maxdepth = 0;
+    cx.n = 0;
+    cx.first_mask = 1u << s1;
+    int src[4];
+    CountSink ck;
+    DblLevel<0, CountSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, ck);
+    return (uint32_t)cx.n;
+  }
+  static NHD void dbl_emit_exact(const Pos& P, int d, int H, int s1, uint32_t off, uint32_t cnt, uint64_t* slice, int cap,
+                                 uint32_t idx, uint64_t* chosen) {
+    if (!slice && !(idx >= off && idx < off + cnt)) return;
+    DblCtx cx;
+    cx.d = d;
+    cx.H = H;
+    cx.target = 4;
+    cx.blockchk = true;
+    cx.maxdepth = 0;
+    cx.n = 0;
+    cx.first_mask = 1u << s1;
+    int src[4];
+    OffsetSink sk = {slice, cap, off, idx, chosen};
+    DblLevel<0, OffsetSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sk);
+  }
+
   // ---- phase 3a: ND rows -> pres ; doubles items -> leaf counts --------------------------
   static NHD void ph_rows(int tid, Sh& sh) {
     int j0, j1, e, p;
@@ -344,7 +408,8 @@ struct BlockStep {
     uint32_t sum = 0;
     int j = j0;
     while (it.next(sh.dmask, &e, &p, &f, &l)) {
-      uint32_t c = dbl_count_under(pos_of(sh, e), sh.a[e], head_budget(sh, e), p);
+      uint32_t c = sh.blk[e] ? dbl_count_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), p)
+                             : dbl_count_under(pos_of(sh, e), sh.a[e], head_budget(sh, e), p);
       sh.dcnt[j < BLK * 16 ? j : 0] = c;
       sum += c;
       j++;
@@ -452,7 +517,10 @@ struct BlockStep {
       uint32_t total = sh.eEnd[e] - sh.eG[e];
       uint32_t idx = pick_index(sh, e, row0 + e, total, A);
       uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
-      dbl_emit_under(pos_of(sh, e), sh.a[e], head_budget(sh, e), p, off, cnt, slice, A.cap, idx, &sh.chosen[e]);
+      if (sh.blk[e])
+        dbl_emit_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), p, off, cnt, slice, A.cap, idx, &sh.chosen[e]);
+      else
+        dbl_emit_under(pos_of(sh, e), sh.a[e], head_budget(sh, e), p, off, cnt, slice, A.cap, idx, &sh.chosen[e]);
     }
   }
 
@@ -467,7 +535,8 @@ struct BlockStep {
       if (A.dice_out) A.dice_out[2 * i] = A.dice_out[2 * i + 1] = 0;
       if (A.chosen) A.chosen[i] = ACT_EMPTY;
       if (A.reward) A.reward[i] = 0.0f;
-      if (A.done) A.done[i] = DONE_TERMINATED;
+      if (A.done) A.done[i] = 1;
+      if (A.truncated) A.truncated[i] = 0;
       return;
     }
     State s = sh.st[tid];
@@ -476,7 +545,7 @@ struct BlockStep {
     uint64_t* slice = A.actions ? A.actions + (int64_t)i * A.cap : nullptr;
     uint32_t count = sh.eEnd[tid] - sh.eG[tid];
     uint64_t act = sh.chosen[tid];
-    bool sequential = kind == K_SLOW || (kind == K_D && count == 0);
+    bool sequential = kind == K_D && count == 0;
     if (kind == K_ND && count == 0) {
       // maximal length 1: the higher die if it can be played (narde.py:6 rule 4), else the lower
       uint32_t m = sh.Ca[tid] ? sh.Ca[tid] : sh.S[tid];
@@ -493,7 +562,7 @@ struct BlockStep {
         k++;
       }
     } else if (sequential) {
-      // block rule may matter, or a doubles turn that cannot use all four dice: exact per-thread walk
+      // a doubles turn that cannot use all four dice (~3% of turns): exact per-thread walk
       Pos P = pos_of(sh, tid);
       bool ft = sh.first[tid] != 0;
       // dice order is irrelevant to enumerate_turn (it sorts); a >= b
@@ -545,7 +614,8 @@ struct BlockStep {
     }
     if (A.chosen) A.chosen[i] = count ? act : ACT_EMPTY;
     if (A.reward) A.reward[i] = rew;
-    if (A.done) A.done[i] = (uint8_t)bits;
+    if (A.done) A.done[i] = (bits & DONE_TERMINATED) ? 1 : 0;
+    if (A.truncated) A.truncated[i] = (bits & DONE_TRUNCATED) ? 1 : 0;
   }
 };
 

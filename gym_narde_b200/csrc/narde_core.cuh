@@ -608,6 +608,7 @@ struct DblCtx {
   bool blockchk;
   int maxdepth;
   int n;
+  uint32_t first_mask;  // restricts the highest source (level 0) -- lets callers split the tree
 };
 
 template <int K, class Sink>
@@ -615,6 +616,7 @@ struct DblLevel {
   static NHD void run(const Pos& base, const Pos& P, DblCtx& cx, int head_used, int last, bool reach,
                       bool desc_ok, uint64_t act, int* src, Sink& sink) {
     uint32_t m = cand_mask(P.own, P.opp, cx.d, head_used < cx.H) & ((2u << last) - 1u);
+    if (K == 0) m &= cx.first_mask;
     while (m) {
       int s = fls32(m);
       m &= ~(1u << s);
@@ -670,6 +672,7 @@ NHD int enum_double(const Pos& P, int d, bool first_turn, bool blockchk, Sink& s
   cx.target = 4;
   cx.maxdepth = 0;
   cx.n = 0;
+  cx.first_mask = 0xFFFFFFu;
   int src[4];
   DblLevel<0, Sink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sink);
   NPROF(dbl_env++);
@@ -753,6 +756,25 @@ NHD void finish_turn(State& s, int player, int reward_mode, float* reward, int* 
   s.set_steps(s.steps() + 1);
 }
 
+// off / 15 as float32, bit-identical to numpy's np.float32(off / 15.0): the 16 possible values are
+// rounded once from double by the host compiler (no fp64 arithmetic on the device).
+#define NARDE_OFF15_TABLE                                                                                   \
+  {(float)(0.0 / 15.0),  (float)(1.0 / 15.0),  (float)(2.0 / 15.0),  (float)(3.0 / 15.0),  (float)(4.0 / 15.0),  \
+   (float)(5.0 / 15.0),  (float)(6.0 / 15.0),  (float)(7.0 / 15.0),  (float)(8.0 / 15.0),  (float)(9.0 / 15.0),  \
+   (float)(10.0 / 15.0), (float)(11.0 / 15.0), (float)(12.0 / 15.0), (float)(13.0 / 15.0), (float)(14.0 / 15.0), \
+   (float)(15.0 / 15.0)}
+#if defined(__CUDACC__)
+__device__ __constant__ float c_off15[16] = NARDE_OFF15_TABLE;
+#endif
+NHD float off15(int n) {
+#if defined(__CUDA_ARCH__)
+  return c_off15[n & 15];
+#else
+  const float t[16] = NARDE_OFF15_TABLE;
+  return t[n & 15];
+#endif
+}
+
 // README.md:44-102: one float2 of the 99 that make an env's Box(198) row.
 //   k in [0,48): WHITE point k/2, half k%2;  k == 48: (bar, off)   ; k in [49,97): BLACK
 //   k == 97: BLACK (bar, off) ; k == 98: turn one-hot
@@ -767,7 +789,7 @@ NHD void obs198_pair(const State& s, int k, float* x, float* y) {
   if (kk == 48) {
     int off = colour ? s.off_b() : s.off_w();
     *x = 0.0f;                              // bar / 2: no hitting in Narde (narde.py:71)
-    *y = (float)((double)off / 15.0);       // exactly np.float32(off / 15.0)
+    *y = off15(off);                        // exactly np.float32(off / 15.0)
     return;
   }
   int v = s.point(kk >> 1);

@@ -69,7 +69,8 @@ struct StepFullArgs {
   uint8_t* dice_out;
   uint64_t* chosen;
   float* reward;
-  uint8_t* done;
+  uint8_t* done;       // terminated (0/1)
+  uint8_t* truncated;  // TimeLimit hit without termination (0/1), may be NULL
   int flags;
   int max_episode_steps;
 };
@@ -88,7 +89,8 @@ NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal
     if (A.dice_out) A.dice_out[2 * i] = A.dice_out[2 * i + 1] = 0;
     if (A.chosen) A.chosen[i] = ACT_EMPTY;
     if (A.reward) A.reward[i] = 0.0f;
-    if (A.done) A.done[i] = DONE_TERMINATED;
+    if (A.done) A.done[i] = 1;
+    if (A.truncated) A.truncated[i] = 0;
     return;
   }
   U4 rnd = turn_random(A.seed, env, A.step);
@@ -160,7 +162,8 @@ NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal
   }
   if (A.chosen) A.chosen[i] = act;
   if (A.reward) A.reward[i] = rew;
-  if (A.done) A.done[i] = (uint8_t)bits;
+  if (A.done) A.done[i] = (bits & DONE_TERMINATED) ? 1 : 0;
+  if (A.truncated) A.truncated[i] = (bits & DONE_TRUNCATED) ? 1 : 0;
 }
 
 // ---- narde_enumerate body -------------------------------------------------------------------

@@ -29,36 +29,49 @@ __device__ __forceinline__ void st_state(uint4* __restrict__ lo, uint4* __restri
   hi[i] = make_uint4(s.w[4], s.w[5], s.meta, s.aux);
 }
 
-// CTA-cooperative Box(198) writer: sm[] holds the CTA's states, rows [row0, row0+rows).
-__device__ __forceinline__ void write_obs198_cta(const State* sm, int rows, int64_t row0, float* __restrict__ obs) {
+// CTA-cooperative Box(198) writer (README.md:44-102).  sm[] holds the CTA's states, rows
+// [row0, row0+rows).  Work item = (env, point): one board byte gives the WHITE and the BLACK
+// 4-float encodings of that point through a 16-entry shared-memory table (n -> [n>=1, n>=2, n>=3,
+// (n-3)/2]); rows are 792 B, so 8-byte stores are always aligned.  lut must be filled
+// (obs_lut_init) and the CTA synchronised before the call.
+__device__ __forceinline__ void obs_lut_init(float4* lut) {
+  if (threadIdx.x < 16) {
+    int n = threadIdx.x;
+    lut[n] = make_float4(n >= 1 ? 1.0f : 0.0f, n >= 2 ? 1.0f : 0.0f, n >= 3 ? 1.0f : 0.0f,
+                         n > 3 ? (float)(n - 3) * 0.5f : 0.0f);
+  }
+}
+__device__ __forceinline__ void write_obs198_cta(const State* sm, const float4* lut, int rows, int64_t row0,
+                                                 float* __restrict__ obs) {
   float* base = obs + row0 * 198;
-  const int pairs = rows * 99;
-  if ((((uintptr_t)base) & 15u) == 0) {
-    // 16-byte lanes: two (x,y) pairs per store; pairs never straddle more than two rows
-    float4* b4 = reinterpret_cast<float4*>(base);
-    const int quads = pairs >> 1;
-    for (int g = threadIdx.x; g < quads; g += blockDim.x) {
-      int p0 = 2 * g, p1 = p0 + 1;
-      int e0 = p0 / 99, e1 = p1 / 99;
-      float4 v;
-      obs198_pair(sm[e0], p0 - e0 * 99, &v.x, &v.y);
-      obs198_pair(sm[e1], p1 - e1 * 99, &v.z, &v.w);
-      b4[g] = v;
+  const int items = rows * 24;
+  for (int g = threadIdx.x; g < items; g += blockDim.x) {
+    int e = g / 24, pt = g - e * 24;
+    int v = sm[e].point(pt);
+    float4 fw = lut[v > 0 ? v : 0], fb = lut[v < 0 ? -v : 0];
+    float2* pw = reinterpret_cast<float2*>(base + e * 198 + 4 * pt);
+    float2* pb = reinterpret_cast<float2*>(base + e * 198 + 98 + 4 * pt);
+    pw[0] = make_float2(fw.x, fw.y);
+    pw[1] = make_float2(fw.z, fw.w);
+    pb[0] = make_float2(fb.x, fb.y);
+    pb[1] = make_float2(fb.z, fb.w);
+  }
+  for (int g = threadIdx.x; g < rows * 3; g += blockDim.x) {
+    int e = g / 3, k = g - e * 3;
+    const State& s = sm[e];
+    float2 v;
+    int at;
+    if (k == 0) {  // WHITE bar (always empty: no hitting, narde.py:71) and off / 15
+      v = make_float2(0.0f, off15(s.off_w()));
+      at = 96;
+    } else if (k == 1) {
+      v = make_float2(0.0f, off15(s.off_b()));
+      at = 194;
+    } else {
+      v = s.turn() == 1 ? make_float2(1.0f, 0.0f) : make_float2(0.0f, 1.0f);
+      at = 196;
     }
-    if ((pairs & 1) && threadIdx.x == 0) {
-      int p = pairs - 1, e = p / 99;
-      float2 v;
-      obs198_pair(sm[e], p - e * 99, &v.x, &v.y);
-      reinterpret_cast<float2*>(base)[p] = v;
-    }
-  } else {
-    float2* b2 = reinterpret_cast<float2*>(base);
-    for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
-      int e = p / 99;
-      float2 v;
-      obs198_pair(sm[e], p - e * 99, &v.x, &v.y);
-      b2[p] = v;
-    }
+    *reinterpret_cast<float2*>(base + e * 198 + at) = v;
   }
 }
 
@@ -81,7 +94,8 @@ __global__ void __launch_bounds__(kThreads) k_half_moves(const uint4* lo, const 
 }
 
 __global__ void __launch_bounds__(kThreads) k_step_ref(uint4* lo, uint4* hi, const uint8_t* dice, const int32_t* codes, int64_t n,
-                                                      int max_episode_steps, int32_t* o24, int32_t* reward, uint8_t* done) {
+                                                      int max_episode_steps, int32_t* o24, int32_t* reward, uint8_t* done,
+                                                      uint8_t* truncated) {
   __shared__ State sm[kThreads];
   int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
   int64_t i = row0 + threadIdx.x;
@@ -93,7 +107,8 @@ __global__ void __launch_bounds__(kThreads) k_step_ref(uint4* lo, uint4* hi, con
     step_ref_env(s, d2 & 0xFF, d2 >> 8, c.x, c.y, max_episode_steps, &r, &dn);
     st_state(lo, hi, i, s);
     if (reward) reward[i] = r;
-    if (done) done[i] = (uint8_t)dn;
+    if (done) done[i] = (dn & DONE_TERMINATED) ? 1 : 0;
+    if (truncated) truncated[i] = (dn & DONE_TRUNCATED) ? 1 : 0;
     sm[threadIdx.x] = s;
   }
   if (!o24) return;
@@ -154,10 +169,20 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
     }
   }
   if (!obs198) return;
+  __shared__ float4 lut[16];
+  obs_lut_init(lut);
   __syncthreads();
   int rows = (int)min((int64_t)blockDim.x, n - row0);
-  write_obs198_cta(sm, rows, row0, obs198);
+  write_obs198_cta(sm, lut, rows, row0, obs198);
 }
+
+// Debug aid: per-CTA phase timestamps (clock64) when a buffer was registered through
+// narde_debug_set_clock_buffer; [block][16] u64.  Not part of the public ABI.
+__device__ unsigned long long* g_dbg_clk = nullptr;
+#define PHASE_MARK(k)                                                                  \
+  do {                                                                                 \
+    if (g_dbg_clk && threadIdx.x == 0) g_dbg_clk[(size_t)blockIdx.x * 16 + (k)] = clock64(); \
+  } while (0)
 
 // Fused full-rules step, CTA-cooperative (narde_block.cuh): the phases run with a CTA barrier
 // between them; everything between the state load and the Box(198) store stays in shared memory.
@@ -171,9 +196,11 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   const int64_t i = row0 + tid;
   const bool valid = i < n;
   State s;
+  PHASE_MARK(0);
   if (valid) s = ld_state(lo, hi, i);
   BS::ph_load(tid, sh, valid, s, i, A);
   __syncthreads();
+  PHASE_MARK(1);
   BS::ph_scan1(tid, sh);
   __syncthreads();
   BS::ph_scan2(tid, sh);
@@ -181,10 +208,13 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_scan3(tid, sh);
   BS::ph_item_bases(tid, sh);
   __syncthreads();
+  PHASE_MARK(2);
   BS::ph_rows(tid, sh);
   __syncthreads();
+  PHASE_MARK(3);
   BS::ph_nd_count(tid, sh);
   __syncthreads();
+  PHASE_MARK(4);
   BS::ph_scan1(tid, sh);
   __syncthreads();
   BS::ph_scan2(tid, sh);
@@ -193,10 +223,14 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   __syncthreads();
   BS::ph_offsets(tid, sh);
   __syncthreads();
+  PHASE_MARK(5);
   BS::ph_emit(tid, sh, row0, A);
   __syncthreads();
+  PHASE_MARK(6);
   StepFullLocal L;
   BS::ph_finish(tid, sh, valid, i, A, L);
+  __syncthreads();
+  PHASE_MARK(7);
   if (valid) st_state(lo, hi, i, sh.st[tid]);
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
@@ -218,19 +252,25 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
     }
   }
   if (!obs198) return;
+  __shared__ float4 lut[16];
+  obs_lut_init(lut);
   __syncthreads();
   int rows = (int)min((int64_t)BLK, n - row0);
-  write_obs198_cta(sh.st, rows, row0, obs198);
+  write_obs198_cta(sh.st, lut, rows, row0, obs198);
+  __syncthreads();
+  PHASE_MARK(8);
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {
   __shared__ State sm[kThreads];
   int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
   int64_t i = row0 + threadIdx.x;
+  __shared__ float4 lut[16];
+  obs_lut_init(lut);
   if (i < n) sm[threadIdx.x] = ld_state(lo, hi, i);
   __syncthreads();
   int rows = (int)min((int64_t)blockDim.x, n - row0);
-  write_obs198_cta(sm, rows, row0, obs198);
+  write_obs198_cta(sm, lut, rows, row0, obs198);
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs24(const uint4* lo, const uint4* hi, int64_t n, int32_t* o24) {
@@ -314,12 +354,12 @@ int narde_half_moves(const void* lo, const void* hi, const uint8_t* dice, int64_
 }
 
 int narde_step_ref(void* lo, void* hi, const uint8_t* dice, const int32_t* codes, int64_t n, int32_t max_episode_steps,
-                   int32_t* obs24, int32_t* reward, uint8_t* done, void* stream) {
+                   int32_t* obs24, int32_t* reward, uint8_t* done, uint8_t* truncated, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || !lo || !hi || !dice || !codes || !aligned16(lo) || !aligned16(hi)) return -1;
   if ((((uintptr_t)dice) & 1u) != 0 || (((uintptr_t)codes) & 7u) != 0) return -1;
   k_step_ref<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, dice, codes, n,
-                                                                 max_episode_steps, obs24, reward, done);
+                                                                 max_episode_steps, obs24, reward, done, truncated);
   return launch_status();
 }
 
@@ -336,8 +376,8 @@ int narde_enumerate(const void* lo, const void* hi, const uint8_t* dice, int64_t
 
 int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
                     const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
-                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, int64_t* stats, int32_t flags,
-                    int32_t max_episode_steps, void* stream) {
+                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
+                    int32_t flags, int32_t max_episode_steps, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || cap < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
   if (obs198 && (((uintptr_t)obs198) & 7u) != 0) return -1;
@@ -355,6 +395,7 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.chosen = chosen;
   A.reward = reward;
   A.done = done;
+  A.truncated = truncated;
   A.flags = flags;
   A.max_episode_steps = max_episode_steps;
   if (flags & NARDE_PER_THREAD_KERNEL)
@@ -398,6 +439,11 @@ int narde_violates_block_rule(const int8_t* boards, int64_t n, uint8_t* out, voi
   if (n < 0 || !boards || !out) return -1;
   k_block_rule<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(boards, n, out);
   return launch_status();
+}
+
+int narde_debug_set_clock_buffer(void* devptr) {
+  unsigned long long* p = (unsigned long long*)devptr;
+  return (int)cudaMemcpyToSymbol(g_dbg_clk, &p, sizeof(p));
 }
 
 }  // extern "C"

@@ -128,7 +128,7 @@ class NardeEnv(_Base):
         self.current_player = int(u["turn"][0])
         obs = dev.obs24.cpu().numpy()[0].astype(np.int32)
         reward = int(dev.rew_i.cpu()[0])
-        done = bool(int(dev.done.cpu()[0]) & _cabi.TERMINATED)
+        done = bool(int(dev.done.cpu()[0]))
         self.last_roll = tuple(dice)
         return obs, reward, done, False, {}
 
@@ -171,7 +171,7 @@ class NardeEnv(_Base):
         self.current_player = int(u["turn"][0])
         self.last_roll = None
         obs = dev.obs198.cpu().numpy()[0].copy()
-        return obs, float(dev.rew_f.cpu()[0]), bool(int(dev.done.cpu()[0]) & _cabi.TERMINATED), False, {}
+        return obs, float(dev.rew_f.cpu()[0]), bool(int(dev.done.cpu()[0])), False, {}
 
     # ---- misc (narde_env.py:122-141) -----------------------------------------------------
     def render(self):

@@ -43,8 +43,13 @@ class VecNardeEnv:
         self.chosen = torch.zeros(n, dtype=torch.int64, device=dev)
         self.actions = torch.zeros((n, self.max_actions), dtype=torch.int64, device=dev)
         self.overflow = torch.zeros(n, dtype=torch.uint8, device=dev)
-        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)        # terminated (0/1)
+        self.trunc = torch.zeros(n, dtype=torch.uint8, device=dev)       # truncated (0/1)
+        # zero-copy bool views: step() launches exactly one kernel and no torch ops
+        self.terminated = self.done.view(torch.bool)
+        self.truncated = self.trunc.view(torch.bool)
         self.stats = torch.zeros(_cabi.NUM_STATS, dtype=torch.int64, device=dev)
+        self.info = {"dice": self.dice, "counts": self.counts, "chosen": self.chosen}
         if rules == "full":
             self.obs = torch.zeros((n, 198), dtype=torch.float32, device=dev)
             self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -108,7 +113,7 @@ class VecNardeEnv:
                             action_idx=actions, actions=self.actions if self.write_actions else None,
                             counts=self.counts, dice_out=self.dice, chosen=self.chosen, obs198=self.obs,
                             reward=self.reward, done=self.done, stats=self.stats, flags=flags,
-                            max_episode_steps=self.max_episode_steps)
+                            max_episode_steps=self.max_episode_steps, truncated=self.trunc)
         else:
             if actions is None:
                 raise ValueError("rules='reference' needs action codes [N,2]")
@@ -116,11 +121,8 @@ class VecNardeEnv:
                 _cabi.roll_dice(self.dice, self.env_base, self.seed, self.step_count)
                 dice = self.dice
             _cabi.step_ref(self.lo, self.hi, dice, actions, self.obs, self.reward, self.done,
-                           max_episode_steps=self.max_episode_steps)
-        terminated = (self.done & _cabi.TERMINATED) != 0
-        truncated = (self.done & _cabi.TRUNCATED) != 0
-        info = {"dice": self.dice, "counts": self.counts, "chosen": self.chosen}
-        return self.obs, self.reward, terminated, truncated, info
+                           max_episode_steps=self.max_episode_steps, truncated=self.trunc)
+        return self.obs, self.reward, self.terminated, self.truncated, self.info
 
     def episode_stats(self):
         """Device-side counters as a dict (one D2H copy)."""

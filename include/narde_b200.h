@@ -45,9 +45,8 @@ extern "C" {
 #define NARDE_PER_THREAD_KERNEL 8 /* narde_step_full: use the thread-per-env kernel (A/B testing; same results) */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 
-/* done[] bits */
-#define NARDE_TERMINATED 1
-#define NARDE_TRUNCATED 2
+/* done[i] = 1 when the episode terminated (a player bore off 15 checkers); truncated[i] = 1 when
+ * max_episode_steps was reached without termination (gymnasium TimeLimit semantics). */
 
 /* stats[] slots (int64, accumulated with atomics; caller zeroes) */
 #define NARDE_STAT_EPISODES 0
@@ -84,11 +83,11 @@ int narde_half_moves(const void *lo, const void *hi, const uint8_t *dice, int64_
 /* NardeEnv.step(action) (narde_env.py:27-103) with the dice supplied by the caller.
  * dice: [n,2] u8 in roll order (the order matters: narde_env.py:77-83).  codes: [n,2] i32 action
  * codes from*24+to.  Outputs: obs24 [n,24] i32 (narde_env.py:24-25), reward [n] i32 (0/1/2),
- * done [n] u8 (NARDE_TERMINATED | NARDE_TRUNCATED).  max_episode_steps: 0 = no TimeLimit
+ * done [n] u8 (terminated), truncated [n] u8 (may be NULL).  max_episode_steps: 0 = no TimeLimit
  * (gym_narde/__init__.py:6 registers 1000).  Terminated environments are left untouched. */
 int narde_step_ref(void *lo, void *hi, const uint8_t *dice, const int32_t *codes, int64_t n,
                    int32_t max_episode_steps, int32_t *obs24, int32_t *reward, uint8_t *done,
-                   void *stream);
+                   uint8_t *truncated, void *stream);
 
 /* README get_valid_actions(roll) (README.md:156-165) for every environment: all legal full-turn
  * actions (max-dice rule, higher-die rule, per-turn head rule, doubles = up to 4 half-moves),
@@ -103,12 +102,12 @@ int narde_enumerate(const void *lo, const void *hi, const uint8_t *dice, int64_t
  *   enumeration (written to actions/counts like narde_enumerate; actions may be NULL) -> action
  *   choice (action_idx[i], clamped; NULL = Philox-uniform) -> apply -> termination / reward
  *   -> player switch -> optional auto-reset -> Box(198) observation (README.md:44-102).
- * Any of actions, counts, dice_out, obs198, reward, done, chosen, stats may be NULL. */
+ * Any of actions, counts, dice_out, obs198, reward, done, truncated, chosen, stats may be NULL. */
 int narde_step_full(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
                     const uint8_t *dice_in, const int32_t *action_idx, int32_t cap,
                     uint64_t *actions, int32_t *counts, uint8_t *dice_out, uint64_t *chosen,
-                    float *obs198, float *reward, uint8_t *done, int64_t *stats, int32_t flags,
-                    int32_t max_episode_steps, void *stream);
+                    float *obs198, float *reward, uint8_t *done, uint8_t *truncated, int64_t *stats,
+                    int32_t flags, int32_t max_episode_steps, void *stream);
 
 /* Observations of the current states: Box(198) float32 (README.md:44-102) / the reference's
  * mover-perspective int32[24] (narde_env.py:24-25). */

@@ -57,7 +57,7 @@ int hs_half_moves(const void* lo, const void* hi, const uint8_t* dice, int64_t n
 }
 
 int hs_step_ref(void* lo, void* hi, const uint8_t* dice, const int32_t* codes, int64_t n,
-                int32_t max_episode_steps, int32_t* o24, int32_t* reward, uint8_t* done, void*) {
+                int32_t max_episode_steps, int32_t* o24, int32_t* reward, uint8_t* done, uint8_t* truncated, void*) {
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
     int r, d;
@@ -65,7 +65,8 @@ int hs_step_ref(void* lo, void* hi, const uint8_t* dice, const int32_t* codes, i
     store_state(lo, hi, i, s);
     if (o24) obs24(s, s.turn(), o24 + 24 * i);
     if (reward) reward[i] = r;
-    if (done) done[i] = (uint8_t)d;
+    if (done) done[i] = (d & DONE_TERMINATED) ? 1 : 0;
+    if (truncated) truncated[i] = (d & DONE_TRUNCATED) ? 1 : 0;
   }
   return 0;
 }
@@ -98,10 +99,10 @@ int hs_obs24(const void* lo, const void* hi, int64_t n, int32_t* o, void*) {
 
 int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
                  const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
-                 uint64_t* chosen, float* obs198, float* reward, uint8_t* done, int64_t* stats, int32_t flags,
-                 int32_t max_episode_steps, void*) {
+                 uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
+                 int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
-                    chosen, reward, done, flags, max_episode_steps};
+                    chosen, reward, done, truncated, flags, max_episode_steps};
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
     StepFullLocal L;
@@ -166,10 +167,10 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
 extern "C" {
 int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
                     const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
-                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, int64_t* stats, int32_t flags,
-                    int32_t max_episode_steps, void*) {
+                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
+                    int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
-                    chosen, reward, done, flags, max_episode_steps};
+                    chosen, reward, done, truncated, flags, max_episode_steps};
   step_full_v2_host<128>(lo, hi, n, A, obs198, stats);
   return 0;
 }

@@ -61,7 +61,7 @@ class HostSim:
         rew = np.zeros(n, np.int32)
         done = np.zeros(n, np.uint8)
         self.lib.hs_step_ref(_p(lo), _p(hi), _p(dice), _p(codes), C.c_int64(n), C.c_int32(max_episode_steps),
-                             _p(obs), _p(rew), _p(done), None)
+                             _p(obs), _p(rew), _p(done), None, None)
         return obs, rew, done
 
     def enumerate(self, lo, hi, dice, cap):
@@ -103,13 +103,14 @@ class HostSim:
             "obs198": np.zeros((n, 198), np.float32) if want_obs else None,
             "reward": np.zeros(n, np.float32),
             "done": np.zeros(n, np.uint8),
+            "trunc": np.zeros(n, np.uint8),
             "stats": np.zeros(8, np.int64),
         }
         fn = self.lib.hs_step_full if (self.per_thread or (flags & 8)) else self.lib.hs_step_full_v2
         fn(_p(lo), _p(hi), C.c_int64(n), C.c_int64(env_base), C.c_uint64(seed), C.c_uint64(step),
                               _p(dice_in), _p(action_idx), C.c_int32(cap), _p(out["actions"]), _p(out["counts"]),
                               _p(out["dice"]), _p(out["chosen"]), _p(out["obs198"]), _p(out["reward"]),
-                              _p(out["done"]), _p(out["stats"]), C.c_int32(flags), C.c_int32(max_episode_steps), None)
+                              _p(out["done"]), _p(out["trunc"]), _p(out["stats"]), C.c_int32(flags), C.c_int32(max_episode_steps), None)
         return out
 
     def apply_actions(self, lo, hi, acts, flags=0):
@@ -214,20 +215,21 @@ class CudaBackend:
         rew = t.zeros(n, dtype=t.float32, device=self.dev)
         done = t.zeros(n, dtype=t.uint8, device=self.dev)
         stats = t.zeros(8, dtype=t.int64, device=self.dev)
+        trunc = t.zeros(n, dtype=t.uint8, device=self.dev)
         if getattr(self, "per_thread", False):
             flags |= 8  # NARDE_PER_THREAD_KERNEL
         self.cabi.step_full(tlo, thi, env_base, seed, step,
                             dice_in=self._up(None if dice_in is None else np.asarray(dice_in, np.uint8)),
                             action_idx=self._up(None if action_idx is None else np.asarray(action_idx, np.int32)),
                             actions=actions, counts=counts, dice_out=dice, chosen=chosen, obs198=obs, reward=rew,
-                            done=done, stats=stats, flags=flags, max_episode_steps=max_episode_steps)
+                            done=done, stats=stats, flags=flags, max_episode_steps=max_episode_steps, truncated=trunc)
         self._sync_back(lo, hi, tlo, thi)
         return {
             "actions": actions.cpu().numpy().view(np.uint64) if want_actions else None,
             "counts": counts.cpu().numpy(), "dice": dice.cpu().numpy(),
             "chosen": chosen.cpu().numpy().view(np.uint64),
             "obs198": obs.cpu().numpy() if want_obs else None, "reward": rew.cpu().numpy(),
-            "done": done.cpu().numpy(), "stats": stats.cpu().numpy(),
+            "done": done.cpu().numpy(), "trunc": trunc.cpu().numpy(), "stats": stats.cpu().numpy(),
         }
 
     def apply_actions(self, lo, hi, acts, flags=0):
