@@ -3,24 +3,42 @@
 // One CTA of BLK threads owns BLK environments.  Instead of one thread walking one environment's
 // whole move tree (badly divergent: doubles vs non-doubles, 1 vs 1000 legal turns), the CTA
 // flattens the enumeration into uniform work items that are dealt out evenly to its threads:
-//   non-doubles : item = (env, p)  = "source p plays the higher die"      (~9 per env)
-//   doubles     : item = (env, s1) = "highest source played is s1"        (~4 per env)
+//   non-doubles : item = (env, p)       "source p plays the higher die"            (~9 per env)
+//   doubles     : item = (env, s1, s2)  "the two highest sources played"           (~7 per env)
 // Items are counted, prefix-summed in shared memory, and every thread takes a contiguous chunk of
-// ceil(items / BLK).  Legal-action counts per item are prefix-summed again to give every item its
-// slot in the env's canonical action list, so the list is written in order without sorting.
-// Environments for which the 6-prime block rule could matter (~4%) and doubles turns that cannot
-// use all four dice (~3%) take the sequential per-thread path of narde_core.cuh.
+// ceil(items / BLK).  Legal-action counts per chunk / per env are prefix-summed again to give
+// every item its slot in the env's canonical action list, so the list is written in order
+// without sorting.  Positions where the 6-prime block rule could matter (~4%) run the exact
+// (board-testing) arithmetic inside the same items; only doubles turns that cannot use all four
+// dice (~3%) fall back to a sequential per-thread walk.
 //
 // The code is written as PHASES: plain functions of (tid, shared block state) that only read what
-// earlier phases wrote.  The kernel runs them with __syncthreads() in between; the test-only host
-// harness runs "for tid in 0..BLK" per phase, which is the same thing, so this file is verified
-// against the oracle on the CPU before it reaches the GPU.
+// earlier phases wrote (shared-memory atomics aside).  The kernel runs them with __syncthreads()
+// in between; the test-only host harness runs "for tid in 0..BLK" per phase, which is the same
+// thing, so this file is verified against the oracle on the CPU before it reaches the GPU.
 #pragma once
 #include "narde_env.cuh"
 
 namespace narde {
 
 enum : uint8_t { K_NONE = 0, K_DONE = 1, K_ND = 2, K_D = 3 };
+
+NHD void sm_add(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+NHD void sm_max(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  atomicMax(p, v);
+#else
+  if (v > *p) *p = v;
+#endif
+}
+
+constexpr int kL1Cap = 1024;  // level-1 doubles items a CTA can hold (128 envs x <= 15 sources, never reached)
 
 template <int BLK>
 struct BlockShared {
@@ -30,31 +48,33 @@ struct BlockShared {
   uint32_t nlo0[BLK], nlo1[BLK], nhi[BLK];
   uint32_t Ca[BLK], S[BLK], qhome[BLK];  // non-doubles: candidates of die a, die b; "q makes all home"
   uint32_t rnd[BLK];
-  int32_t count[BLK];
   uint64_t chosen[BLK];
   uint8_t a[BLK], b[BLK], kind[BLK], first[BLK], d1[BLK], d2[BLK], blk[BLK];
-  // item masks / bases: ND rows and doubles first sources
+  uint32_t maxd[BLK];                    // doubles: deepest playable level seen
+  uint32_t etotal[BLK], ebase[BLK];      // legal actions of the env / start of its list in item space
+  // work items: ND rows, doubles level-1 sources, doubles level-2 sources
   uint32_t rowmask[BLK], dmask[BLK];
   uint32_t ibase[BLK + 1], dbase[BLK + 1];
-  uint32_t pres[BLK * 24];   // ND: pairs (p, q) legal in some order, one mask per row
-  uint8_t icnt[BLK * 24];    // ND: de-duplicated pairs per row
-  uint32_t dcnt[BLK * 16];   // doubles: 4-move leaves under each first source
-  uint32_t eG[BLK], eEnd[BLK];
-  // scan scratch
-  uint32_t partA[BLK], partB[BLK], baseA[BLK], baseB[BLK];
-  uint32_t wsA[40], wsB[40];
+  uint32_t pres[BLK * 24];               // ND: pairs (p, q) legal in some order, one mask per row
+  uint32_t d2mask[kL1Cap];
+  uint32_t d2base[kL1Cap + 1];
+  uint8_t l1env[kL1Cap], l1src[kL1Cap];
+  uint32_t n_l1;
+  // scan scratch (4 lanes)
+  uint32_t part[4][BLK], base[4][BLK], ws[4][36];
 };
 
-struct ItemIter {  // items (env e, bit p) over masks[e], envs ascending, bits descending
+template <class BaseT>
+struct ItemIter {  // items (parent e, bit p) over masks[e], parents ascending, bits descending
   int e, j, j1;
   uint32_t rem;
-  NHD void init(const uint32_t* masks, const uint32_t* base, int nenv, int j0, int j1_) {
+  NHD void init(const uint32_t* masks, const BaseT* base, int nparent, int j0, int j1_) {
     j = j0;
     j1 = j1_;
     e = 0;
     rem = 0;
     if (j >= j1) return;
-    int lo = 0, hi = nenv - 1;
+    int lo = 0, hi = nparent - 1;
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
       if ((int)base[mid] <= j0)
@@ -66,16 +86,14 @@ struct ItemIter {  // items (env e, bit p) over masks[e], envs ascending, bits d
     rem = masks[e];
     for (int k = j0 - (int)base[e]; k > 0; k--) rem &= ~(1u << fls32(rem));
   }
-  NHD bool next(const uint32_t* masks, int* eo, int* po, bool* first, bool* last) {
+  NHD bool next(const uint32_t* masks, int* eo, int* po) {
     if (j >= j1) return false;
     while (rem == 0u) {
       e++;
       rem = masks[e];
     }
-    *first = rem == masks[e];
     int p = fls32(rem);
     rem &= ~(1u << p);
-    *last = rem == 0u;
     *eo = e;
     *po = p;
     j++;
@@ -98,19 +116,24 @@ struct BlockStep {
   }
   static NHD int head_budget(const Sh& sh, int e) {
     int d = sh.a[e];
-    return (sh.first[e] && (d == 3 || d == 4 || d == 6)) ? 2 : 1;
+    return (sh.first[e] && (d == 3 || d == 4 || d == 6)) ? 2 : 1;  // narde.py:100-103, per turn
+  }
+  static NHD void chunk(int total, int tid, int* j0, int* j1) {
+    int c = (total + BLK - 1) / BLK;
+    int a = tid * c, b = a + c;
+    *j0 = a < total ? a : total;
+    *j1 = b < total ? b : total;
   }
 
   // ---- phase 1: load, dice, decode, classify, item masks --------------------------------
   static NHD void ph_load(int tid, Sh& sh, bool valid, const State& s_in, int64_t i, const StepFullArgs& A) {
-    sh.partA[tid] = 0;
-    sh.partB[tid] = 0;
+    for (int l = 0; l < 4; l++) sh.part[l][tid] = 0;
     sh.rowmask[tid] = 0;
     sh.dmask[tid] = 0;
-    sh.count[tid] = 0;
     sh.chosen[tid] = ACT_EMPTY;
-    sh.eG[tid] = 0;
-    sh.eEnd[tid] = 0;
+    sh.etotal[tid] = 0;
+    sh.ebase[tid] = 0;
+    sh.maxd[tid] = 0;
     sh.kind[tid] = K_NONE;
     if (!valid) return;
     sh.st[tid] = s_in;
@@ -146,7 +169,7 @@ struct BlockStep {
     sh.nlo1[tid] = (uint32_t)(P.lo >> 32);
     sh.nhi[tid] = P.hi;
     // the 6-prime block rule can only matter for ~4% of positions; those take the exact
-    // (nibble-board) row arithmetic, everything else the mask-only fast path
+    // (nibble-board) arithmetic, everything else the mask-only fast path
     bool blk = !block_rule_irrelevant(P, d1, d2);
     sh.blk[tid] = blk ? 1 : 0;
     if (a != b) {
@@ -169,68 +192,57 @@ struct BlockStep {
       sh.qhome[tid] = q_home;
       uint32_t rows = (P.own | (S >> b)) & 0xFFFFFFu;
       sh.rowmask[tid] = rows;
-      sh.partA[tid] = (uint32_t)popc32(rows);
+      sh.part[0][tid] = (uint32_t)popc32(rows);
     } else {
       sh.kind[tid] = K_D;
       uint32_t m = cand_mask(P.own, P.opp, a, true);
       sh.dmask[tid] = m;
-      sh.partB[tid] = (uint32_t)popc32(m);
+      sh.part[1][tid] = (uint32_t)popc32(m);
     }
   }
 
-  // ---- block exclusive scan of partA / partB (3 phases) ----------------------------------
+  // ---- block exclusive scan of part[l] -> base[l], totals in ws[l][32] (3 phases) ---------
   static NHD void ph_scan1(int tid, Sh& sh) {
     if (tid < 32) {
-      uint32_t sa = 0, sb = 0;
-      for (int k = 0; k < PER; k++) {
-        sa += sh.partA[tid * PER + k];
-        sb += sh.partB[tid * PER + k];
+      for (int l = 0; l < 4; l++) {
+        uint32_t s = 0;
+        for (int k = 0; k < PER; k++) s += sh.part[l][tid * PER + k];
+        sh.ws[l][tid] = s;
       }
-      sh.wsA[tid] = sa;
-      sh.wsB[tid] = sb;
     }
   }
   static NHD void ph_scan2(int tid, Sh& sh) {
-    if (tid == 0) {
-      uint32_t ra = 0, rb = 0;
+    if (tid < 4) {
+      uint32_t r = 0;
       for (int k = 0; k < 32; k++) {
-        uint32_t ta = sh.wsA[k], tb = sh.wsB[k];
-        sh.wsA[k] = ra;
-        sh.wsB[k] = rb;
-        ra += ta;
-        rb += tb;
+        uint32_t t = sh.ws[tid][k];
+        sh.ws[tid][k] = r;
+        r += t;
       }
-      sh.wsA[32] = ra;
-      sh.wsB[32] = rb;
+      sh.ws[tid][32] = r;
     }
   }
   static NHD void ph_scan3(int tid, Sh& sh) {
     int g = tid / PER;
-    uint32_t ra = sh.wsA[g], rb = sh.wsB[g];
-    for (int k = g * PER; k < tid; k++) {
-      ra += sh.partA[k];
-      rb += sh.partB[k];
+    for (int l = 0; l < 4; l++) {
+      uint32_t r = sh.ws[l][g];
+      for (int k = g * PER; k < tid; k++) r += sh.part[l][k];
+      sh.base[l][tid] = r;
     }
-    sh.baseA[tid] = ra;
-    sh.baseB[tid] = rb;
   }
-  // after the first scan: bases of the item lists
+  // after the first scan: bases of the ND row items and of the doubles level-1 items
   static NHD void ph_item_bases(int tid, Sh& sh) {
-    sh.ibase[tid] = sh.baseA[tid];
-    sh.dbase[tid] = sh.baseB[tid];
+    sh.ibase[tid] = sh.base[0][tid];
+    sh.dbase[tid] = sh.base[1][tid];
     if (tid == 0) {
-      sh.ibase[BLK] = sh.wsA[32];
-      sh.dbase[BLK] = sh.wsB[32];
+      sh.ibase[BLK] = sh.ws[0][32];
+      sh.dbase[BLK] = sh.ws[1][32];
+      uint32_t n1 = sh.ws[1][32];
+      sh.n_l1 = n1 <= (uint32_t)kL1Cap ? n1 : 0u;  // overflow: doubles envs fall back to the sequential walk
     }
-  }
-  static NHD void chunk(int total, int tid, int* j0, int* j1) {
-    int c = (total + BLK - 1) / BLK;
-    int a = tid * c, b = a + c;
-    *j0 = a < total ? a : total;
-    *j1 = b < total ? b : total;
   }
 
-  // ---- non-doubles row arithmetic (masks only; the block rule is known not to matter) -----
+  // ---- non-doubles row arithmetic -----------------------------------------------------------
   static NHD void nd_row(const Sh& sh, int e, int p, uint32_t* m1_out, uint32_t* m2_out) {
     uint32_t own = sh.own[e], opp = sh.opp[e], ones = sh.ones[e], S = sh.S[e];
     int a = sh.a[e], b = sh.b[e];
@@ -285,71 +297,55 @@ struct BlockStep {
     return dup;
   }
 
-  // ---- doubles sub-tree below (s1): count 4-move leaves --------------------------------
-  static NHD uint32_t dbl_count_under(const Pos& P, int d, int H, int s1) {
-    Pos P1 = P;
-    P1.move(s1, s1 - d);
-    int h1 = s1 == 23;
+  // ---- doubles sub-tree below the two highest sources (s1 >= s2) ----------------------------
+  // fast variant (block rule irrelevant): count the 4-move leaves; *deep = 3 if a third move exists
+  static NHD uint32_t dbl_count2(const Pos& P, int d, int H, int s1, int s2, uint32_t* deep) {
+    Pos P2 = P;
+    P2.move(s1, s1 - d);
+    P2.move(s2, s2 - d);
+    int h2 = (s1 == 23) + (s2 == 23);
     uint32_t leaves = 0;
-    uint32_t m2 = cand_mask(P1.own, P1.opp, d, h1 < H) & ((2u << s1) - 1u);
-    while (m2) {
-      int s2 = fls32(m2);
-      m2 &= ~(1u << s2);
-      Pos P2 = P1;
-      P2.move(s2, s2 - d);
-      int h2 = h1 + (s2 == 23);
-      uint32_t m3 = cand_mask(P2.own, P2.opp, d, h2 < H) & ((2u << s2) - 1u);
-      while (m3) {
-        int s3 = fls32(m3);
-        m3 &= ~(1u << s3);
-        Pos P3 = P2;
-        P3.move(s3, s3 - d);
-        int h3 = h2 + (s3 == 23);
-        leaves += (uint32_t)popc32(cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u));
-      }
+    uint32_t m3 = cand_mask(P2.own, P2.opp, d, h2 < H) & ((2u << s2) - 1u);
+    *deep = m3 ? 3u : 2u;
+    while (m3) {
+      int s3 = fls32(m3);
+      m3 &= ~(1u << s3);
+      Pos P3 = P2;
+      P3.move(s3, s3 - d);
+      int h3 = h2 + (s3 == 23);
+      leaves += (uint32_t)popc32(cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u));
     }
     return leaves;
   }
-  // emit the leaves below s1 at list positions off, off+1, ...; capture the idx-th
-  static NHD void dbl_emit_under(const Pos& P, int d, int H, int s1, uint32_t off, uint32_t cnt, uint64_t* slice, int cap,
-                                 uint32_t idx, uint64_t* chosen) {
-    if (!slice && !(idx >= off && idx < off + cnt)) return;
-    Pos P1 = P;
-    P1.move(s1, s1 - d);
-    int h1 = s1 == 23;
-    uint64_t a1 = act_set(ACT_EMPTY, 0, s1, s1 - d);
+  static NHD uint32_t dbl_emit2(const Pos& P, int d, int H, int s1, int s2, uint32_t off, uint64_t* slice, int cap,
+                                uint32_t idx, uint64_t* chosen) {
+    Pos P2 = P;
+    P2.move(s1, s1 - d);
+    P2.move(s2, s2 - d);
+    int h2 = (s1 == 23) + (s2 == 23);
+    uint64_t a2 = act_set(act_set(ACT_EMPTY, 0, s1, s1 - d), 1, s2, s2 - d);
     uint32_t k = off;
-    uint32_t m2 = cand_mask(P1.own, P1.opp, d, h1 < H) & ((2u << s1) - 1u);
-    while (m2) {
-      int s2 = fls32(m2);
-      m2 &= ~(1u << s2);
-      Pos P2 = P1;
-      P2.move(s2, s2 - d);
-      int h2 = h1 + (s2 == 23);
-      uint64_t a2 = act_set(a1, 1, s2, s2 - d);
-      uint32_t m3 = cand_mask(P2.own, P2.opp, d, h2 < H) & ((2u << s2) - 1u);
-      while (m3) {
-        int s3 = fls32(m3);
-        m3 &= ~(1u << s3);
-        Pos P3 = P2;
-        P3.move(s3, s3 - d);
-        int h3 = h2 + (s3 == 23);
-        uint64_t a3 = act_set(a2, 2, s3, s3 - d);
-        uint32_t m4 = cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u);
-        while (m4) {
-          int s4 = fls32(m4);
-          m4 &= ~(1u << s4);
-          uint64_t a4 = act_set(a3, 3, s4, s4 - d);
-          if (slice && (int)k < cap) slice[k] = a4;
-          if (k == idx) *chosen = a4;
-          k++;
-        }
+    uint32_t m3 = cand_mask(P2.own, P2.opp, d, h2 < H) & ((2u << s2) - 1u);
+    while (m3) {
+      int s3 = fls32(m3);
+      m3 &= ~(1u << s3);
+      Pos P3 = P2;
+      P3.move(s3, s3 - d);
+      int h3 = h2 + (s3 == 23);
+      uint64_t a3 = act_set(a2, 2, s3, s3 - d);
+      uint32_t m4 = cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u);
+      while (m4) {
+        int s4 = fls32(m4);
+        m4 &= ~(1u << s4);
+        uint64_t a4 = act_set(a3, 3, s4, s4 - d);
+        if (slice && (int)k < cap) slice[k] = a4;
+        if (k == idx) *chosen = a4;
+        k++;
       }
     }
+    return k - off;
   }
-
-  // exact (block-rule aware) variants: the sequential walker of narde_core.cuh restricted to
-  // highest source s1
+  // exact variants: the block-rule aware sequential walker of narde_core.cuh restricted to (s1, s2)
   struct OffsetSink {
     uint64_t* slice;
     int cap;
@@ -361,7 +357,7 @@ struct BlockStep {
       k++;
     }
   };
-  static NHD uint32_t dbl_count_exact(const Pos& P, int d, int H, int s1) {
+  static NHD DblCtx exact_ctx(int d, int H, int s1, int s2) {
     DblCtx cx;
     cx.d = d;
     cx.H = H;
@@ -370,90 +366,108 @@ struct BlockStep {
     cx.maxdepth = 0;
     cx.n = 0;
     cx.first_mask = 1u << s1;
+    cx.second_mask = 1u << s2;
+    return cx;
+  }
+  static NHD uint32_t dbl_count2_exact(const Pos& P, int d, int H, int s1, int s2) {
+    DblCtx cx = exact_ctx(d, H, s1, s2);
     int src[4];
     CountSink ck;
     DblLevel<0, CountSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, ck);
     return (uint32_t)cx.n;
   }
-  static NHD void dbl_emit_exact(const Pos& P, int d, int H, int s1, uint32_t off, uint32_t cnt, uint64_t* slice, int cap,
-                                 uint32_t idx, uint64_t* chosen) {
-    if (!slice && !(idx >= off && idx < off + cnt)) return;
-    DblCtx cx;
-    cx.d = d;
-    cx.H = H;
-    cx.target = 4;
-    cx.blockchk = true;
-    cx.maxdepth = 0;
-    cx.n = 0;
-    cx.first_mask = 1u << s1;
+  static NHD void dbl_emit2_exact(const Pos& P, int d, int H, int s1, int s2, uint32_t off, uint64_t* slice, int cap,
+                                  uint32_t idx, uint64_t* chosen) {
+    DblCtx cx = exact_ctx(d, H, s1, s2);
     int src[4];
     OffsetSink sk = {slice, cap, off, idx, chosen};
     DblLevel<0, OffsetSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sk);
   }
 
-  // ---- phase 3a: ND rows -> pres ; doubles items -> leaf counts --------------------------
+  // ---- phase 3: ND rows -> pres ; doubles level-1 items -> second-source masks -------------
   static NHD void ph_rows(int tid, Sh& sh) {
     int j0, j1, e, p;
-    bool f, l;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    ItemIter it;
+    ItemIter<uint32_t> it;
     it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
-    while (it.next(sh.rowmask, &e, &p, &f, &l)) {
+    while (it.next(sh.rowmask, &e, &p)) {
       uint32_t m1, m2;
       nd_row(sh, e, p, &m1, &m2);
       sh.pres[e * 24 + p] = m1 | m2;
     }
-    chunk((int)sh.dbase[BLK], tid, &j0, &j1);
+    chunk((int)sh.n_l1, tid, &j0, &j1);
     it.init(sh.dmask, sh.dbase, BLK, j0, j1);
     uint32_t sum = 0;
     int j = j0;
-    while (it.next(sh.dmask, &e, &p, &f, &l)) {
-      uint32_t c = sh.blk[e] ? dbl_count_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), p)
-                             : dbl_count_under(pos_of(sh, e), sh.a[e], head_budget(sh, e), p);
-      sh.dcnt[j < BLK * 16 ? j : 0] = c;
-      sum += c;
+    while (it.next(sh.dmask, &e, &p)) {
+      int d = sh.a[e];
+      Pos P1 = pos_of(sh, e);
+      P1.move(p, p - d);
+      uint32_t m2 = cand_mask(P1.own, P1.opp, d, (p == 23) < head_budget(sh, e)) & ((2u << p) - 1u);
+      sh.d2mask[j] = m2;
+      sh.l1env[j] = (uint8_t)e;
+      sh.l1src[j] = (uint8_t)p;
+      if (!sh.blk[e]) sm_max(&sh.maxd[e], m2 ? 2u : 1u);
+      sum += (uint32_t)popc32(m2);
       j++;
     }
-    sh.partB[tid] = sum;
+    sh.part[1][tid] = sum;
   }
-  // ---- phase 3b: ND de-duplicated counts -------------------------------------------------
-  static NHD void ph_nd_count(int tid, Sh& sh) {
+  // after the scan of level-2 counts: per level-1 item bases
+  static NHD void ph_l2_bases(int tid, Sh& sh) {
+    int j0, j1;
+    chunk((int)sh.n_l1, tid, &j0, &j1);
+    uint32_t r = sh.base[1][tid];
+    for (int j = j0; j < j1; j++) {
+      sh.d2base[j] = r;
+      r += (uint32_t)popc32(sh.d2mask[j]);
+    }
+    if (tid == 0) sh.d2base[sh.n_l1] = sh.ws[1][32];
+  }
+  // ---- phase 5: counts per item -> chunk sums (lanes 0/1) and per-env totals ----------------
+  static NHD void ph_count(int tid, Sh& sh) {
     int j0, j1, e, p;
-    bool f, l;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    ItemIter it;
+    ItemIter<uint32_t> it;
     it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
     uint32_t sum = 0;
-    while (it.next(sh.rowmask, &e, &p, &f, &l)) {
+    while (it.next(sh.rowmask, &e, &p)) {
       uint32_t c = (uint32_t)popc32(sh.pres[e * 24 + p] & ~nd_dups(sh, e, p));
-      sh.icnt[e * 24 + p] = (uint8_t)c;
+      if (c) sm_add(&sh.etotal[e], c);
       sum += c;
     }
-    sh.partA[tid] = sum;
+    sh.part[0][tid] = sum;
+    int n1 = (int)sh.n_l1;
+    sum = 0;
+    if (n1 > 0) {
+      chunk((int)sh.d2base[n1], tid, &j0, &j1);
+      it.init(sh.d2mask, sh.d2base, n1, j0, j1);
+      int j;
+      while (it.next(sh.d2mask, &j, &p)) {
+        e = sh.l1env[j];
+        int s1 = sh.l1src[j];
+        uint32_t c;
+        if (sh.blk[e]) {
+          c = dbl_count2_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p);
+        } else {
+          uint32_t deep;
+          c = dbl_count2(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p, &deep);
+          if (c == 0) sm_max(&sh.maxd[e], deep);
+        }
+        if (c) sm_add(&sh.etotal[e], c);
+        sum += c;
+      }
+    }
+    sh.part[1][tid] = sum;
   }
-  // ---- phase 5: per-env list bounds from the scanned item counts --------------------------
-  static NHD void ph_offsets(int tid, Sh& sh) {
-    int j0, j1, e, p;
-    bool f, l;
-    chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    ItemIter it;
-    it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
-    uint32_t G = sh.baseA[tid];
-    while (it.next(sh.rowmask, &e, &p, &f, &l)) {
-      if (f) sh.eG[e] = G;
-      G += sh.icnt[e * 24 + p];
-      if (l) sh.eEnd[e] = G;
-    }
-    chunk((int)sh.dbase[BLK], tid, &j0, &j1);
-    it.init(sh.dmask, sh.dbase, BLK, j0, j1);
-    G = sh.baseB[tid];
-    int j = j0;
-    while (it.next(sh.dmask, &e, &p, &f, &l)) {
-      if (f) sh.eG[e] = G;
-      G += sh.dcnt[j < BLK * 16 ? j : 0];
-      if (l) sh.eEnd[e] = G;
-      j++;
-    }
+  // per-env totals into scan lanes 2 (ND) / 3 (doubles): list starts in item space
+  static NHD void ph_env_totals(int tid, Sh& sh) {
+    uint8_t k = sh.kind[tid];
+    sh.part[2][tid] = k == K_ND ? sh.etotal[tid] : 0u;
+    sh.part[3][tid] = k == K_D ? sh.etotal[tid] : 0u;
+  }
+  static NHD void ph_env_bases(int tid, Sh& sh) {
+    sh.ebase[tid] = sh.kind[tid] == K_ND ? sh.base[2][tid] : sh.base[3][tid];
   }
   static NHD uint32_t pick_index(const Sh& sh, int e, int64_t i, uint32_t count, const StepFullArgs& A) {
     if (count == 0) return 0;
@@ -465,27 +479,25 @@ struct BlockStep {
     }
     return mulhi32(sh.rnd[e], count);
   }
-  // ---- phase 6: write the action lists in canonical order, capture the chosen action ------
+  // ---- phase 7: write the action lists in canonical order, capture the chosen action ------
   static NHD void ph_emit(int tid, Sh& sh, int64_t row0, const StepFullArgs& A) {
     int j0, j1, e, p;
-    bool f, l;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    ItemIter it;
+    ItemIter<uint32_t> it;
     it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
-    uint32_t G = sh.baseA[tid];
-    while (it.next(sh.rowmask, &e, &p, &f, &l)) {
-      uint32_t cnt = sh.icnt[e * 24 + p];
-      uint32_t off = G - sh.eG[e];
+    uint32_t G = sh.base[0][tid];
+    while (it.next(sh.rowmask, &e, &p)) {
+      uint32_t nd = sh.pres[e * 24 + p] & ~nd_dups(sh, e, p);
+      uint32_t cnt = (uint32_t)popc32(nd);
+      uint32_t off = G - sh.ebase[e];
       G += cnt;
       if (cnt == 0) continue;
-      uint32_t total = sh.eEnd[e] - sh.eG[e];
-      uint32_t idx = pick_index(sh, e, row0 + e, total, A);
+      uint32_t idx = pick_index(sh, e, row0 + e, sh.etotal[e], A);
       uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
       bool want = idx >= off && idx < off + cnt;
-      if (!slice && !want) continue;
+      if (!want && (!slice || (int)off >= A.cap)) continue;
       uint32_t m1, m2;
       nd_row(sh, e, p, &m1, &m2);
-      uint32_t nd = sh.pres[e * 24 + p] & ~nd_dups(sh, e, p);
       int a = sh.a[e], b = sh.b[e], ta = p - a;
       uint32_t k = off;
       while (nd) {
@@ -504,27 +516,50 @@ struct BlockStep {
         k++;
       }
     }
-    chunk((int)sh.dbase[BLK], tid, &j0, &j1);
-    it.init(sh.dmask, sh.dbase, BLK, j0, j1);
-    G = sh.baseB[tid];
-    int j = j0;
-    while (it.next(sh.dmask, &e, &p, &f, &l)) {
-      uint32_t cnt = sh.dcnt[j < BLK * 16 ? j : 0];
-      uint32_t off = G - sh.eG[e];
-      G += cnt;
-      j++;
-      if (cnt == 0) continue;
-      uint32_t total = sh.eEnd[e] - sh.eG[e];
-      uint32_t idx = pick_index(sh, e, row0 + e, total, A);
-      uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
-      if (sh.blk[e])
-        dbl_emit_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), p, off, cnt, slice, A.cap, idx, &sh.chosen[e]);
-      else
-        dbl_emit_under(pos_of(sh, e), sh.a[e], head_budget(sh, e), p, off, cnt, slice, A.cap, idx, &sh.chosen[e]);
+    int n1 = (int)sh.n_l1;
+    if (n1 > 0) {
+      chunk((int)sh.d2base[n1], tid, &j0, &j1);
+      it.init(sh.d2mask, sh.d2base, n1, j0, j1);
+      G = sh.base[1][tid];
+      int j;
+      while (it.next(sh.d2mask, &j, &p)) {
+        e = sh.l1env[j];
+        int s1 = sh.l1src[j];
+        uint32_t total = sh.etotal[e];
+        if (total == 0) continue;  // cannot use four dice: sequential walk in ph_finish
+        uint32_t idx = pick_index(sh, e, row0 + e, total, A);
+        uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
+        uint32_t off = G - sh.ebase[e];
+        Pos P = pos_of(sh, e);
+        int d = sh.a[e], H = head_budget(sh, e);
+        bool store = slice && (int)off < A.cap;
+        bool exact = sh.blk[e] != 0;
+        if (store) {
+          if (exact) {
+            OffsetSink sk = {slice, A.cap, off, idx, &sh.chosen[e]};
+            DblCtx cx = exact_ctx(d, H, s1, p);
+            int src[4];
+            DblLevel<0, OffsetSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sk);
+            G += (uint32_t)cx.n;
+          } else {
+            G += dbl_emit2(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
+          }
+        } else {  // nothing to store: count, and walk again only if the chosen index is inside
+          uint32_t deep;
+          uint32_t cnt = exact ? dbl_count2_exact(P, d, H, s1, p) : dbl_count2(P, d, H, s1, p, &deep);
+          G += cnt;
+          if (idx >= off && idx < off + cnt) {
+            if (exact)
+              dbl_emit2_exact(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
+            else
+              dbl_emit2(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
+          }
+        }
+      }
     }
   }
 
-  // ---- phase 7: per-env completion: rare sequential cases, apply, outputs ------------------
+  // ---- phase 8: per-env completion: rare sequential cases, apply, outputs ------------------
   static NHD void ph_finish(int tid, Sh& sh, bool valid, int64_t i, const StepFullArgs& A, StepFullLocal& L) {
     L.count = 0;
     L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
@@ -543,9 +578,8 @@ struct BlockStep {
     int player = s.turn();
     int a = sh.a[tid], b = sh.b[tid];
     uint64_t* slice = A.actions ? A.actions + (int64_t)i * A.cap : nullptr;
-    uint32_t count = sh.eEnd[tid] - sh.eG[tid];
+    uint32_t count = sh.etotal[tid];
     uint64_t act = sh.chosen[tid];
-    bool sequential = kind == K_D && count == 0;
     if (kind == K_ND && count == 0) {
       // maximal length 1: the higher die if it can be played (narde.py:6 rule 4), else the lower
       uint32_t m = sh.Ca[tid] ? sh.Ca[tid] : sh.S[tid];
@@ -561,17 +595,22 @@ struct BlockStep {
         if (k == idx) act = one;
         k++;
       }
-    } else if (sequential) {
-      // a doubles turn that cannot use all four dice (~3% of turns): exact per-thread walk
+    } else if (kind == K_D && count == 0) {
+      // a doubles turn that cannot use all four dice (~3% of turns): per-thread walk of a small tree
       Pos P = pos_of(sh, tid);
       bool ft = sh.first[tid] != 0;
-      // dice order is irrelevant to enumerate_turn (it sorts); a >= b
-      if (slice) {
+      int target = (int)sh.maxd[tid];
+      bool known = !sh.blk[tid] && sh.n_l1 > 0;  // depth found by the item phases (fast path only)
+      if (known && target == 0) {
+        count = 0;
+      } else if (slice) {
         StoreSink sk = {slice, A.cap, 1, 0};
-        count = (uint32_t)enumerate_turn(P, a, b, ft, sk);
+        count = known ? (uint32_t)enum_double_at(P, a, head_budget(sh, tid), target, sk)
+                      : (uint32_t)enumerate_turn(P, a, b, ft, sk);
       } else {
         CountSink ck;
-        count = (uint32_t)enumerate_turn(P, a, b, ft, ck);
+        count = known ? (uint32_t)enum_double_at(P, a, head_budget(sh, tid), target, ck)
+                      : (uint32_t)enumerate_turn(P, a, b, ft, ck);
       }
       act = ACT_EMPTY;
       if (count) {
@@ -580,7 +619,10 @@ struct BlockStep {
           act = slice[idx];
         } else {
           PickSink pk = {(int)idx, 0, ACT_EMPTY};
-          enumerate_turn(P, a, b, ft, pk);
+          if (known)
+            enum_double_at(P, a, head_budget(sh, tid), target, pk);
+          else
+            enumerate_turn(P, a, b, ft, pk);
           act = pk.picked;
         }
       }
@@ -608,9 +650,8 @@ struct BlockStep {
     sh.st[tid] = s;
     if (A.counts) A.counts[i] = (int32_t)count;
     if (A.dice_out) {
-      int d1 = sh.d1[tid], d2 = sh.d2[tid];  // roll order
-      A.dice_out[2 * i] = (uint8_t)d1;
-      A.dice_out[2 * i + 1] = (uint8_t)d2;
+      A.dice_out[2 * i] = sh.d1[tid];  // roll order
+      A.dice_out[2 * i + 1] = sh.d2[tid];
     }
     if (A.chosen) A.chosen[i] = count ? act : ACT_EMPTY;
     if (A.reward) A.reward[i] = rew;

@@ -608,7 +608,8 @@ struct DblCtx {
   bool blockchk;
   int maxdepth;
   int n;
-  uint32_t first_mask;  // restricts the highest source (level 0) -- lets callers split the tree
+  uint32_t first_mask;   // restricts the highest source (level 0) -- lets callers split the tree
+  uint32_t second_mask;  // restricts the second source (level 1)
 };
 
 template <int K, class Sink>
@@ -617,6 +618,7 @@ struct DblLevel {
                       bool desc_ok, uint64_t act, int* src, Sink& sink) {
     uint32_t m = cand_mask(P.own, P.opp, cx.d, head_used < cx.H) & ((2u << last) - 1u);
     if (K == 0) m &= cx.first_mask;
+    if (K == 1) m &= cx.second_mask;
     while (m) {
       int s = fls32(m);
       m &= ~(1u << s);
@@ -673,6 +675,7 @@ NHD int enum_double(const Pos& P, int d, bool first_turn, bool blockchk, Sink& s
   cx.maxdepth = 0;
   cx.n = 0;
   cx.first_mask = 0xFFFFFFu;
+  cx.second_mask = 0xFFFFFFu;
   int src[4];
   DblLevel<0, Sink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sink);
   NPROF(dbl_env++);
@@ -683,6 +686,24 @@ NHD int enum_double(const Pos& P, int d, bool first_turn, bool blockchk, Sink& s
     DblLevel<0, Sink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sink);
   }
   *depth_out = cx.n ? cx.target : 0;
+  return cx.n;
+}
+
+// Same walk when the number of playable dice (`target`, 1..4) is already known and the block rule
+// cannot matter: one pass, emitting the depth-`target` multisets.
+template <class Sink>
+NHD int enum_double_at(const Pos& P, int d, int H, int target, Sink& sink) {
+  DblCtx cx;
+  cx.d = d;
+  cx.H = H;
+  cx.blockchk = false;
+  cx.target = target;
+  cx.maxdepth = 0;
+  cx.n = 0;
+  cx.first_mask = 0xFFFFFFu;
+  cx.second_mask = 0xFFFFFFu;
+  int src[4];
+  DblLevel<0, Sink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sink);
   return cx.n;
 }
 

@@ -212,25 +212,34 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_rows(tid, sh);
   __syncthreads();
   PHASE_MARK(3);
-  BS::ph_nd_count(tid, sh);
-  __syncthreads();
-  PHASE_MARK(4);
   BS::ph_scan1(tid, sh);
   __syncthreads();
   BS::ph_scan2(tid, sh);
   __syncthreads();
   BS::ph_scan3(tid, sh);
+  BS::ph_l2_bases(tid, sh);
   __syncthreads();
-  BS::ph_offsets(tid, sh);
+  PHASE_MARK(4);
+  BS::ph_count(tid, sh);
   __syncthreads();
   PHASE_MARK(5);
-  BS::ph_emit(tid, sh, row0, A);
+  BS::ph_env_totals(tid, sh);
+  __syncthreads();
+  BS::ph_scan1(tid, sh);
+  __syncthreads();
+  BS::ph_scan2(tid, sh);
+  __syncthreads();
+  BS::ph_scan3(tid, sh);
+  BS::ph_env_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(6);
+  BS::ph_emit(tid, sh, row0, A);
+  __syncthreads();
+  PHASE_MARK(7);
   StepFullLocal L;
   BS::ph_finish(tid, sh, valid, i, A, L);
   __syncthreads();
-  PHASE_MARK(7);
+  PHASE_MARK(8);
   if (valid) st_state(lo, hi, i, sh.st[tid]);
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   int rows = (int)min((int64_t)BLK, n - row0);
   write_obs198_cta(sh.st, lut, rows, row0, obs198);
   __syncthreads();
-  PHASE_MARK(8);
+  PHASE_MARK(9);
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {

@@ -135,15 +135,20 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
       if (valid) s = load_state(lo, hi, row0 + t);
       BS::ph_load(t, sh, valid, s, row0 + t, A);
     }
+    // NOTE: phases fused between two barriers on the GPU are emulated in DESCENDING tid order as
+    // well as ascending elsewhere, so that a read-after-write hazard inside a fused pair shows up
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
-    for (int t = 0; t < BLK; t++) { BS::ph_scan3(t, sh); BS::ph_item_bases(t, sh); }
+    for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_item_bases(t, sh); }
     for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_nd_count(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_scan3(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_offsets(t, sh);
+    for (int t = 0; t < BLK; t++) { BS::ph_scan3(t, sh); BS::ph_l2_bases(t, sh); }
+    for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_env_totals(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
+    for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_env_bases(t, sh); }
     for (int t = 0; t < BLK; t++) BS::ph_emit(t, sh, row0, A);
     for (int t = 0; t < BLK; t++) {
       bool valid = row0 + t < n;
