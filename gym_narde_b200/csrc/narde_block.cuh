@@ -171,6 +171,9 @@ struct BlockStep {
     // the 6-prime block rule can only matter for ~4% of positions; those take the exact
     // (nibble-board) arithmetic, everything else the mask-only fast path
     bool blk = !block_rule_irrelevant(P, d1, d2);
+#if defined(__CUDA_ARCH__) && defined(NARDE_DEBUG_HOOKS)
+    if (g_dbg_flags & 1) blk = false;  // timing experiment only (wrong results when the rule matters)
+#endif
     sh.blk[tid] = blk ? 1 : 0;
     if (a != b) {
       sh.kind[tid] = K_ND;
@@ -345,43 +348,74 @@ struct BlockStep {
     }
     return k - off;
   }
-  // exact variants: the block-rule aware sequential walker of narde_core.cuh restricted to (s1, s2)
-  struct OffsetSink {
-    uint64_t* slice;
-    int cap;
-    uint32_t k, idx;
-    uint64_t* chosen;
-    NHD void operator()(uint64_t a) {
-      if (slice && (int)k < cap) slice[k] = a;
-      if (k == idx) *chosen = a;
-      k++;
+  // exact variant (the block rule may matter, narde.py:78-89,139-184): same walk, but every board on
+  // the way is tested.  A multiset is legal iff SOME ordering keeps all intermediate boards legal;
+  // highest-source-first is tried implicitly (desc), any other ordering by dbl_order_search, which
+  // is only reached below a violating prefix.  Leaves are tested on occupancy masks only.
+  // EMIT = false: returns the number of legal 4-move leaves.  EMIT = true: also writes them.
+  template <bool EMIT>
+  static NHD uint32_t dbl_exact2(const Pos& P, int d, int H, int s1, int s2, uint32_t off, uint64_t* slice, int cap,
+                                 uint32_t idx, uint64_t* chosen) {
+    int src[4], order[4];
+    src[0] = s1;
+    src[1] = s2;
+    Pos P1 = P;
+    P1.move(s1, s1 - d);
+    bool v1 = violates_block(P1.own, P1.opp);
+    Pos P2 = P1;
+    P2.move(s2, s2 - d);
+    if (violates_block(P2.own, P2.opp)) {
+      // (s1, s2) itself is not a legal pair in any order, but longer multisets containing it may be
+      // reachable through other sub-multisets: handled per node by the ordering search below
     }
-  };
-  static NHD DblCtx exact_ctx(int d, int H, int s1, int s2) {
-    DblCtx cx;
-    cx.d = d;
-    cx.H = H;
-    cx.target = 4;
-    cx.blockchk = true;
-    cx.maxdepth = 0;
-    cx.n = 0;
-    cx.first_mask = 1u << s1;
-    cx.second_mask = 1u << s2;
-    return cx;
+    bool v2 = violates_block(P2.own, P2.opp);
+    bool desc2 = !v1 && !v2;
+    bool reach2 = !v2 && (!v1 || dbl_order_search(P, src, 2, d, H, order));
+    int h2 = (s1 == 23) + (s2 == 23);
+    uint32_t k = off;
+    uint32_t m3 = cand_mask(P2.own, P2.opp, d, h2 < H) & ((2u << s2) - 1u);
+    while (m3) {
+      int s3 = fls32(m3);
+      m3 &= ~(1u << s3);
+      src[2] = s3;
+      Pos P3 = P2;
+      P3.move(s3, s3 - d);
+      bool v3 = violates_block(P3.own, P3.opp);
+      bool desc3 = desc2 && !v3;
+      bool reach3 = !v3 && (reach2 || dbl_order_search(P, src, 3, d, H, order));
+      int h3 = h2 + (s3 == 23);
+      uint32_t m4 = cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u);
+      while (m4) {
+        int s4 = fls32(m4);
+        m4 &= ~(1u << s4);
+        if (violates_block(after_mask(P3, s4, s4 - d), P3.opp)) continue;
+        src[3] = s4;
+        bool searched = false;
+        if (!reach3) {
+          if (!dbl_order_search(P, src, 4, d, H, order)) continue;
+          searched = true;
+        }
+        if (EMIT) {
+          bool hit = k == idx;
+          if (hit || (slice && (int)k < cap)) {
+            uint64_t act = ACT_EMPTY;
+            if (desc3) {
+              for (int i = 0; i < 4; i++) act = act_set(act, i, src[i], src[i] - d);
+            } else {  // representative = first legal ordering, higher sources tried first
+              if (!searched) dbl_order_search(P, src, 4, d, H, order);
+              for (int i = 0; i < 4; i++) act = act_set(act, i, order[i], order[i] - d);
+            }
+            if (slice && (int)k < cap) slice[k] = act;
+            if (hit) *chosen = act;
+          }
+        }
+        k++;
+      }
+    }
+    return k - off;
   }
   static NHD uint32_t dbl_count2_exact(const Pos& P, int d, int H, int s1, int s2) {
-    DblCtx cx = exact_ctx(d, H, s1, s2);
-    int src[4];
-    CountSink ck;
-    DblLevel<0, CountSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, ck);
-    return (uint32_t)cx.n;
-  }
-  static NHD void dbl_emit2_exact(const Pos& P, int d, int H, int s1, int s2, uint32_t off, uint64_t* slice, int cap,
-                                  uint32_t idx, uint64_t* chosen) {
-    DblCtx cx = exact_ctx(d, H, s1, s2);
-    int src[4];
-    OffsetSink sk = {slice, cap, off, idx, chosen};
-    DblLevel<0, OffsetSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sk);
+    return dbl_exact2<false>(P, d, H, s1, s2, 0, nullptr, 0, 0xFFFFFFFFu, nullptr);
   }
 
   // ---- phase 3: ND rows -> pres ; doubles level-1 items -> second-source masks -------------
@@ -536,11 +570,7 @@ struct BlockStep {
         bool exact = sh.blk[e] != 0;
         if (store) {
           if (exact) {
-            OffsetSink sk = {slice, A.cap, off, idx, &sh.chosen[e]};
-            DblCtx cx = exact_ctx(d, H, s1, p);
-            int src[4];
-            DblLevel<0, OffsetSink>::run(P, P, cx, 0, 23, true, true, ACT_EMPTY, src, sk);
-            G += (uint32_t)cx.n;
+            G += dbl_exact2<true>(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
           } else {
             G += dbl_emit2(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
           }
@@ -550,7 +580,7 @@ struct BlockStep {
           G += cnt;
           if (idx >= off && idx < off + cnt) {
             if (exact)
-              dbl_emit2_exact(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
+              dbl_exact2<true>(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
             else
               dbl_emit2(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
           }

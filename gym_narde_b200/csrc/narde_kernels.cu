@@ -8,6 +8,8 @@
 #include <stdint.h>
 
 #include "../../include/narde_b200.h"
+#define NARDE_DEBUG_HOOKS 1
+namespace narde { __device__ int g_dbg_flags = 0; }
 #include "narde_block.cuh"
 #include "narde_env.cuh"
 
@@ -449,6 +451,8 @@ int narde_violates_block_rule(const int8_t* boards, int64_t n, uint8_t* out, voi
   k_block_rule<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(boards, n, out);
   return launch_status();
 }
+
+int narde_debug_set_flags(int flags) { return (int)cudaMemcpyToSymbol(narde::g_dbg_flags, &flags, sizeof(flags)); }
 
 int narde_debug_set_clock_buffer(void* devptr) {
   unsigned long long* p = (unsigned long long*)devptr;

@@ -16,7 +16,9 @@ buf = torch.zeros((nb, 16), dtype=torch.int64, device="cuda")
 lib = _cabi.load()
 lib.narde_debug_set_clock_buffer.argtypes = [C.c_void_p]
 assert lib.narde_debug_set_clock_buffer(C.c_void_p(buf.data_ptr())) == 0
-names = ["load", "scan+bases", "rows+dcount", "nd_count", "scan+offsets", "emit", "finish", "obs"]
+names = ["load", "scan+bases", "rows+L1", "scan+L2bases", "count", "scan+envbases", "emit", "finish", "obs"]
+if len(sys.argv) > 2:
+    lib0 = _cabi.load(); lib0.narde_debug_set_flags(int(sys.argv[2]))
 acc = []
 for _ in range(5):
     env.step()
@@ -24,13 +26,13 @@ for _ in range(5):
     acc.append(buf.cpu().numpy().copy())
 lib.narde_debug_set_clock_buffer(None)
 a = np.stack(acc).astype(np.float64)          # [steps, blocks, 16]
-d = np.diff(a[:, :, :9], axis=2)              # phase durations in cycles
-tot = a[:, :, 8] - a[:, :, 0]
+d = np.diff(a[:, :, :10], axis=2)              # phase durations in cycles
+tot = a[:, :, 9] - a[:, :, 0]
 print("blocks", nb, "block total cycles: mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f" % (
     tot.mean(), np.percentile(tot, 50), np.percentile(tot, 90), np.percentile(tot, 99), tot.max()))
 for k, nm in enumerate(names):
     x = d[:, :, k]
     print("%-14s mean %8.0f  p50 %8.0f  p99 %8.0f  max %9.0f  share %.1f%%" % (
         nm, x.mean(), np.percentile(x, 50), np.percentile(x, 99), x.max(), 100 * x.sum() / tot.sum()))
-span = a[:, :, 8].max(axis=1) - a[:, :, 0].min(axis=1)
+span = a[:, :, 9].max(axis=1) - a[:, :, 0].min(axis=1)
 print("kernel span cycles per step (max end - min start, per-SM clocks differ slightly):", span)
