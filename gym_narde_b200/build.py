@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libnarde_b200.so")
 SOURCES = ["narde_kernels.cu"]
-HEADERS = ["narde_core.cuh", "narde_env.cuh", os.path.join("..", "..", "include", "narde_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+    os.path.join("..", "..", "include", "narde_b200.h")]
 
 
 def nvcc_path() -> str:
