@@ -385,10 +385,16 @@ struct BlockStep {
       bool reach3 = !v3 && (reach2 || dbl_order_search(P, src, 3, d, H, order));
       int h3 = h2 + (s3 == 23);
       uint32_t m4 = cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u);
+      // leaves that cannot violate: the board is legal and the move does not land on a completing point
+      uint32_t risky = v3 ? m4 : (m4 & (completing_points(P3.own, P3.opp) << d));
+      if (!EMIT && reach3) {  // counting below a reachable node: only the risky leaves need a look
+        k += (uint32_t)popc32(m4 & ~risky);
+        m4 = risky;
+      }
       while (m4) {
         int s4 = fls32(m4);
         m4 &= ~(1u << s4);
-        if (violates_block(after_mask(P3, s4, s4 - d), P3.opp)) continue;
+        if (((risky >> s4) & 1u) && violates_block(after_mask(P3, s4, s4 - d), P3.opp)) continue;
         src[3] = s4;
         bool searched = false;
         if (!reach3) {

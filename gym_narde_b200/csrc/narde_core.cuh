@@ -241,13 +241,36 @@ NHD uint32_t after_mask(const Pos& P, int s, int t) {
 }
 
 // narde.py:78-89: drop candidates whose after-board violates the block rule
-NHD uint32_t block_filter(const Pos& P, uint32_t m, int d) {
+NHD uint32_t block_filter_each(const Pos& P, uint32_t m, int d) {
   uint32_t out = 0;
   for (uint32_t mm = m; mm; mm &= mm - 1) {
     int s = ctz32(mm);
     if (!violates_block(after_mask(P, s, s - d), P.opp)) out |= 1u << s;
   }
   return out;
+}
+
+// Empty points t for which own | {t} contains a violating 6-run (bit-parallel run arithmetic).
+// A run violates iff it lies entirely below the opponent's lowest checker, so only that part of
+// the board is looked at.  Only meaningful when `own` itself does not violate.
+NHD uint32_t completing_points(uint32_t own, uint32_t opp) {
+  uint32_t below = opp ? ((opp & (0u - opp)) - 1u) : 0xFFFFFFu;
+  uint32_t a = own & below;
+  uint32_t s1 = a, s2 = s1 & (a >> 1), s3 = s2 & (a >> 2), s4 = s3 & (a >> 3), s5 = s4 & (a >> 4);
+  // e_j: bit i set when points i-j+1..i are all own  (runs of length j ENDING at i)
+  uint32_t e1 = s1, e2 = s2 << 1, e3 = s3 << 2, e4 = s4 << 3, e5 = s5 << 4;
+  // t completes a run of >= 6 when (run ending at t-1) + 1 + (run starting at t+1) >= 6
+  uint32_t t = (s5 >> 1) | ((e1 << 1) & (s4 >> 1)) | ((e2 << 1) & (s3 >> 1)) | ((e3 << 1) & (s2 >> 1)) |
+               ((e4 << 1) & (s1 >> 1)) | (e5 << 1);
+  return t & ~own & below;
+}
+
+// narde.py:78-89 with the per-candidate board test only where it can fail: when the board is legal
+// now, a move can only create a violation by landing on a completing point.
+NHD uint32_t block_filter(const Pos& P, uint32_t m, int d) {
+  if (violates_block(P.own, P.opp)) return block_filter_each(P, m, d);
+  uint32_t risky = m & (completing_points(P.own, P.opp) << d);
+  return risky ? ((m & ~risky) | block_filter_each(P, risky, d)) : m;
 }
 
 // True when no board reachable from P within this turn can contain a violating 6-run: the run
@@ -266,7 +289,16 @@ NHD bool block_rule_irrelevant(const Pos& P, int d1, int d2) {
   u &= below_opp;
   uint32_t t2 = u & (u >> 1);
   uint32_t t4 = t2 & (t2 >> 2);
-  return (t4 & (t2 >> 4)) == 0u;
+  uint32_t w6 = t4 & (t2 >> 4);  // bit i: the 6-window starting at i could become all-own
+  if (w6 == 0u) return true;
+  // refinement: a turn adds at most `moves` newly occupied points (2 dice, or 4 for doubles), so a
+  // window needing more new points than that can never fill up
+  int moves = d1 == d2 ? 4 : 2;
+  for (; w6; w6 &= w6 - 1) {
+    int i = ctz32(w6);
+    if (popc32((0x3Fu << i) & ~P.own) <= moves) return false;
+  }
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------
