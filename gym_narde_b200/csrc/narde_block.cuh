@@ -353,6 +353,15 @@ struct BlockStep {
   // highest-source-first is tried implicitly (desc), any other ordering by dbl_order_search, which
   // is only reached below a violating prefix.  Leaves are tested on occupancy masks only.
   // EMIT = false: returns the number of legal 4-move leaves.  EMIT = true: also writes them.
+  static NHD bool order_search_dbg(const Pos& P, const int* src, int k, int d, int H, int* order) {
+#if defined(__CUDA_ARCH__) && defined(NARDE_DEBUG_HOOKS)
+    if (g_dbg_flags & 2) {  // timing experiment only
+      for (int i = 0; i < k; i++) order[i] = src[i];
+      return false;
+    }
+#endif
+    return dbl_order_search(P, src, k, d, H, order);
+  }
   template <bool EMIT>
   static NHD uint32_t dbl_exact2(const Pos& P, int d, int H, int s1, int s2, uint32_t off, uint64_t* slice, int cap,
                                  uint32_t idx, uint64_t* chosen) {
@@ -370,7 +379,7 @@ struct BlockStep {
     }
     bool v2 = violates_block(P2.own, P2.opp);
     bool desc2 = !v1 && !v2;
-    bool reach2 = !v2 && (!v1 || dbl_order_search(P, src, 2, d, H, order));
+    bool reach2 = !v2 && (!v1 || order_search_dbg(P, src, 2, d, H, order));
     int h2 = (s1 == 23) + (s2 == 23);
     uint32_t k = off;
     uint32_t m3 = cand_mask(P2.own, P2.opp, d, h2 < H) & ((2u << s2) - 1u);
@@ -382,7 +391,7 @@ struct BlockStep {
       P3.move(s3, s3 - d);
       bool v3 = violates_block(P3.own, P3.opp);
       bool desc3 = desc2 && !v3;
-      bool reach3 = !v3 && (reach2 || dbl_order_search(P, src, 3, d, H, order));
+      bool reach3 = !v3 && (reach2 || order_search_dbg(P, src, 3, d, H, order));
       int h3 = h2 + (s3 == 23);
       uint32_t m4 = cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u);
       // leaves that cannot violate: the board is legal and the move does not land on a completing point
@@ -398,7 +407,7 @@ struct BlockStep {
         src[3] = s4;
         bool searched = false;
         if (!reach3) {
-          if (!dbl_order_search(P, src, 4, d, H, order)) continue;
+          if (!order_search_dbg(P, src, 4, d, H, order)) continue;
           searched = true;
         }
         if (EMIT) {
@@ -408,7 +417,7 @@ struct BlockStep {
             if (desc3) {
               for (int i = 0; i < 4; i++) act = act_set(act, i, src[i], src[i] - d);
             } else {  // representative = first legal ordering, higher sources tried first
-              if (!searched) dbl_order_search(P, src, 4, d, H, order);
+              if (!searched) order_search_dbg(P, src, 4, d, H, order);
               for (int i = 0; i < 4; i++) act = act_set(act, i, order[i], order[i] - d);
             }
             if (slice && (int)k < cap) slice[k] = act;
