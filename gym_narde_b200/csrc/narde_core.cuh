@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define NHD __host__ __device__ __forceinline__
+#define NHD_NOINLINE __host__ __device__ __noinline__
 #else
 #define NHD inline
+#define NHD_NOINLINE inline
 #endif
 
 namespace narde {
@@ -589,7 +591,7 @@ NHD int enum_nondouble(const Pos& P, int a, int b, bool blockchk, Sink& sink) {
 // are legal half-moves; boards depend only on the sub-multiset, so this is a reachability problem
 // on the 2^k subsets (bounded work, no permutation blow-up).  Returns whether M is playable and
 // writes the lexicographically first legal ordering (higher sources tried first) to order[].
-NHD bool dbl_order_search(const Pos& base, const int* src, int k, int d, int H, int* order) {
+NHD_NOINLINE bool dbl_order_search(const Pos& base, const int* src, int k, int d, int H, int* order) {
   NPROF(dbl_order_search++);
   const uint32_t full = (1u << k) - 1u;
   uint32_t own_s[16];
