@@ -586,68 +586,55 @@ NHD int enum_nondouble(const Pos& P, int a, int b, bool blockchk, Sink& sink) {
 // rule (an intermediate 6-run can depend on the order); when the block rule can matter
 // (blockchk) every multiset whose descending order fails is re-tested over all its orderings.
 
-// Ordering search (rare path).  src[0..k) sorted descending, k <= 4.  A multiset is playable iff
-// there is a chain of sub-multisets 0 c S1 c ... c M whose boards are all legal and whose steps
-// are legal half-moves; boards depend only on the sub-multiset, so this is a reachability problem
-// on the 2^k subsets (bounded work, no permutation blow-up).  Returns whether M is playable and
-// writes the lexicographically first legal ordering (higher sources tried first) to order[].
-NHD_NOINLINE bool dbl_order_search(const Pos& base, const int* src, int k, int d, int H, int* order) {
+// Exhaustive ordering search (rare path).  src[0..k) sorted descending.  Finds the
+// lexicographically first legal ordering (trying higher sources first); writes it to order[].
+NHD bool dbl_order_search(const Pos& base, const int* src, int k, int d, int H, int* order) {
   NPROF(dbl_order_search++);
-  const uint32_t full = (1u << k) - 1u;
-  uint32_t own_s[16];
-  uint32_t ok = 1u;  // bit S: board of subset S is consistent and legal (the start board counts as legal)
-  own_s[0] = base.own;
-  uint32_t headbits = 0;
-  for (int i = 0; i < k; i++)
-    if (src[i] == 23) headbits |= 1u << i;
-  for (uint32_t S = 1; S <= full; S++) {
-    Pos P = base;
-    bool valid = true;
-    for (int i = 0; i < k; i++) {  // highest sources first: arrivals precede departures
-      if (!((S >> i) & 1u)) continue;
-      if (!((P.own >> src[i]) & 1u)) {
-        valid = false;
-        break;
-      }
-      P.move(src[i], src[i] - d);
-    }
-    own_s[S] = P.own;
-    if (valid && !violates_block(P.own, base.opp)) ok |= 1u << S;
-  }
-  if (!((ok >> full) & 1u)) return false;
-  // good[S]: from subset S the remaining moves can be completed legally
-  uint32_t good = 1u << full;
-  for (int S = (int)full - 1; S >= 0; S--) {
-    if (!((ok >> S) & 1u)) continue;
-    for (int i = 0; i < k; i++) {
-      if ((S >> i) & 1) continue;
-      uint32_t T = (uint32_t)S | (1u << i);
-      if (!((good >> T) & 1u)) continue;
-      int s = src[i];
-      if (!((own_s[S] >> s) & 1u)) continue;                                  // a checker to move
-      if (s - d >= 0 ? ((base.opp >> (s - d)) & 1u) != 0 : (own_s[S] >> 6) != 0u) continue;  // narde.py:69-77
-      if (s == 23 && popc32((uint32_t)S & headbits) >= H) continue;           // per-turn head budget
-      good |= 1u << S;
+  // iterative DFS over permutations, depth <= 4
+  Pos st[5];
+  int head[5];
+  int choice[4];   // index into src chosen at each depth
+  uint32_t used = 0;
+  st[0] = base;
+  head[0] = 0;
+  int depth = 0;
+  choice[0] = -1;
+  for (;;) {
+    // advance choice at this depth
+    int c = choice[depth] + 1;
+    bool placed = false;
+    for (; c < k; c++) {
+      if ((used >> c) & 1u) continue;
+      // skip equal sources already tried at this depth (same move)
+      bool same = false;
+      for (int e = 0; e < c; e++)
+        if (!((used >> e) & 1u) && src[e] == src[c]) same = true;
+      if (same) continue;
+      int s = src[c];
+      const Pos& cur = st[depth];
+      uint32_t m = cand_mask(cur.own, cur.opp, d, head[depth] < H);
+      if (!((m >> s) & 1u)) continue;
+      Pos nx = cur;
+      nx.move(s, s - d);
+      if (violates_block(nx.own, nx.opp)) continue;
+      st[depth + 1] = nx;
+      head[depth + 1] = head[depth] + (s == 23);
+      placed = true;
       break;
     }
-  }
-  if (!(good & 1u)) return false;
-  uint32_t S = 0;
-  for (int step = 0; step < k; step++) {
-    for (int i = 0; i < k; i++) {
-      if ((S >> i) & 1u) continue;
-      uint32_t T = S | (1u << i);
-      if (!((good >> T) & 1u)) continue;
-      int s = src[i];
-      if (!((own_s[S] >> s) & 1u)) continue;
-      if (s - d >= 0 ? ((base.opp >> (s - d)) & 1u) != 0 : (own_s[S] >> 6) != 0u) continue;
-      if (s == 23 && popc32(S & headbits) >= H) continue;
-      order[step] = s;
-      S = T;
-      break;
+    if (placed) {
+      choice[depth] = c;
+      used |= 1u << c;
+      order[depth] = src[c];
+      depth++;
+      if (depth == k) return true;
+      choice[depth] = -1;
+    } else {
+      if (depth == 0) return false;
+      depth--;
+      used &= ~(1u << choice[depth]);
     }
   }
-  return true;
 }
 
 struct DblCtx {
