@@ -30,6 +30,15 @@ NHD void sm_add(uint32_t* p, uint32_t v) {
   *p += v;
 #endif
 }
+NHD int32_t gl_fetch_add(int32_t* p, int32_t v) {  // global-memory counter
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, v);
+#else
+  int32_t o = *p;
+  *p += v;
+  return o;
+#endif
+}
 NHD void sm_max(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   atomicMax(p, v);
@@ -51,6 +60,7 @@ struct BlockShared {
   uint64_t chosen[BLK];
   uint8_t a[BLK], b[BLK], kind[BLK], first[BLK], d1[BLK], d2[BLK], blk[BLK];
   uint32_t maxd[BLK];                    // doubles: deepest playable level seen
+  uint32_t defer[BLK];                   // doubles: a reachable-looking board violates the block rule -> exact kernel
   uint32_t etotal[BLK], ebase[BLK];      // legal actions of the env / start of its list in item space
   // work items: ND rows, doubles level-1 sources, doubles level-2 sources
   uint32_t rowmask[BLK], dmask[BLK];
@@ -134,6 +144,7 @@ struct BlockStep {
     sh.etotal[tid] = 0;
     sh.ebase[tid] = 0;
     sh.maxd[tid] = 0;
+    sh.defer[tid] = 0;
     sh.kind[tid] = K_NONE;
     if (!valid) return;
     sh.st[tid] = s_in;
@@ -302,10 +313,23 @@ struct BlockStep {
 
   // ---- doubles sub-tree below the two highest sources (s1 >= s2) ----------------------------
   // fast variant (block rule irrelevant): count the 4-move leaves; *deep = 3 if a third move exists
-  static NHD uint32_t dbl_count2(const Pos& P, int d, int H, int s1, int s2, uint32_t* deep) {
+  // detect = true (block rule may matter): also test every board on the way; *taint is set when one
+  // violates -- then orderings matter and the env is handed to the exact CTA-per-env kernel.  When no
+  // board of the tree violates, highest-source-first play is legal for every multiset and the rule
+  // changes nothing, so the fast result is exact.
+  static NHD uint32_t dbl_count2(const Pos& P, int d, int H, int s1, int s2, uint32_t* deep, bool detect = false,
+                                 uint32_t* taint = nullptr) {
     Pos P2 = P;
     P2.move(s1, s1 - d);
+    if (detect && violates_block(P2.own, P2.opp)) {
+      *taint = 1;
+      return 0;
+    }
     P2.move(s2, s2 - d);
+    if (detect && violates_block(P2.own, P2.opp)) {
+      *taint = 1;
+      return 0;
+    }
     int h2 = (s1 == 23) + (s2 == 23);
     uint32_t leaves = 0;
     uint32_t m3 = cand_mask(P2.own, P2.opp, d, h2 < H) & ((2u << s2) - 1u);
@@ -316,7 +340,21 @@ struct BlockStep {
       Pos P3 = P2;
       P3.move(s3, s3 - d);
       int h3 = h2 + (s3 == 23);
-      leaves += (uint32_t)popc32(cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u));
+      uint32_t m4 = cand_mask(P3.own, P3.opp, d, h3 < H) & ((2u << s3) - 1u);
+      if (detect) {
+        if (violates_block(P3.own, P3.opp)) {
+          *taint = 1;
+          return 0;
+        }
+        for (uint32_t r = m4 & (completing_points(P3.own, P3.opp) << d); r; r &= r - 1) {
+          int s4 = ctz32(r);
+          if (violates_block(after_mask(P3, s4, s4 - d), P3.opp)) {
+            *taint = 1;
+            return 0;
+          }
+        }
+      }
+      leaves += (uint32_t)popc32(m4);
     }
     return leaves;
   }
@@ -434,7 +472,7 @@ struct BlockStep {
   }
 
   // ---- phase 3: ND rows -> pres ; doubles level-1 items -> second-source masks -------------
-  static NHD void ph_rows(int tid, Sh& sh) {
+  static NHD void ph_rows(int tid, Sh& sh, bool deferral) {
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
     ItemIter<uint32_t> it;
@@ -456,7 +494,8 @@ struct BlockStep {
       sh.d2mask[j] = m2;
       sh.l1env[j] = (uint8_t)e;
       sh.l1src[j] = (uint8_t)p;
-      if (!sh.blk[e]) sm_max(&sh.maxd[e], m2 ? 2u : 1u);
+      if (!sh.blk[e] || deferral) sm_max(&sh.maxd[e], m2 ? 2u : 1u);
+      if (sh.blk[e] && deferral && violates_block(P1.own, P1.opp)) sm_max(&sh.defer[e], 1u);
       sum += (uint32_t)popc32(m2);
       j++;
     }
@@ -474,7 +513,7 @@ struct BlockStep {
     if (tid == 0) sh.d2base[sh.n_l1] = sh.ws[1][32];
   }
   // ---- phase 5: counts per item -> chunk sums (lanes 0/1) and per-env totals ----------------
-  static NHD void ph_count(int tid, Sh& sh) {
+  static NHD void ph_count(int tid, Sh& sh, bool deferral) {
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
     ItemIter<uint32_t> it;
@@ -496,11 +535,12 @@ struct BlockStep {
         e = sh.l1env[j];
         int s1 = sh.l1src[j];
         uint32_t c;
-        if (sh.blk[e]) {
+        if (sh.blk[e] && !deferral) {
           c = dbl_count2_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p);
         } else {
-          uint32_t deep;
-          c = dbl_count2(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p, &deep);
+          uint32_t deep = 0, taint = 0;
+          c = dbl_count2(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p, &deep, sh.blk[e] != 0, &taint);
+          if (taint) sm_max(&sh.defer[e], 1u);
           if (c == 0) sm_max(&sh.maxd[e], deep);
         }
         if (c) sm_add(&sh.etotal[e], c);
@@ -575,14 +615,20 @@ struct BlockStep {
         e = sh.l1env[j];
         int s1 = sh.l1src[j];
         uint32_t total = sh.etotal[e];
-        if (total == 0) continue;  // cannot use four dice: sequential walk in ph_finish
+        if (total == 0 || sh.defer[e]) {  // cannot use four dice (ph_finish) / deferred to the exact kernel
+          if (total && sh.defer[e]) {  // keep the running offset consistent with what ph_count added
+            uint32_t deep, taint = 0;
+            G += dbl_count2(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p, &deep, true, &taint);
+          }
+          continue;
+        }
         uint32_t idx = pick_index(sh, e, row0 + e, total, A);
         uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
         uint32_t off = G - sh.ebase[e];
         Pos P = pos_of(sh, e);
         int d = sh.a[e], H = head_budget(sh, e);
         bool store = slice && (int)off < A.cap;
-        bool exact = sh.blk[e] != 0;
+        bool exact = sh.blk[e] != 0 && !A.defer_list;
         if (store) {
           if (exact) {
             G += dbl_exact2<true>(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
@@ -619,6 +665,10 @@ struct BlockStep {
       if (A.truncated) A.truncated[i] = 0;
       return;
     }
+    if (sh.defer[tid]) {  // handed to the exact CTA-per-env kernel; this kernel leaves the env untouched
+      A.defer_list[gl_fetch_add(A.defer_count, 1)] = (int32_t)i;
+      return;
+    }
     State s = sh.st[tid];
     int player = s.turn();
     int a = sh.a[tid], b = sh.b[tid];
@@ -645,7 +695,7 @@ struct BlockStep {
       Pos P = pos_of(sh, tid);
       bool ft = sh.first[tid] != 0;
       int target = (int)sh.maxd[tid];
-      bool known = !sh.blk[tid] && sh.n_l1 > 0;  // depth found by the item phases (fast path only)
+      bool known = (!sh.blk[tid] || A.defer_list) && sh.n_l1 > 0;  // depth found by the item phases
       if (known && target == 0) {
         count = 0;
       } else if (slice) {
@@ -672,36 +722,8 @@ struct BlockStep {
         }
       }
     }
-    L.count = (int)count;
-    L.overflow = (slice && (int)count > A.cap) ? 1 : 0;
-    if (count) apply_action(s, player, act);
-    float rew;
-    int dn;
-    finish_turn(s, player, (A.flags & F_REWARD_MOVER12) ? 1 : 0, &rew, &dn);
-    int bits = dn ? DONE_TERMINATED : 0;
-    if (!dn && A.max_episode_steps > 0 && (int)s.steps() >= A.max_episode_steps) bits |= DONE_TRUNCATED;
-    if (bits) {
-      L.finished = 1;
-      L.ep_len = (int)s.steps();
-      if (dn) {
-        if (player == 1)
-          L.white_win = 1;
-        else
-          L.black_win = 1;
-        L.mars = (player == 1 ? s.off_b() : s.off_w()) == 0 ? 1 : 0;
-      }
-      if (A.flags & F_AUTORESET) s = reset_env(A.seed, (uint32_t)(A.env_base + i), A.step);
-    }
+    complete_env(s, i, A, player, count, act, sh.d1[tid], sh.d2[tid], L);
     sh.st[tid] = s;
-    if (A.counts) A.counts[i] = (int32_t)count;
-    if (A.dice_out) {
-      A.dice_out[2 * i] = sh.d1[tid];  // roll order
-      A.dice_out[2 * i + 1] = sh.d2[tid];
-    }
-    if (A.chosen) A.chosen[i] = count ? act : ACT_EMPTY;
-    if (A.reward) A.reward[i] = rew;
-    if (A.done) A.done[i] = (bits & DONE_TERMINATED) ? 1 : 0;
-    if (A.truncated) A.truncated[i] = (bits & DONE_TRUNCATED) ? 1 : 0;
   }
 };
 

@@ -73,6 +73,10 @@ struct StepFullArgs {
   uint8_t* truncated;  // TimeLimit hit without termination (0/1), may be NULL
   int flags;
   int max_episode_steps;
+  // optional deferral of block-rule doubles turns to the CTA-per-env kernel (narde_deferred.cuh):
+  // defer_count[0] = number of deferred envs, defer_list[k] = their local indices
+  int32_t* defer_count;
+  int32_t* defer_list;
 };
 
 struct StepFullLocal {  // per-env contributions to the stats vector
@@ -165,6 +169,44 @@ NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal
   if (A.done) A.done[i] = (bits & DONE_TERMINATED) ? 1 : 0;
   if (A.truncated) A.truncated[i] = (bits & DONE_TRUNCATED) ? 1 : 0;
 }
+
+// End-of-turn completion shared by the kernels: apply, termination / reward / switch, auto-reset,
+// outputs and per-env stats contributions.
+NHD void complete_env(State& s, int64_t i, const StepFullArgs& A, int player, uint32_t count, uint64_t act, int d1, int d2,
+                      StepFullLocal& L) {
+  uint64_t* slice = A.actions ? A.actions + (int64_t)i * A.cap : nullptr;
+  L.count = (int)count;
+  L.overflow = (slice && (int)count > A.cap) ? 1 : 0;
+  L.finished = L.white_win = L.black_win = L.mars = L.ep_len = 0;
+  if (count) apply_action(s, player, act);
+  float rew;
+  int dn;
+  finish_turn(s, player, (A.flags & F_REWARD_MOVER12) ? 1 : 0, &rew, &dn);
+  int bits = dn ? DONE_TERMINATED : 0;
+  if (!dn && A.max_episode_steps > 0 && (int)s.steps() >= A.max_episode_steps) bits |= DONE_TRUNCATED;
+  if (bits) {
+    L.finished = 1;
+    L.ep_len = (int)s.steps();
+    if (dn) {
+      if (player == 1)
+        L.white_win = 1;
+      else
+        L.black_win = 1;
+      L.mars = (player == 1 ? s.off_b() : s.off_w()) == 0 ? 1 : 0;
+    }
+    if (A.flags & F_AUTORESET) s = reset_env(A.seed, (uint32_t)(A.env_base + i), A.step);
+  }
+  if (A.counts) A.counts[i] = (int32_t)count;
+  if (A.dice_out) {
+    A.dice_out[2 * i] = (uint8_t)d1;
+    A.dice_out[2 * i + 1] = (uint8_t)d2;
+  }
+  if (A.chosen) A.chosen[i] = count ? act : ACT_EMPTY;
+  if (A.reward) A.reward[i] = rew;
+  if (A.done) A.done[i] = (bits & DONE_TERMINATED) ? 1 : 0;
+  if (A.truncated) A.truncated[i] = (bits & DONE_TRUNCATED) ? 1 : 0;
+}
+
 
 // ---- narde_enumerate body -------------------------------------------------------------------
 NHD int enumerate_env(const State& s, int d1, int d2, int cap, uint64_t* slice) {

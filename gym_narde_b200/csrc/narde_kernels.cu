@@ -11,6 +11,7 @@
 #define NARDE_DEBUG_HOOKS 1
 namespace narde { __device__ int g_dbg_flags = 0; }
 #include "narde_block.cuh"
+#include "narde_deferred.cuh"
 #include "narde_env.cuh"
 
 using namespace narde;
@@ -44,11 +45,12 @@ __device__ __forceinline__ void obs_lut_init(float4* lut) {
   }
 }
 __device__ __forceinline__ void write_obs198_cta(const State* sm, const float4* lut, int rows, int64_t row0,
-                                                 float* __restrict__ obs) {
+                                                 float* __restrict__ obs, const uint32_t* skip = nullptr) {
   float* base = obs + row0 * 198;
   const int items = rows * 24;
   for (int g = threadIdx.x; g < items; g += blockDim.x) {
     int e = g / 24, pt = g - e * 24;
+    if (skip && skip[e]) continue;  // row written by the deferred kernel
     int v = sm[e].point(pt);
     float4 fw = lut[v > 0 ? v : 0], fb = lut[v < 0 ? -v : 0];
     float2* pw = reinterpret_cast<float2*>(base + e * 198 + 4 * pt);
@@ -60,6 +62,7 @@ __device__ __forceinline__ void write_obs198_cta(const State* sm, const float4* 
   }
   for (int g = threadIdx.x; g < rows * 3; g += blockDim.x) {
     int e = g / 3, k = g - e * 3;
+    if (skip && skip[e]) continue;
     const State& s = sm[e];
     float2 v;
     int at;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_item_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(2);
-  BS::ph_rows(tid, sh);
+  BS::ph_rows(tid, sh, A.defer_list != nullptr);
   __syncthreads();
   PHASE_MARK(3);
   BS::ph_scan1(tid, sh);
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_l2_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(4);
-  BS::ph_count(tid, sh);
+  BS::ph_count(tid, sh, A.defer_list != nullptr);
   __syncthreads();
   PHASE_MARK(5);
   BS::ph_env_totals(tid, sh);
@@ -267,9 +270,73 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   obs_lut_init(lut);
   __syncthreads();
   int rows = (int)min((int64_t)BLK, n - row0);
-  write_obs198_cta(sh.st, lut, rows, row0, obs198);
+  write_obs198_cta(sh.st, lut, rows, row0, obs198, sh.defer);
   __syncthreads();
   PHASE_MARK(9);
+}
+
+// Exact doubles turns handed over by k_step_full_v2 (narde_deferred.cuh): persistent CTAs walk the
+// deferred list, one environment per CTA at a time.
+template <int BLK>
+__global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A, float* obs198, int64_t* stats) {
+  typedef DeferredStep<BLK> DS;
+  extern __shared__ __align__(16) unsigned char dsm_raw[];
+  DeferredShared& sh = *reinterpret_cast<DeferredShared*>(dsm_raw);
+  __shared__ float4 lut[16];
+  obs_lut_init(lut);
+  const int tid = threadIdx.x;
+  const int n_def = *A.defer_count;
+  for (int q = blockIdx.x; q < n_def; q += gridDim.x) {
+    const int64_t i = A.defer_list[q];
+    State s;
+    if (tid == 0) s = ld_state(lo, hi, i);
+    DS::ph_init(tid, sh, s, i, A);
+    __syncthreads();
+    for (int level = 1; level <= 4; level++) {
+      DS::ph_clear(tid, sh);
+      __syncthreads();
+      DS::ph_expand(tid, sh, level);
+      __syncthreads();
+      bool more = sh.n_next > 0;
+      __syncthreads();
+      DS::ph_advance(tid, sh, level);
+      __syncthreads();
+      if (!more) break;
+    }
+    if (sh.overflow) {
+      DS::ph_fallback(tid, sh, i, A);
+    } else {
+      DS::ph_pad(tid, sh);
+      __syncthreads();
+      const uint32_t n2 = DS::padded(sh);
+      for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          DS::ph_sort_stage(tid, sh, k, j);
+          __syncthreads();
+        }
+      DS::ph_pick(tid, sh, i, A);
+      __syncthreads();
+      DS::ph_emit(tid, sh, i, A);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      StepFullLocal L;
+      State st = sh.st;
+      complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
+      sh.st = st;
+      st_state(lo, hi, i, st);
+      if (stats) {
+        int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
+        for (int k = 0; k < 6; k++)
+          if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
+        if (L.count) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)L.count);
+        if (L.overflow) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), 1ull);
+      }
+    }
+    __syncthreads();
+    if (obs198) write_obs198_cta(&sh.st, lut, 1, i, obs198);
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {
@@ -388,7 +455,7 @@ int narde_enumerate(const void* lo, const void* hi, const uint8_t* dice, int64_t
 int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
                     const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
                     uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
-                    int32_t flags, int32_t max_episode_steps, void* stream) {
+                    int32_t flags, int32_t max_episode_steps, int32_t* workspace, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || cap < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
   if (obs198 && (((uintptr_t)obs198) & 7u) != 0) return -1;
@@ -409,10 +476,30 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.truncated = truncated;
   A.flags = flags;
   A.max_episode_steps = max_episode_steps;
-  if (flags & NARDE_PER_THREAD_KERNEL)
+  A.defer_count = nullptr;
+  A.defer_list = nullptr;
+  if (flags & NARDE_PER_THREAD_KERNEL) {
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
-  else
-    k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
+    return launch_status();
+  }
+  if (workspace) {  // [0] = number of deferred envs, [1..n] = their indices
+    if ((((uintptr_t)workspace) & 3u) != 0) return -1;
+    A.defer_count = workspace;
+    A.defer_list = workspace + 1;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
+  if (workspace) {
+    static bool attr_set = false;
+    const int dyn = (int)sizeof(DeferredShared);
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_step_deferred<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    k_step_deferred<128><<<296, 128, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
+  }
   return launch_status();
 }
 

@@ -49,6 +49,7 @@ class VecNardeEnv:
         self.terminated = self.done.view(torch.bool)
         self.truncated = self.trunc.view(torch.bool)
         self.stats = torch.zeros(_cabi.NUM_STATS, dtype=torch.int64, device=dev)
+        self.workspace = torch.zeros(n + 1, dtype=torch.int32, device=dev)  # deferred-turn list (see narde_b200.h)
         self.info = {"dice": self.dice, "counts": self.counts, "chosen": self.chosen}
         if rules == "full":
             self.obs = torch.zeros((n, 198), dtype=torch.float32, device=dev)
@@ -113,7 +114,8 @@ class VecNardeEnv:
                             action_idx=actions, actions=self.actions if self.write_actions else None,
                             counts=self.counts, dice_out=self.dice, chosen=self.chosen, obs198=self.obs,
                             reward=self.reward, done=self.done, stats=self.stats, flags=flags,
-                            max_episode_steps=self.max_episode_steps, truncated=self.trunc)
+                            max_episode_steps=self.max_episode_steps, truncated=self.trunc,
+                            workspace=self.workspace)
         else:
             if actions is None:
                 raise ValueError("rules='reference' needs action codes [N,2]")

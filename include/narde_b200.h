@@ -102,12 +102,15 @@ int narde_enumerate(const void *lo, const void *hi, const uint8_t *dice, int64_t
  *   enumeration (written to actions/counts like narde_enumerate; actions may be NULL) -> action
  *   choice (action_idx[i], clamped; NULL = Philox-uniform) -> apply -> termination / reward
  *   -> player switch -> optional auto-reset -> Box(198) observation (README.md:44-102).
- * Any of actions, counts, dice_out, obs198, reward, done, truncated, chosen, stats may be NULL. */
+ * Any of actions, counts, dice_out, obs198, reward, done, truncated, chosen, stats may be NULL.
+ * workspace: optional scratch of (n + 1) int32 owned by the caller.  With it, the rare doubles
+ * turns in which the 6-prime block rule makes the move ORDER matter are handed to a second,
+ * CTA-per-environment kernel (same results, shorter tail); without it they are resolved inline. */
 int narde_step_full(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
                     const uint8_t *dice_in, const int32_t *action_idx, int32_t cap,
                     uint64_t *actions, int32_t *counts, uint8_t *dice_out, uint64_t *chosen,
                     float *obs198, float *reward, uint8_t *done, uint8_t *truncated, int64_t *stats,
-                    int32_t flags, int32_t max_episode_steps, void *stream);
+                    int32_t flags, int32_t max_episode_steps, int32_t *workspace, void *stream);
 
 /* Observations of the current states: Box(198) float32 (README.md:44-102) / the reference's
  * mover-perspective int32[24] (narde_env.py:24-25). */

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "../../gym_narde_b200/csrc/narde_block.cuh"
+#include "../../gym_narde_b200/csrc/narde_deferred.cuh"
 #include "../../gym_narde_b200/csrc/narde_env.cuh"
 
 using namespace narde;
@@ -102,7 +103,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
                  uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
                  int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
-                    chosen, reward, done, truncated, flags, max_episode_steps};
+                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr};
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
     StepFullLocal L;
@@ -140,11 +141,11 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
     for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_item_bases(t, sh); }
-    for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh);
+    for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh, A.defer_list != nullptr);
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
     for (int t = 0; t < BLK; t++) { BS::ph_scan3(t, sh); BS::ph_l2_bases(t, sh); }
-    for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh);
+    for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh, A.defer_list != nullptr);
     for (int t = 0; t < BLK; t++) BS::ph_env_totals(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
@@ -154,7 +155,7 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
       bool valid = row0 + t < n;
       StepFullLocal L;
       BS::ph_finish(t, sh, valid, row0 + t, A, L);
-      if (!valid) continue;
+      if (!valid || sh.defer[t]) continue;
       store_state(lo, hi, row0 + t, sh.st[t]);
       if (stats) {
         stats[0] += L.finished; stats[1] += L.white_win; stats[2] += L.black_win; stats[3] += L.mars;
@@ -169,14 +170,62 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
   }
 }
 
+// CTA-per-env exact kernel (narde_deferred.cuh), emulated phase by phase
+template <int BLK>
+static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float* obs198, int64_t* stats) {
+  typedef DeferredStep<BLK> DS;
+  static DeferredShared sh;
+  for (int q = 0; q < A.defer_count[0]; q++) {
+    int64_t i = A.defer_list[q];
+    State s = load_state(lo, hi, i);
+    for (int t = 0; t < BLK; t++) DS::ph_init(t, sh, s, i, A);
+    for (int level = 1; level <= 4; level++) {
+      for (int t = 0; t < BLK; t++) DS::ph_clear(t, sh);
+      for (int t = BLK - 1; t >= 0; t--) DS::ph_expand(t, sh, level);
+      bool more = sh.n_next > 0;
+      for (int t = 0; t < BLK; t++) DS::ph_advance(t, sh, level);
+      if (!more) break;
+    }
+    if (sh.overflow) {
+      for (int t = 0; t < BLK; t++) DS::ph_fallback(t, sh, i, A);
+    } else {
+      for (int t = 0; t < BLK; t++) DS::ph_pad(t, sh);
+      uint32_t n2 = DS::padded(sh);
+      for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1)
+          for (int t = 0; t < BLK; t++) DS::ph_sort_stage(t, sh, k, j);
+      for (int t = 0; t < BLK; t++) DS::ph_pick(t, sh, i, A);
+      for (int t = BLK - 1; t >= 0; t--) DS::ph_emit(t, sh, i, A);
+    }
+    StepFullLocal L;
+    State st = sh.st;
+    complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
+    store_state(lo, hi, i, st);
+    if (stats) {
+      stats[0] += L.finished; stats[1] += L.white_win; stats[2] += L.black_win; stats[3] += L.mars;
+      stats[4] += L.ep_len; stats[5] += L.count;
+      if (L.count > stats[6]) stats[6] = L.count;
+      stats[7] += L.overflow;
+    }
+    if (obs198)
+      for (int k = 0; k < 99; k++) obs198_pair(st, k, obs198 + 198 * i + 2 * k, obs198 + 198 * i + 2 * k + 1);
+  }
+}
+
 extern "C" {
 int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
                     const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
                     uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
-                    int32_t flags, int32_t max_episode_steps, void*) {
+                    int32_t flags, int32_t max_episode_steps, int32_t* workspace, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
-                    chosen, reward, done, truncated, flags, max_episode_steps};
+                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr};
+  if (workspace) {
+    workspace[0] = 0;
+    A.defer_count = workspace;
+    A.defer_list = workspace + 1;
+  }
   step_full_v2_host<128>(lo, hi, n, A, obs198, stats);
+  if (workspace) step_deferred_host<128>(lo, hi, A, obs198, stats);
   return 0;
 }
 

@@ -87,6 +87,7 @@ class HostSim:
         return obs
 
     per_thread = False  # True: the thread-per-env body (k_step_full); False: the CTA-cooperative phases
+    defer = True        # CTA-cooperative path: hand block-rule doubles turns to the CTA-per-env exact phases
 
     def step_full(self, lo, hi, env_base=0, seed=0, step=0, dice_in=None, action_idx=None, cap=64, flags=0,
                   max_episode_steps=0, want_actions=True, want_obs=True):
@@ -106,11 +107,15 @@ class HostSim:
             "trunc": np.zeros(n, np.uint8),
             "stats": np.zeros(8, np.int64),
         }
-        fn = self.lib.hs_step_full if (self.per_thread or (flags & 8)) else self.lib.hs_step_full_v2
+        v1 = self.per_thread or (flags & 8)
+        ws = np.zeros(n + 1, np.int32) if (self.defer and not v1) else None
+        fn = self.lib.hs_step_full if v1 else self.lib.hs_step_full_v2
+        tail = (None,) if v1 else (_p(ws), None)
         fn(_p(lo), _p(hi), C.c_int64(n), C.c_int64(env_base), C.c_uint64(seed), C.c_uint64(step),
                               _p(dice_in), _p(action_idx), C.c_int32(cap), _p(out["actions"]), _p(out["counts"]),
                               _p(out["dice"]), _p(out["chosen"]), _p(out["obs198"]), _p(out["reward"]),
-                              _p(out["done"]), _p(out["trunc"]), _p(out["stats"]), C.c_int32(flags), C.c_int32(max_episode_steps), None)
+                              _p(out["done"]), _p(out["trunc"]), _p(out["stats"]), C.c_int32(flags), C.c_int32(max_episode_steps), *tail)
+        out["deferred"] = int(ws[0]) if ws is not None else 0
         return out
 
     def apply_actions(self, lo, hi, acts, flags=0):
@@ -216,13 +221,15 @@ class CudaBackend:
         done = t.zeros(n, dtype=t.uint8, device=self.dev)
         stats = t.zeros(8, dtype=t.int64, device=self.dev)
         trunc = t.zeros(n, dtype=t.uint8, device=self.dev)
+        ws = t.zeros(n + 1, dtype=t.int32, device=self.dev) if (getattr(self, "defer", True) and not (flags & 8)) else None
         if getattr(self, "per_thread", False):
             flags |= 8  # NARDE_PER_THREAD_KERNEL
         self.cabi.step_full(tlo, thi, env_base, seed, step,
                             dice_in=self._up(None if dice_in is None else np.asarray(dice_in, np.uint8)),
                             action_idx=self._up(None if action_idx is None else np.asarray(action_idx, np.int32)),
                             actions=actions, counts=counts, dice_out=dice, chosen=chosen, obs198=obs, reward=rew,
-                            done=done, stats=stats, flags=flags, max_episode_steps=max_episode_steps, truncated=trunc)
+                            done=done, stats=stats, flags=flags, max_episode_steps=max_episode_steps, truncated=trunc,
+                            workspace=ws)
         self._sync_back(lo, hi, tlo, thi)
         return {
             "actions": actions.cpu().numpy().view(np.uint64) if want_actions else None,
@@ -230,6 +237,7 @@ class CudaBackend:
             "chosen": chosen.cpu().numpy().view(np.uint64),
             "obs198": obs.cpu().numpy() if want_obs else None, "reward": rew.cpu().numpy(),
             "done": done.cpu().numpy(), "trunc": trunc.cpu().numpy(), "stats": stats.cpu().numpy(),
+            "deferred": int(ws[0].item()) if ws is not None else 0,
         }
 
     def apply_actions(self, lo, hi, acts, flags=0):
