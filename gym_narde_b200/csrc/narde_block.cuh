@@ -589,17 +589,15 @@ struct BlockStep {
       nd_row(sh, e, p, &m1, &m2);
       int a = sh.a[e], b = sh.b[e], ta = p - a;
       uint32_t k = off;
+      const uint32_t hp = (uint32_t)p | ((ta < 0 ? 255u : (uint32_t)ta) << 8);  // half-move of the higher die
       while (nd) {
         int q = fls32(nd);
         nd &= ~(1u << q);
-        uint64_t act = ACT_EMPTY;
-        if ((m1 >> q) & 1u) {
-          act = act_set(act, 0, p, ta);
-          act = act_set(act, 1, q, q - b);
-        } else {
-          act = act_set(act, 0, q, q - b);
-          act = act_set(act, 1, p, ta);
-        }
+        int tb = q - b;
+        uint32_t hq = (uint32_t)q | ((tb < 0 ? 255u : (uint32_t)tb) << 8);
+        // two half-moves in slots 0,1 (played in that order), slots 2,3 unused (0xFFFF)
+        uint32_t lo32 = ((m1 >> q) & 1u) ? (hp | (hq << 16)) : (hq | (hp << 16));
+        uint64_t act = 0xFFFFFFFF00000000ull | lo32;
         if (slice && (int)k < A.cap) slice[k] = act;
         if (k == idx) sh.chosen[e] = act;
         k++;

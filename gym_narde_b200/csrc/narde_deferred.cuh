@@ -45,9 +45,12 @@ struct DeferredShared {
   uint32_t n_cur, n_next, depth, overflow, which;  // which: 0 -> level list in a[], 1 -> in b[]
   uint32_t count, idx;
   uint64_t chosen;
+  uint32_t part[132];
+  // a | b | hash are contiguous: once the search is over, b..hash is reused as a 24^4-bit bitmap
   uint32_t a[kDefCap], b[kDefCap];
   uint32_t hash[kDefHash];
 };
+static_assert(kDefCap + kDefHash >= (24 * 24 * 24 * 24 + 31) / 32, "bitmap must fit in b + hash");
 
 template <int BLK>
 struct DeferredStep {
@@ -173,29 +176,72 @@ struct DeferredStep {
       sh.depth = (uint32_t)level;
     }
   }
-  // ---- sort the final level ascending (bitonic, padded to a power of two with 0xFFFFFFFF) ----
-  static NHD uint32_t padded(const Sh& sh) {
-    uint32_t n2 = 1;
-    while (n2 < sh.n_cur) n2 <<= 1;
-    return n2;
+  // ---- sort the final level ascending: set one bit per multiset in a dense bitmap (index = the
+  // base-24 value of the digits, same order as the key), then compact the bitmap in order --------
+  static NHD uint32_t bm_words(const Sh& sh) {
+    uint32_t bits = 1;
+    for (uint32_t k = 0; k < sh.depth; k++) bits *= 24u;
+    return (bits + 31u) >> 5;
   }
-  static NHD void ph_pad(int tid, Sh& sh) {
-    uint32_t* cur = sh.which ? sh.b : sh.a;
-    uint32_t n2 = padded(sh);
-    for (uint32_t k = sh.n_cur + (uint32_t)tid; k < n2; k += BLK) cur[k] = 0xFFFFFFFFu;
+  static NHD void ph_to_a(int tid, Sh& sh) {  // the final list must live in a[] (b..hash become the bitmap)
+    if (sh.which)
+      for (uint32_t k = (uint32_t)tid; k < sh.n_cur; k += BLK) sh.a[k] = sh.b[k];
   }
-  static NHD void ph_sort_stage(int tid, Sh& sh, uint32_t k, uint32_t j) {
-    uint32_t* cur = sh.which ? sh.b : sh.a;
-    uint32_t n2 = padded(sh);
-    for (uint32_t i = (uint32_t)tid; i < n2; i += BLK) {
-      uint32_t l = i ^ j;
-      if (l > i) {
-        uint32_t x = cur[i], y = cur[l];
-        bool up = (i & k) == 0;
-        if ((x > y) == up) {
-          cur[i] = y;
-          cur[l] = x;
+  static NHD void ph_bm_clear(int tid, Sh& sh) {
+    uint32_t* bm = sh.b;
+    uint32_t nw = bm_words(sh);
+    for (uint32_t k = (uint32_t)tid; k < nw; k += BLK) bm[k] = 0;
+    if (tid == 0) sh.which = 0;
+  }
+  static NHD void ph_bm_set(int tid, Sh& sh) {
+    uint32_t* bm = sh.b;
+    int j = (int)sh.depth;
+    for (uint32_t k = (uint32_t)tid; k < sh.n_cur; k += BLK) {
+      uint32_t code = sh.a[k], dense = 0;
+      for (int i = 0; i < j; i++) dense = dense * 24u + ((code >> (5 * (j - 1 - i))) & 31u);
+#if defined(__CUDA_ARCH__)
+      atomicOr(&bm[dense >> 5], 1u << (dense & 31u));
+#else
+      bm[dense >> 5] |= 1u << (dense & 31u);
+#endif
+    }
+  }
+  static NHD void bm_range(const Sh& sh, int tid, uint32_t* w0, uint32_t* w1) {
+    uint32_t nw = bm_words(sh);
+    uint32_t per = (nw + BLK - 1) / BLK;
+    uint32_t lo = (uint32_t)tid * per, hi = lo + per;
+    *w0 = lo < nw ? lo : nw;
+    *w1 = hi < nw ? hi : nw;
+  }
+  static NHD void ph_bm_count(int tid, Sh& sh) {
+    const uint32_t* bm = sh.b;
+    uint32_t w0, w1, c = 0;
+    bm_range(sh, tid, &w0, &w1);
+    for (uint32_t w = w0; w < w1; w++) c += (uint32_t)popc32(bm[w]);
+    sh.part[tid] = c;
+  }
+  static NHD void ph_bm_scan(int tid, Sh& sh) {
+    if (tid != 0) return;
+    uint32_t r = 0;
+    for (int k = 0; k < BLK; k++) {
+      uint32_t t = sh.part[k];
+      sh.part[k] = r;
+      r += t;
+    }
+  }
+  static NHD void ph_bm_emit(int tid, Sh& sh) {
+    const uint32_t* bm = sh.b;
+    int j = (int)sh.depth;
+    uint32_t w0, w1, at = sh.part[tid];
+    bm_range(sh, tid, &w0, &w1);
+    for (uint32_t w = w0; w < w1; w++) {
+      for (uint32_t m = bm[w]; m; m &= m - 1) {
+        uint32_t dense = (w << 5) + (uint32_t)ctz32(m), code = 0;
+        for (int i = 0; i < j; i++) {  // base-24 digits, least significant first
+          code |= (dense % 24u) << (5 * i);
+          dense /= 24u;
         }
+        sh.a[at++] = code;
       }
     }
   }

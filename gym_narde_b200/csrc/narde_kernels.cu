@@ -306,14 +306,18 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
     if (sh.overflow) {
       DS::ph_fallback(tid, sh, i, A);
     } else {
-      DS::ph_pad(tid, sh);
+      DS::ph_to_a(tid, sh);
       __syncthreads();
-      const uint32_t n2 = DS::padded(sh);
-      for (uint32_t k = 2; k <= n2; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-          DS::ph_sort_stage(tid, sh, k, j);
-          __syncthreads();
-        }
+      DS::ph_bm_clear(tid, sh);
+      __syncthreads();
+      DS::ph_bm_set(tid, sh);
+      __syncthreads();
+      DS::ph_bm_count(tid, sh);
+      __syncthreads();
+      DS::ph_bm_scan(tid, sh);
+      __syncthreads();
+      DS::ph_bm_emit(tid, sh);
+      __syncthreads();
       DS::ph_pick(tid, sh, i, A);
       __syncthreads();
       DS::ph_emit(tid, sh, i, A);

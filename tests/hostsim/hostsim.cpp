@@ -189,11 +189,12 @@ static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float*
     if (sh.overflow) {
       for (int t = 0; t < BLK; t++) DS::ph_fallback(t, sh, i, A);
     } else {
-      for (int t = 0; t < BLK; t++) DS::ph_pad(t, sh);
-      uint32_t n2 = DS::padded(sh);
-      for (uint32_t k = 2; k <= n2; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1)
-          for (int t = 0; t < BLK; t++) DS::ph_sort_stage(t, sh, k, j);
+      for (int t = 0; t < BLK; t++) DS::ph_to_a(t, sh);
+      for (int t = 0; t < BLK; t++) DS::ph_bm_clear(t, sh);
+      for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_set(t, sh);
+      for (int t = 0; t < BLK; t++) DS::ph_bm_count(t, sh);
+      for (int t = 0; t < BLK; t++) DS::ph_bm_scan(t, sh);
+      for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_emit(t, sh);
       for (int t = 0; t < BLK; t++) DS::ph_pick(t, sh, i, A);
       for (int t = BLK - 1; t >= 0; t--) DS::ph_emit(t, sh, i, A);
     }
