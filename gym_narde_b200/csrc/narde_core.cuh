@@ -637,6 +637,69 @@ NHD bool dbl_order_search(const Pos& base, const int* src, int k, int d, int H, 
   }
 }
 
+// Ordering search, bounded-work variant used by the CTA-per-env exact kernel.  src[0..k) sorted descending, k <= 4.  A multiset is playable iff
+// there is a chain of sub-multisets 0 c S1 c ... c M whose boards are all legal and whose steps
+// are legal half-moves; boards depend only on the sub-multiset, so this is a reachability problem
+// on the 2^k subsets (bounded work, no permutation blow-up).  Returns whether M is playable and
+// writes the lexicographically first legal ordering (higher sources tried first) to order[].
+NHD bool dbl_order_search_dp(const Pos& base, const int* src, int k, int d, int H, int* order) {
+  const uint32_t full = (1u << k) - 1u;
+  uint32_t own_s[16];
+  uint32_t ok = 1u;  // bit S: board of subset S is consistent and legal (the start board counts as legal)
+  own_s[0] = base.own;
+  uint32_t headbits = 0;
+  for (int i = 0; i < k; i++)
+    if (src[i] == 23) headbits |= 1u << i;
+  for (uint32_t S = 1; S <= full; S++) {
+    Pos P = base;
+    bool valid = true;
+    for (int i = 0; i < k; i++) {  // highest sources first: arrivals precede departures
+      if (!((S >> i) & 1u)) continue;
+      if (!((P.own >> src[i]) & 1u)) {
+        valid = false;
+        break;
+      }
+      P.move(src[i], src[i] - d);
+    }
+    own_s[S] = P.own;
+    if (valid && !violates_block(P.own, base.opp)) ok |= 1u << S;
+  }
+  if (!((ok >> full) & 1u)) return false;
+  // good[S]: from subset S the remaining moves can be completed legally
+  uint32_t good = 1u << full;
+  for (int S = (int)full - 1; S >= 0; S--) {
+    if (!((ok >> S) & 1u)) continue;
+    for (int i = 0; i < k; i++) {
+      if ((S >> i) & 1) continue;
+      uint32_t T = (uint32_t)S | (1u << i);
+      if (!((good >> T) & 1u)) continue;
+      int s = src[i];
+      if (!((own_s[S] >> s) & 1u)) continue;                                  // a checker to move
+      if (s - d >= 0 ? ((base.opp >> (s - d)) & 1u) != 0 : (own_s[S] >> 6) != 0u) continue;  // narde.py:69-77
+      if (s == 23 && popc32((uint32_t)S & headbits) >= H) continue;           // per-turn head budget
+      good |= 1u << S;
+      break;
+    }
+  }
+  if (!(good & 1u)) return false;
+  uint32_t S = 0;
+  for (int step = 0; step < k; step++) {
+    for (int i = 0; i < k; i++) {
+      if ((S >> i) & 1u) continue;
+      uint32_t T = S | (1u << i);
+      if (!((good >> T) & 1u)) continue;
+      int s = src[i];
+      if (!((own_s[S] >> s) & 1u)) continue;
+      if (s - d >= 0 ? ((base.opp >> (s - d)) & 1u) != 0 : (own_s[S] >> 6) != 0u) continue;
+      if (s == 23 && popc32(S & headbits) >= H) continue;
+      order[step] = s;
+      S = T;
+      break;
+    }
+  }
+  return true;
+}
+
 struct DblCtx {
   int d, H, target;
   bool blockchk;

@@ -45,7 +45,7 @@ struct DeferredShared {
   uint32_t n_cur, n_next, depth, overflow, which;  // which: 0 -> level list in a[], 1 -> in b[]
   uint32_t count, idx;
   uint64_t chosen;
-  uint32_t part[132];
+  uint32_t part[1028];
   // a | b | hash are contiguous: once the search is over, b..hash is reused as a 24^4-bit bitmap
   uint32_t a[kDefCap], b[kDefCap];
   uint32_t hash[kDefHash];
@@ -251,7 +251,7 @@ struct DeferredStep {
     unpack(code, j, src);
     Pos P = base_pos(sh);
     uint64_t act = ACT_EMPTY;
-    if (dbl_order_search(P, src, j, sh.d, sh.H, order))
+    if (dbl_order_search_dp(P, src, j, sh.d, sh.H, order))
       for (int k = 0; k < j; k++) act = act_set(act, k, order[k], order[k] - sh.d);
     return act;
   }

@@ -498,11 +498,11 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     static bool attr_set = false;
     const int dyn = (int)sizeof(DeferredShared);
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_step_deferred<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+      cudaError_t e = cudaFuncSetAttribute(k_step_deferred<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
       if (e != cudaSuccess) return (int)e;
       attr_set = true;
     }
-    k_step_deferred<128><<<296, 128, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
+    k_step_deferred<512><<<148, 512, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
   }
   return launch_status();
 }

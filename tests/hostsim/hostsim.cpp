@@ -226,7 +226,7 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     A.defer_list = workspace + 1;
   }
   step_full_v2_host<128>(lo, hi, n, A, obs198, stats);
-  if (workspace) step_deferred_host<128>(lo, hi, A, obs198, stats);
+  if (workspace) step_deferred_host<512>(lo, hi, A, obs198, stats);
   return 0;
 }
 
