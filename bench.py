@@ -277,13 +277,13 @@ def run_cuda_arm(args):
                        "mean_legal_actions": A, "max_legal_actions": int(st_all[:, 6].max().item()),
                        "l2": "flushed between timed steps (256 MiB fill, untimed)" if flush is not None else "not flushed",
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
-            "roofline": {"bound": "hbm", "kernel": "k_step_full", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_step_full_v2<128> (+ k_step_deferred<512> for order-dependent doubles turns), %d chunk launches per step, timed as one step" % len(env._chunks), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 5 * E,
                     "ms_per_step": total_e2e_max / K,
                     "note": "VecNardeEnv.step(action_idx): pinned int32 action indices H2D, reward f32 + done u8 D2H every step; Box(198) stays in HBM for the device-resident policy"},
-            "gpu_launches": K, "wall_ms": wall_ms, "clocks": clocks,
+            "gpu_launches": K * 2 * len(env._chunks), "wall_ms": wall_ms, "clocks": clocks,
             "config2_4096_envs": {"value": 4096 * len(ms_small) / (sum(ms_small) * 1e-3), "unit": UNIT,
                                   "ms_per_step": sum(ms_small) / len(ms_small)},
             "episode_stats": {k: int(v) for k, v in zip(_cabi.STAT_NAMES, st_all.sum(0).tolist())},

@@ -45,7 +45,7 @@ struct DeferredShared {
   uint32_t n_cur, n_next, depth, overflow, which;  // which: 0 -> level list in a[], 1 -> in b[]
   uint32_t count, idx;
   uint64_t chosen;
-  uint32_t part[1028];
+  uint32_t part[1024], base[1024], part2[32];
   // a | b | hash are contiguous: once the search is over, b..hash is reused as a 24^4-bit bitmap
   uint32_t a[kDefCap], b[kDefCap];
   uint32_t hash[kDefHash];
@@ -220,19 +220,33 @@ struct DeferredStep {
     for (uint32_t w = w0; w < w1; w++) c += (uint32_t)popc32(bm[w]);
     sh.part[tid] = c;
   }
-  static NHD void ph_bm_scan(int tid, Sh& sh) {
+  // block exclusive scan of part[0..BLK) in three short phases (part2 = per-32-group sums)
+  static NHD void ph_bm_scan1(int tid, Sh& sh) {
+    if (tid < 32) {
+      uint32_t r = 0;
+      for (int k = 0; k < BLK / 32; k++) r += sh.part[tid * (BLK / 32) + k];
+      sh.part2[tid] = r;
+    }
+  }
+  static NHD void ph_bm_scan2(int tid, Sh& sh) {
     if (tid != 0) return;
     uint32_t r = 0;
-    for (int k = 0; k < BLK; k++) {
-      uint32_t t = sh.part[k];
-      sh.part[k] = r;
+    for (int k = 0; k < 32; k++) {
+      uint32_t t = sh.part2[k];
+      sh.part2[k] = r;
       r += t;
     }
+  }
+  static NHD void ph_bm_scan3(int tid, Sh& sh) {
+    int g = tid / (BLK / 32);
+    uint32_t r = sh.part2[g];
+    for (int k = g * (BLK / 32); k < tid; k++) r += sh.part[k];
+    sh.base[tid] = r;
   }
   static NHD void ph_bm_emit(int tid, Sh& sh) {
     const uint32_t* bm = sh.b;
     int j = (int)sh.depth;
-    uint32_t w0, w1, at = sh.part[tid];
+    uint32_t w0, w1, at = sh.base[tid];
     bm_range(sh, tid, &w0, &w1);
     for (uint32_t w = w0; w < w1; w++) {
       for (uint32_t m = bm[w]; m; m &= m - 1) {
@@ -251,7 +265,7 @@ struct DeferredStep {
     unpack(code, j, src);
     Pos P = base_pos(sh);
     uint64_t act = ACT_EMPTY;
-    if (dbl_order_search_dp(P, src, j, sh.d, sh.H, order))
+    if (dbl_order_search(P, src, j, sh.d, sh.H, order))
       for (int k = 0; k < j; k++) act = act_set(act, k, order[k], order[k] - sh.d);
     return act;
   }

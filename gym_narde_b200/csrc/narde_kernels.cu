@@ -286,12 +286,18 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
   obs_lut_init(lut);
   const int tid = threadIdx.x;
   const int n_def = *A.defer_count;
+#define DMARK(k)                                                                                      \
+  do {                                                                                                \
+    if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + (k)] = clock64();      \
+  } while (0)
   for (int q = blockIdx.x; q < n_def; q += gridDim.x) {
     const int64_t i = A.defer_list[q];
     State s;
+    DMARK(0);
     if (tid == 0) s = ld_state(lo, hi, i);
     DS::ph_init(tid, sh, s, i, A);
     __syncthreads();
+    DMARK(1);
     for (int level = 1; level <= 4; level++) {
       DS::ph_clear(tid, sh);
       __syncthreads();
@@ -303,6 +309,7 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
       __syncthreads();
       if (!more) break;
     }
+    DMARK(2);
     if (sh.overflow) {
       DS::ph_fallback(tid, sh, i, A);
     } else {
@@ -314,15 +321,21 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
       __syncthreads();
       DS::ph_bm_count(tid, sh);
       __syncthreads();
-      DS::ph_bm_scan(tid, sh);
+      DS::ph_bm_scan1(tid, sh);
+      __syncthreads();
+      DS::ph_bm_scan2(tid, sh);
+      __syncthreads();
+      DS::ph_bm_scan3(tid, sh);
       __syncthreads();
       DS::ph_bm_emit(tid, sh);
       __syncthreads();
+      DMARK(3);
       DS::ph_pick(tid, sh, i, A);
       __syncthreads();
       DS::ph_emit(tid, sh, i, A);
     }
     __syncthreads();
+    DMARK(4);
     if (tid == 0) {
       StepFullLocal L;
       State st = sh.st;
@@ -338,9 +351,13 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
       }
     }
     __syncthreads();
+    DMARK(5);
     if (obs198) write_obs198_cta(&sh.st, lut, 1, i, obs198);
     __syncthreads();
+    DMARK(6);
+    if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + 7] = sh.count;
   }
+#undef DMARK
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {

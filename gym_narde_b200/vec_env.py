@@ -16,7 +16,7 @@ from . import _cabi
 
 class VecNardeEnv:
     def __init__(self, num_envs, seed=0, rules="full", reward=None, max_actions=64, device="cuda",
-                 env_base=0, autoreset=True, max_episode_steps=1000, write_actions=True):
+                 env_base=0, autoreset=True, max_episode_steps=1000, write_actions=True, chunks=None):
         torch = _cabi.require_cuda()
         _cabi.load()
         if rules not in ("full", "reference"):
@@ -49,7 +49,17 @@ class VecNardeEnv:
         self.terminated = self.done.view(torch.bool)
         self.truncated = self.trunc.view(torch.bool)
         self.stats = torch.zeros(_cabi.NUM_STATS, dtype=torch.int64, device=dev)
-        self.workspace = torch.zeros(n + 1, dtype=torch.int32, device=dev)  # deferred-turn list (see narde_b200.h)
+        # The fused step is launched as `chunks` independent sub-batches (multiples of the 128-env CTA
+        # tile) on separate CUDA streams: the small CTA-per-env kernel for order-dependent doubles turns
+        # of one chunk overlaps the main kernel of the next, and the tail of one wave is filled by
+        # another chunk's CTAs.  Results do not depend on the chunking (global env ids).
+        if chunks is None:
+            chunks = 2 if n >= 32768 else 1
+        per = -(-n // (128 * chunks)) * 128
+        self._chunks = [(b, min(b + per, n)) for b in range(0, n, per)]
+        self._streams = [torch.cuda.Stream(device=dev) for _ in self._chunks[1:]]
+        # deferred-turn lists (see narde_b200.h: (n + 1) int32 per call)
+        self._workspaces = [torch.zeros(e - b + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
         self.info = {"dice": self.dice, "counts": self.counts, "chosen": self.chosen}
         if rules == "full":
             self.obs = torch.zeros((n, 198), dtype=torch.float32, device=dev)
@@ -110,12 +120,22 @@ class VecNardeEnv:
         if self.rules == "full":
             flags = (_cabi.REWARD_MOVER12 if self.reward_mode == "mover12" else 0) | (
                 _cabi.AUTORESET if self.autoreset else 0)
-            _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, self.step_count, dice_in=dice,
-                            action_idx=actions, actions=self.actions if self.write_actions else None,
-                            counts=self.counts, dice_out=self.dice, chosen=self.chosen, obs198=self.obs,
-                            reward=self.reward, done=self.done, stats=self.stats, flags=flags,
-                            max_episode_steps=self.max_episode_steps, truncated=self.trunc,
-                            workspace=self.workspace)
+            main = t.cuda.current_stream(self.device)
+            for k, (b, e) in enumerate(self._chunks):
+                stream = main if k == 0 else self._streams[k - 1]
+                if k:
+                    stream.wait_stream(main)
+                with t.cuda.stream(stream):
+                    _cabi.step_full(self.lo[b:e], self.hi[b:e], self.env_base + b, self.seed, self.step_count,
+                                    dice_in=None if dice is None else dice[b:e],
+                                    action_idx=None if actions is None else actions[b:e],
+                                    actions=self.actions[b:e] if self.write_actions else None,
+                                    counts=self.counts[b:e], dice_out=self.dice[b:e], chosen=self.chosen[b:e],
+                                    obs198=self.obs[b:e], reward=self.reward[b:e], done=self.done[b:e],
+                                    stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
+                                    truncated=self.trunc[b:e], workspace=self._workspaces[k])
+            for s_ in self._streams:
+                main.wait_stream(s_)
         else:
             if actions is None:
                 raise ValueError("rules='reference' needs action codes [N,2]")

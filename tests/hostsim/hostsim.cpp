@@ -193,7 +193,9 @@ static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float*
       for (int t = 0; t < BLK; t++) DS::ph_bm_clear(t, sh);
       for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_set(t, sh);
       for (int t = 0; t < BLK; t++) DS::ph_bm_count(t, sh);
-      for (int t = 0; t < BLK; t++) DS::ph_bm_scan(t, sh);
+      for (int t = 0; t < BLK; t++) DS::ph_bm_scan1(t, sh);
+      for (int t = 0; t < BLK; t++) DS::ph_bm_scan2(t, sh);
+      for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_scan3(t, sh);
       for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_emit(t, sh);
       for (int t = 0; t < BLK; t++) DS::ph_pick(t, sh, i, A);
       for (int t = BLK - 1; t >= 0; t--) DS::ph_emit(t, sh, i, A);

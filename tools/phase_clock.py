@@ -12,7 +12,7 @@ env.reset()
 for _ in range(300):
     env.step()
 nb = (E + 127) // 128
-buf = torch.zeros((nb, 16), dtype=torch.int64, device="cuda")
+buf = torch.zeros((max(nb, 2048) + 148, 16), dtype=torch.int64, device="cuda")
 lib = _cabi.load()
 lib.narde_debug_set_clock_buffer.argtypes = [C.c_void_p]
 assert lib.narde_debug_set_clock_buffer(C.c_void_p(buf.data_ptr())) == 0
@@ -25,7 +25,8 @@ for _ in range(5):
     torch.cuda.synchronize()
     acc.append(buf.cpu().numpy().copy())
 lib.narde_debug_set_clock_buffer(None)
-a = np.stack(acc).astype(np.float64)          # [steps, blocks, 16]
+full = np.stack(acc).astype(np.float64)
+a = full[:, :nb]          # [steps, blocks, 16]
 d = np.diff(a[:, :, :10], axis=2)              # phase durations in cycles
 tot = a[:, :, 9] - a[:, :, 0]
 print("blocks", nb, "block total cycles: mean %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f" % (
@@ -36,3 +37,15 @@ for k, nm in enumerate(names):
         nm, x.mean(), np.percentile(x, 50), np.percentile(x, 99), x.max(), 100 * x.sum() / tot.sum()))
 span = a[:, :, 9].max(axis=1) - a[:, :, 0].min(axis=1)
 print("kernel span cycles per step (max end - min start, per-SM clocks differ slightly):", span)
+
+dd = full[:, 2048:2048 + 148]
+ok = dd[:, :, 6] > dd[:, :, 0]
+dn = ["init", "search", "order", "pick+emit", "complete", "obs"]
+for st in range(dd.shape[0]):
+    x = dd[st][ok[st]]
+    if len(x) == 0:
+        continue
+    dur = np.diff(x[:, :7], axis=1)
+    w = np.argmax(x[:, 6] - x[:, 0])
+    print("step", st, "deferred envs", len(x), "slowest total %.0f cycles count %d:" % (x[w, 6] - x[w, 0], x[w, 7]),
+          " ".join("%s=%.0f" % (n, v) for n, v in zip(dn, dur[w])), "| mean total %.0f" % (x[:, 6] - x[:, 0]).mean())
