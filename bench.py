@@ -216,7 +216,7 @@ def run_cuda_arm(args):
 
     # ---- end-to-end arm: host action indices in (pinned) -> step -> reward/done out (pinned) ----
     h_idx = torch.randint(0, 1 << 20, (E,), dtype=torch.int32).pin_memory()
-    d_idx = torch.zeros(E, dtype=torch.int32, device=dev)
+    d_idx = env.action_in                                    # persistent device input of VecNardeEnv.step
     h_rew = torch.zeros(E, dtype=torch.float32).pin_memory()
     h_done = torch.zeros(E, dtype=torch.uint8).pin_memory()
 

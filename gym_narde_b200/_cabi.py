@@ -32,7 +32,8 @@ _SIGNATURES = {
     "narde_step_ref": ([_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_enumerate": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp], _int),
     "narde_step_full": ([_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                         _vp, _vp, _i32, _i32, _vp, _vp], _int),
+                         _vp, _vp, _i32, _i32, _vp, _vp, _vp], _int),
+    "narde_advance_counter": ([_vp, _vp], _int),
     "narde_obs198": ([_vp, _vp, _i64, _vp, _vp], _int),
     "narde_obs24": ([_vp, _vp, _i64, _vp, _vp], _int),
     "narde_apply_actions": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp], _int),
@@ -150,7 +151,7 @@ def enumerate_actions(lo, hi, dice, actions, counts, overflow=None):
 
 def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actions=None, counts=None,
               dice_out=None, chosen=None, obs198=None, reward=None, done=None, stats=None, flags=0,
-              max_episode_steps=0, truncated=None, workspace=None):
+              max_episode_steps=0, truncated=None, workspace=None, step_dev=None):
     import torch
 
     cap = actions.shape[1] if actions is not None else 0
@@ -163,8 +164,15 @@ def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actio
         _ptr(dice_out, torch.uint8, "dice_out"), _ptr(chosen, torch.int64, "chosen"),
         _ptr(obs198, torch.float32, "obs198"), _ptr(reward, torch.float32, "reward"),
         _ptr(done, torch.uint8, "done"), _ptr(truncated, torch.uint8, "truncated"), _ptr(stats, torch.int64, "stats"),
-        flags, max_episode_steps, _ptr(workspace, torch.int32, "workspace"), _stream())
+        flags, max_episode_steps, _ptr(workspace, torch.int32, "workspace"), _ptr(step_dev, torch.int64, "step_dev"),
+        _stream())
     _check(rc, "narde_step_full")
+
+
+def advance_counter(counter):
+    import torch
+
+    _check(load().narde_advance_counter(_ptr(counter, torch.int64, "counter"), _stream()), "narde_advance_counter")
 
 
 def obs198(lo, hi, out):

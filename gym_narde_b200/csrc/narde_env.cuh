@@ -77,6 +77,9 @@ struct StepFullArgs {
   // defer_count[0] = number of deferred envs, defer_list[k] = their local indices
   int32_t* defer_count;
   int32_t* defer_list;
+  // optional device-resident step counter (overrides `step`): lets the whole step be replayed as a
+  // CUDA graph with frozen kernel arguments
+  const uint64_t* step_dev;
 };
 
 struct StepFullLocal {  // per-env contributions to the stats vector

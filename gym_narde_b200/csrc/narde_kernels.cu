@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(kThreads) k_enumerate(const uint4* lo, const u
   if (overflow) overflow[i] = c > cap ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, int64_t n, StepFullArgs A, float* obs198, int64_t* stats) {
+__global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, int64_t n, StepFullArgs A_in, float* obs198, int64_t* stats) {
+  StepFullArgs A = A_in;
+  if (A.step_dev) A.step = *A.step_dev;
   __shared__ State sm[kThreads];
   int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
   int64_t i = row0 + threadIdx.x;
@@ -192,9 +194,11 @@ __device__ unsigned long long* g_dbg_clk = nullptr;
 // Fused full-rules step, CTA-cooperative (narde_block.cuh): the phases run with a CTA barrier
 // between them; everything between the state load and the Box(198) store stays in shared memory.
 template <int BLK>
-__global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int64_t n, StepFullArgs A, float* obs198,
+__global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int64_t n, StepFullArgs A_in, float* obs198,
                                                       int64_t* stats) {
   typedef BlockStep<BLK> BS;
+  StepFullArgs A = A_in;
+  if (A.step_dev) A.step = *A.step_dev;
   __shared__ BlockShared<BLK> sh;
   const int tid = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.x * BLK;
@@ -278,8 +282,10 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
 // Exact doubles turns handed over by k_step_full_v2 (narde_deferred.cuh): persistent CTAs walk the
 // deferred list, one environment per CTA at a time.
 template <int BLK>
-__global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A, float* obs198, int64_t* stats) {
+__global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A_in, float* obs198, int64_t* stats) {
   typedef DeferredStep<BLK> DS;
+  StepFullArgs A = A_in;
+  if (A.step_dev) A.step = *A.step_dev;
   extern __shared__ __align__(16) unsigned char dsm_raw[];
   DeferredShared& sh = *reinterpret_cast<DeferredShared*>(dsm_raw);
   __shared__ float4 lut[16];
@@ -419,6 +425,10 @@ __global__ void __launch_bounds__(kThreads) k_block_rule(const int8_t* boards, i
   out[i] = violates_block(own, opp) ? 1 : 0;
 }
 
+bool g_deferred_attr_set = false;
+
+__global__ void k_advance_counter(uint64_t* ctr) { *ctr += 1; }
+
 inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 inline int launch_status() { return (int)cudaGetLastError(); }
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -427,7 +437,13 @@ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 extern "C" {
 
-int narde_abi_version(void) { return NARDE_ABI_VERSION; }
+int narde_abi_version(void) {
+  // one-time function attributes are set here (outside any stream capture)
+  if (!g_deferred_attr_set &&
+      cudaFuncSetAttribute(k_step_deferred<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeferredShared)) == cudaSuccess)
+    g_deferred_attr_set = true;
+  return NARDE_ABI_VERSION;
+}
 const char* narde_build_arch(void) { return "sm_100a"; }
 
 int narde_reset_masked(void* lo, void* hi, const uint8_t* mask, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
@@ -476,7 +492,7 @@ int narde_enumerate(const void* lo, const void* hi, const uint8_t* dice, int64_t
 int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
                     const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
                     uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
-                    int32_t flags, int32_t max_episode_steps, int32_t* workspace, void* stream) {
+                    int32_t flags, int32_t max_episode_steps, int32_t* workspace, const uint64_t* step_dev, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || cap < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
   if (obs198 && (((uintptr_t)obs198) & 7u) != 0) return -1;
@@ -499,6 +515,7 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.max_episode_steps = max_episode_steps;
   A.defer_count = nullptr;
   A.defer_list = nullptr;
+  A.step_dev = step_dev;
   if (flags & NARDE_PER_THREAD_KERNEL) {
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
     return launch_status();
@@ -512,12 +529,11 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   }
   k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
   if (workspace) {
-    static bool attr_set = false;
     const int dyn = (int)sizeof(DeferredShared);
-    if (!attr_set) {
+    if (!g_deferred_attr_set) {
       cudaError_t e = cudaFuncSetAttribute(k_step_deferred<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
       if (e != cudaSuccess) return (int)e;
-      attr_set = true;
+      g_deferred_attr_set = true;
     }
     k_step_deferred<512><<<148, 512, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
   }
@@ -557,6 +573,12 @@ int narde_violates_block_rule(const int8_t* boards, int64_t n, uint8_t* out, voi
   if (n == 0) return 0;
   if (n < 0 || !boards || !out) return -1;
   k_block_rule<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(boards, n, out);
+  return launch_status();
+}
+
+int narde_advance_counter(uint64_t* counter, void* stream) {
+  if (!counter) return -1;
+  k_advance_counter<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
   return launch_status();
 }
 

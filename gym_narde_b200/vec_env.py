@@ -16,7 +16,8 @@ from . import _cabi
 
 class VecNardeEnv:
     def __init__(self, num_envs, seed=0, rules="full", reward=None, max_actions=64, device="cuda",
-                 env_base=0, autoreset=True, max_episode_steps=1000, write_actions=True, chunks=None):
+                 env_base=0, autoreset=True, max_episode_steps=1000, write_actions=True, chunks=None,
+                 graph=True):
         torch = _cabi.require_cuda()
         _cabi.load()
         if rules not in ("full", "reference"):
@@ -35,6 +36,8 @@ class VecNardeEnv:
         self.max_episode_steps = int(max_episode_steps)
         self.write_actions = bool(write_actions)
         self.step_count = 0  # Philox step counter (global, shared by all envs)
+        self.use_graph = bool(graph)
+        self._graphs = {}    # (action ptr, dice ptr) -> captured CUDA graph of one step
         n, dev = self.num_envs, self.device
         self.lo = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
         self.hi = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
@@ -60,6 +63,9 @@ class VecNardeEnv:
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._chunks[1:]]
         # deferred-turn lists (see narde_b200.h: (n + 1) int32 per call)
         self._workspaces = [torch.zeros(e - b + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
+        # device-resident copy of step_count: kernel arguments stay frozen, so a step is one graph replay
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.action_in = torch.zeros(n, dtype=torch.int32, device=dev)   # persistent policy input (graph-replayable)
         self.info = {"dice": self.dice, "counts": self.counts, "chosen": self.chosen}
         if rules == "full":
             self.obs = torch.zeros((n, 198), dtype=torch.float32, device=dev)
@@ -74,6 +80,7 @@ class VecNardeEnv:
         if seed is not None:
             self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.step_count = 0
+        self._step_dev.zero_()
         _cabi.reset(self.lo, self.hi, self.env_base, self.seed, 0)
         self.stats.zero_()
         return self.observe(), {}
@@ -120,22 +127,19 @@ class VecNardeEnv:
         if self.rules == "full":
             flags = (_cabi.REWARD_MOVER12 if self.reward_mode == "mover12" else 0) | (
                 _cabi.AUTORESET if self.autoreset else 0)
-            main = t.cuda.current_stream(self.device)
-            for k, (b, e) in enumerate(self._chunks):
-                stream = main if k == 0 else self._streams[k - 1]
-                if k:
-                    stream.wait_stream(main)
-                with t.cuda.stream(stream):
-                    _cabi.step_full(self.lo[b:e], self.hi[b:e], self.env_base + b, self.seed, self.step_count,
-                                    dice_in=None if dice is None else dice[b:e],
-                                    action_idx=None if actions is None else actions[b:e],
-                                    actions=self.actions[b:e] if self.write_actions else None,
-                                    counts=self.counts[b:e], dice_out=self.dice[b:e], chosen=self.chosen[b:e],
-                                    obs198=self.obs[b:e], reward=self.reward[b:e], done=self.done[b:e],
-                                    stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
-                                    truncated=self.trunc[b:e], workspace=self._workspaces[k])
-            for s_ in self._streams:
-                main.wait_stream(s_)
+            # graphs are replayed only for frozen argument sets: the random-policy step and the step
+            # driven by the persistent input buffer `self.action_in`; anything else is launched directly
+            graphable = self.use_graph and dice is None and (actions is None or actions is self.action_in)
+            if graphable:
+                key = "random" if actions is None else "action_in"
+                g = self._graphs.get(key)
+                if g is None:
+                    g = self._capture(actions, dice, flags)
+                    self._graphs[key] = g
+                g.replay()
+            else:
+                self._step_dev.fill_(self.step_count)
+                self._launch_full(actions, dice, flags)
         else:
             if actions is None:
                 raise ValueError("rules='reference' needs action codes [N,2]")
@@ -145,6 +149,38 @@ class VecNardeEnv:
             _cabi.step_ref(self.lo, self.hi, dice, actions, self.obs, self.reward, self.done,
                            max_episode_steps=self.max_episode_steps, truncated=self.trunc)
         return self.obs, self.reward, self.terminated, self.truncated, self.info
+
+    def _launch_full(self, actions, dice, flags):
+        """Enqueue one fused step: every chunk on its own stream (fork/join around the current stream)."""
+        t = self.torch
+        main = t.cuda.current_stream(self.device)
+        for k, (b, e) in enumerate(self._chunks):
+            stream = main if k == 0 else self._streams[k - 1]
+            if k:
+                stream.wait_stream(main)
+            with t.cuda.stream(stream):
+                _cabi.step_full(self.lo[b:e], self.hi[b:e], self.env_base + b, self.seed, 0,
+                                dice_in=None if dice is None else dice[b:e],
+                                action_idx=None if actions is None else actions[b:e],
+                                actions=self.actions[b:e] if self.write_actions else None,
+                                counts=self.counts[b:e], dice_out=self.dice[b:e], chosen=self.chosen[b:e],
+                                obs198=self.obs[b:e], reward=self.reward[b:e], done=self.done[b:e],
+                                stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
+                                truncated=self.trunc[b:e], workspace=self._workspaces[k], step_dev=self._step_dev)
+        for s_ in self._streams:
+            main.wait_stream(s_)
+
+    def _capture(self, actions, dice, flags):
+        """Capture one step (counter advance + all chunk launches) into a CUDA graph.  The first replay
+        performs the step, so nothing is executed here."""
+        t = self.torch
+        self._step_dev.fill_(self.step_count - 1)
+        t.cuda.synchronize(self.device)
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g):
+            _cabi.advance_counter(self._step_dev)
+            self._launch_full(actions, dice, flags)
+        return g
 
     def episode_stats(self):
         """Device-side counters as a dict (one D2H copy)."""
@@ -160,6 +196,8 @@ class VecNardeEnv:
         self.lo.copy_(sd["lo"])
         self.hi.copy_(sd["hi"])
         self.seed, self.step_count, self.env_base = sd["seed"], sd["step_count"], sd["env_base"]
+        self._step_dev.fill_(self.step_count)
+        self._graphs.clear()  # the seed is a frozen kernel argument
 
     def close(self):
         pass

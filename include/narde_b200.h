@@ -105,12 +105,15 @@ int narde_enumerate(const void *lo, const void *hi, const uint8_t *dice, int64_t
  * Any of actions, counts, dice_out, obs198, reward, done, truncated, chosen, stats may be NULL.
  * workspace: optional scratch of (n + 1) int32 owned by the caller.  With it, the rare doubles
  * turns in which the 6-prime block rule makes the move ORDER matter are handed to a second,
- * CTA-per-environment kernel (same results, shorter tail); without it they are resolved inline. */
+ * CTA-per-environment kernel (same results, shorter tail); without it they are resolved inline.
+ * step_dev: optional device-resident step counter that overrides `step`, so that a captured CUDA
+ * graph of the step can be replayed (advance it with narde_advance_counter inside the graph). */
 int narde_step_full(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
                     const uint8_t *dice_in, const int32_t *action_idx, int32_t cap,
                     uint64_t *actions, int32_t *counts, uint8_t *dice_out, uint64_t *chosen,
                     float *obs198, float *reward, uint8_t *done, uint8_t *truncated, int64_t *stats,
-                    int32_t flags, int32_t max_episode_steps, int32_t *workspace, void *stream);
+                    int32_t flags, int32_t max_episode_steps, int32_t *workspace, const uint64_t *step_dev,
+                    void *stream);
 
 /* Observations of the current states: Box(198) float32 (README.md:44-102) / the reference's
  * mover-perspective int32[24] (narde_env.py:24-25). */
@@ -121,6 +124,9 @@ int narde_obs24(const void *lo, const void *hi, int64_t n, int32_t *obs24, void 
  * transition + termination/reward/switch as in narde_step_full.  acts: [n] u64. */
 int narde_apply_actions(void *lo, void *hi, const uint64_t *acts, int64_t n, int32_t flags,
                         float *reward, uint8_t *done, void *stream);
+
+/* *counter += 1 on the device (one tiny launch); see step_dev above. */
+int narde_advance_counter(uint64_t *counter, void *stream);
 
 /* The turn's dice for every environment from the counter-based stream the fused step uses:
  * Philox4x32-10(key = seed, ctr = (env_base+i, step_lo, step_hi, 0)), die = 1 + ((w*6) >> 32) on

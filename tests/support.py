@@ -229,7 +229,7 @@ class CudaBackend:
                             action_idx=self._up(None if action_idx is None else np.asarray(action_idx, np.int32)),
                             actions=actions, counts=counts, dice_out=dice, chosen=chosen, obs198=obs, reward=rew,
                             done=done, stats=stats, flags=flags, max_episode_steps=max_episode_steps, truncated=trunc,
-                            workspace=ws)
+                            workspace=ws)  # noqa
         self._sync_back(lo, hi, tlo, thi)
         return {
             "actions": actions.cpu().numpy().view(np.uint64) if want_actions else None,
