@@ -171,7 +171,8 @@ def run_cuda_arm(args):
     from gym_narde_b200 import VecNardeEnv, _cabi
 
     E, K, W = args.envs_per_gpu, args.steps, args.warmup
-    env = VecNardeEnv(E, seed=SEED, max_actions=args.cap, env_base=rank * E, device=dev)
+    env = VecNardeEnv(E, seed=SEED, max_actions=args.cap, env_base=rank * E, device=dev, chunks=args.chunks,
+                      graph=not args.no_graph)
     env.reset()
     for _ in range(args.burn_in):           # de-correlate game phases: steady-state self-play mix
         env.step()
@@ -309,6 +310,8 @@ def main():
     ap.add_argument("--cap", type=int, default=64)
     ap.add_argument("--burn-in", type=int, default=300)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--chunks", type=int, default=None)
+    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -77,6 +77,7 @@ struct StepFullArgs {
   // defer_count[0] = number of deferred envs, defer_list[k] = their local indices
   int32_t* defer_count;
   int32_t* defer_list;
+  int32_t* defer_flags;  // optional [n]: 1 where the env was deferred (lets the Box(198) pass skip those rows)
   // optional device-resident step counter (overrides `step`): lets the whole step be replayed as a
   // CUDA graph with frozen kernel arguments
   const uint64_t* step_dev;

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   PHASE_MARK(7);
   StepFullLocal L;
   BS::ph_finish(tid, sh, valid, i, A, L);
+  if (A.defer_flags && valid) A.defer_flags[i] = (int32_t)sh.defer[tid];
   __syncthreads();
   PHASE_MARK(8);
   if (valid) st_state(lo, hi, i, sh.st[tid]);
@@ -378,6 +379,24 @@ __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint
   write_obs198_cta(sm, lut, rows, row0, obs198);
 }
 
+// Box(198) pass of the split step: rows of deferred envs are written by k_step_deferred
+__global__ void __launch_bounds__(kThreads) k_obs198_masked(const uint4* lo, const uint4* hi, int64_t n, float* obs198,
+                                                           const int32_t* flags) {
+  __shared__ State sm[kThreads];
+  __shared__ uint32_t skip[kThreads];
+  __shared__ float4 lut[16];
+  int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
+  int64_t i = row0 + threadIdx.x;
+  obs_lut_init(lut);
+  if (i < n) {
+    sm[threadIdx.x] = ld_state(lo, hi, i);
+    skip[threadIdx.x] = (uint32_t)flags[i];
+  }
+  __syncthreads();
+  int rows = (int)min((int64_t)blockDim.x, n - row0);
+  write_obs198_cta(sm, lut, rows, row0, obs198, skip);
+}
+
 __global__ void __launch_bounds__(kThreads) k_obs24(const uint4* lo, const uint4* hi, int64_t n, int32_t* o24) {
   __shared__ State sm[kThreads];
   int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
@@ -426,6 +445,9 @@ __global__ void __launch_bounds__(kThreads) k_block_rule(const int8_t* boards, i
 }
 
 bool g_deferred_attr_set = false;
+// library-owned side stream + events for the fork/join inside narde_step_full (created once)
+cudaStream_t g_side_stream = nullptr;
+cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
 
 __global__ void k_advance_counter(uint64_t* ctr) { *ctr += 1; }
 
@@ -442,6 +464,10 @@ int narde_abi_version(void) {
   if (!g_deferred_attr_set &&
       cudaFuncSetAttribute(k_step_deferred<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeferredShared)) == cudaSuccess)
     g_deferred_attr_set = true;
+  if (!g_side_stream && cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) == cudaSuccess) {
+    cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming);
+  }
   return NARDE_ABI_VERSION;
 }
 const char* narde_build_arch(void) { return "sm_100a"; }
@@ -516,18 +542,32 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.defer_count = nullptr;
   A.defer_list = nullptr;
   A.step_dev = step_dev;
+  A.defer_flags = nullptr;
   if (flags & NARDE_PER_THREAD_KERNEL) {
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
     return launch_status();
   }
-  if (workspace) {  // [0] = number of deferred envs, [1..n] = their indices
+  // With a workspace ([0] = number of deferred envs, [1..n] = their indices, [n+1..2n] = flags) the
+  // step is split: main kernel without the Box(198) pass, then the exact kernel for deferred envs
+  // and the observation pass of all other envs run CONCURRENTLY (fork/join on a side stream).
+  const bool split = workspace && obs198 && g_side_stream && !(flags & NARDE_NO_SPLIT);
+  if (workspace) {
     if ((((uintptr_t)workspace) & 3u) != 0) return -1;
     A.defer_count = workspace;
     A.defer_list = workspace + 1;
+    if (split) A.defer_flags = workspace + 1 + n;
     cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
   }
-  k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
+  k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A,
+                                                                              split ? nullptr : obs198, stats);
+  if (split) {
+    cudaEventRecord(g_ev_fork, (cudaStream_t)stream);
+    cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0);
+    k_obs198_masked<<<grid_for(n), kThreads, 0, g_side_stream>>>((const uint4*)lo, (const uint4*)hi, n, obs198,
+                                                                 A.defer_flags);
+    cudaEventRecord(g_ev_join, g_side_stream);
+  }
   if (workspace) {
     const int dyn = (int)sizeof(DeferredShared);
     if (!g_deferred_attr_set) {
@@ -537,6 +577,7 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     }
     k_step_deferred<512><<<148, 512, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
   }
+  if (split) cudaStreamWaitEvent((cudaStream_t)stream, g_ev_join, 0);
   return launch_status();
 }
 

@@ -57,12 +57,12 @@ class VecNardeEnv:
         # of one chunk overlaps the main kernel of the next, and the tail of one wave is filled by
         # another chunk's CTAs.  Results do not depend on the chunking (global env ids).
         if chunks is None:
-            chunks = 2 if n >= 32768 else 1
+            chunks = 1
         per = -(-n // (128 * chunks)) * 128
         self._chunks = [(b, min(b + per, n)) for b in range(0, n, per)]
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._chunks[1:]]
         # deferred-turn lists (see narde_b200.h: (n + 1) int32 per call)
-        self._workspaces = [torch.zeros(e - b + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
+        self._workspaces = [torch.zeros(2 * (e - b) + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
         # device-resident copy of step_count: kernel arguments stay frozen, so a step is one graph replay
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.action_in = torch.zeros(n, dtype=torch.int32, device=dev)   # persistent policy input (graph-replayable)

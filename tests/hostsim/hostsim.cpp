@@ -103,7 +103,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
                  uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
                  int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
-                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
+                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr, nullptr};
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
     StepFullLocal L;
@@ -221,7 +221,7 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
                     uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
                     int32_t flags, int32_t max_episode_steps, int32_t* workspace, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
-                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
+                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr, nullptr};
   if (workspace) {
     workspace[0] = 0;
     A.defer_count = workspace;
