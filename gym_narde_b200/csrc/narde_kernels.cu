@@ -547,10 +547,10 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
     return launch_status();
   }
-  // With a workspace ([0] = number of deferred envs, [1..n] = their indices, [n+1..2n] = flags) the
-  // step is split: main kernel without the Box(198) pass, then the exact kernel for deferred envs
-  // and the observation pass of all other envs run CONCURRENTLY (fork/join on a side stream).
-  const bool split = workspace && obs198 && g_side_stream && !(flags & NARDE_NO_SPLIT);
+  // Workspace: [0] = number of deferred envs, [1..n] = their indices, [n+1..2n] = flags.
+  // NARDE_SPLIT_OBS (experimental, measured slower on B200): main kernel without the Box(198) pass, then
+  // the exact kernel for deferred envs and the observation pass of the other envs on two streams.
+  const bool split = workspace && obs198 && g_side_stream && (flags & NARDE_SPLIT_OBS);
   if (workspace) {
     if ((((uintptr_t)workspace) & 3u) != 0) return -1;
     A.defer_count = workspace;
