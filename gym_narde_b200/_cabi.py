@@ -34,6 +34,7 @@ _SIGNATURES = {
     "narde_step_full": ([_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp, _i32, _i32, _vp, _vp, _vp], _int),
     "narde_advance_counter": ([_vp, _vp], _int),
+    "narde_mlp_forward": ([_vp, _i64, _vp, _vp, _vp, _vp], _int),
     "narde_obs198": ([_vp, _vp, _i64, _vp, _vp], _int),
     "narde_obs24": ([_vp, _vp, _i64, _vp, _vp], _int),
     "narde_apply_actions": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp], _int),

@@ -9,7 +9,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libnarde_b200.so")
-SOURCES = ["narde_kernels.cu"]
+SOURCES = ["narde_kernels.cu", "narde_mlp.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
     os.path.join("..", "..", "include", "narde_b200.h")]
 

@@ -1,0 +1,54 @@
+"""GPU (-m gpu): the tcgen05 afterstate-scoring MLP against the fp32 torch reference of the same net.
+
+Architecture = DecomposedDQN.forward(x) with state_size 198 (train_deepq_pytorch.py:184-236),
+torch.manual_seed(0) default nn.Linear init (BASELINE config 5: random-init weights).  This is the
+one floating-point kernel of the path: tolerance (bf16 operands, fp32 accumulate) is stated below."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL = 2e-2          # |q_kernel - q_fp32| on Q-values of magnitude ~0.1-0.5
+ARGMAX_AGREEMENT = 0.97  # bf16 rounding flips near-ties; reported, not hidden
+
+
+def _reference_net():
+    import torch
+    import torch.nn as nn
+    torch.manual_seed(0)
+    feature_network = nn.Sequential(nn.Linear(198, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU())
+    move1_head = nn.Linear(256, 576)
+    return feature_network.cuda(), move1_head.cuda()
+
+
+def test_mlp_matches_fp32_reference_on_real_observations():
+    import torch
+    from gym_narde_b200 import VecNardeEnv
+    from gym_narde_b200.mlp import AfterstateMLP
+    fn, head = _reference_net()
+    mlp = AfterstateMLP.from_module(fn, head)
+    env = VecNardeEnv(4096, seed=3)
+    env.reset()
+    for _ in range(40):
+        obs, *_ = env.step()
+    for rows in (4096, 1, 127, 129, 1000):
+        x = obs[:rows].contiguous()
+        q = mlp(x)
+        with torch.no_grad():
+            ref = head(fn(x))
+        err = (q - ref).abs().max().item()
+        assert err < ABS_TOL, (rows, err)
+        if rows == 4096:
+            agree = (q.argmax(1) == ref.argmax(1)).float().mean().item()
+            assert agree > ARGMAX_AGREEMENT, agree
+    # exactness of the data path: with bf16-representable weights/inputs the only error is accumulation order
+    torch.manual_seed(1)
+    xb = torch.randint(0, 2, (512, 198), device="cuda").float()
+    for lin in (fn[0], fn[2], head):
+        lin.weight.data = lin.weight.data.to(torch.bfloat16).float()
+    mlp2 = AfterstateMLP.from_module(fn, head)
+    with torch.no_grad():
+        h1 = torch.relu(fn[0](xb)).to(torch.bfloat16).float()
+        h2 = torch.relu(fn[2](h1)).to(torch.bfloat16).float()
+        ref2 = head(h2)
+    assert (mlp2(xb) - ref2).abs().max().item() < 2e-3
