@@ -28,7 +28,7 @@ constexpr int kKC = 64;          // K elements per weight stage
 constexpr int kStages = 3;       // weight stages in flight
 constexpr int kStageBytes = 256 * kKC * 2;  // 32 KB: a 256-row (N) x 64 (K) bf16 block
 constexpr int kABytes = kRows * kK * 2;     // 64 KB activation tile
-constexpr int kThreads = 128;
+constexpr int kThreads = 512;      // 16 warps: TMEM lane quarter = warp & 3, column group = warp >> 2
 
 // shared memory map (dynamic): [A0 | A1 | B stages | barriers]
 constexpr int kSmemA0 = 0;
@@ -209,22 +209,31 @@ k_mlp_forward(const float* __restrict__ x, int64_t rows, Layer L1, Layer L2, Lay
       const uint32_t a_in = layer == 0 ? a0 : a1;
       uint8_t* a_out = smem + (layer == 0 ? kSmemA1 : kSmemA0);
       gemm_block(a_in, L.w, kH, tmem, bsm, bar_full, bar_empty, bar_acc, it, acc_phase, tid);
-      // epilogue: thread = row (TMEM lane), 256 columns in 8 chunks of 32
-      const int r = tid;
+      // epilogue: row = TMEM lane = (warp & 3) * 32 + lane; the 4 column groups (warp >> 2) take 64 columns each
+      const int r = (warp & 3) * 32 + (tid & 31);
+      const int cg = warp >> 2;
 #pragma unroll 1
-      for (int cb = 0; cb < kH / 32; cb++) {
+      for (int cb = cg * 2; cb < cg * 2 + 2; cb++) {
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
+        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32), v);
+        const float4* b4 = reinterpret_cast<const float4*>(L.bias + cb * 32);
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-          __nv_bfloat16 h[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            int col = cb * 32 + g * 8 + j;
-            float f = __uint_as_float(v[g * 8 + j]) + L.bias[col];
-            h[j] = __float2bfloat16(f > 0.0f ? f : 0.0f);
-          }
-          *reinterpret_cast<uint4*>(a_out + tile_off(kRows, r, cb * 32 + g * 8)) = *reinterpret_cast<uint4*>(h);
+          float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
+          float f0 = __uint_as_float(v[g * 8 + 0]) + ba.x, f1 = __uint_as_float(v[g * 8 + 1]) + ba.y;
+          float f2 = __uint_as_float(v[g * 8 + 2]) + ba.z, f3 = __uint_as_float(v[g * 8 + 3]) + ba.w;
+          float f4 = __uint_as_float(v[g * 8 + 4]) + bb.x, f5 = __uint_as_float(v[g * 8 + 5]) + bb.y;
+          float f6 = __uint_as_float(v[g * 8 + 6]) + bb.z, f7 = __uint_as_float(v[g * 8 + 7]) + bb.w;
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(f0, 0.0f), fmaxf(f1, 0.0f));
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(f2, 0.0f), fmaxf(f3, 0.0f));
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(f4, 0.0f), fmaxf(f5, 0.0f));
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(f6, 0.0f), fmaxf(f7, 0.0f));
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          pk.z = *reinterpret_cast<uint32_t*>(&p2);
+          pk.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(a_out + tile_off(kRows, r, cb * 32 + g * 8)) = pk;
         }
       }
       tc_fence_before();
@@ -238,21 +247,23 @@ k_mlp_forward(const float* __restrict__ x, int64_t rows, Layer L1, Layer L2, Lay
     for (int nb0 = 0; nb0 < kOut; nb0 += 256) {
       const int nb = kOut - nb0 < 256 ? kOut - nb0 : 256;
       gemm_block(a0, L3.w + (size_t)nb0 * kK * 2, nb, tmem, bsm, bar_full, bar_empty, bar_acc, it, acc_phase, tid);
-      const int64_t gr = row0 + tid;
+      const int64_t gr = row0 + (warp & 3) * 32 + (tid & 31);
+      const int cg = warp >> 2, per = nb >= 128 ? nb / 128 : 1;  // 32-column chunks per column group
 #pragma unroll 1
-      for (int cb = 0; cb < nb / 32; cb++) {
+      for (int cb = cg * per; cb < cg * per + per && cb * 32 < nb; cb++) {
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32), v);
+        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32), v);
         if (gr < rows) {
           float* dst = q + gr * kOut + nb0 + cb * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(L3.bias + nb0 + cb * 32);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[j]) + L3.bias[nb0 + cb * 32 + j];
-            o.y = __uint_as_float(v[j + 1]) + L3.bias[nb0 + cb * 32 + j + 1];
-            o.z = __uint_as_float(v[j + 2]) + L3.bias[nb0 + cb * 32 + j + 2];
-            o.w = __uint_as_float(v[j + 3]) + L3.bias[nb0 + cb * 32 + j + 3];
-            *reinterpret_cast<float4*>(dst + j) = o;
+          for (int j = 0; j < 8; j++) {
+            float4 b = __ldg(b4 + j), o;
+            o.x = __uint_as_float(v[4 * j]) + b.x;
+            o.y = __uint_as_float(v[4 * j + 1]) + b.y;
+            o.z = __uint_as_float(v[4 * j + 2]) + b.z;
+            o.w = __uint_as_float(v[4 * j + 3]) + b.w;
+            *reinterpret_cast<float4*>(dst + 4 * j) = o;
           }
         }
       }
