@@ -40,21 +40,38 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_POLLER = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+pci = sys.argv[1]
+h = n.nvmlDeviceGetHandleByPciBusId(pci.encode()) if pci != "-" else n.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+print("max", n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        print(time.time(), n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), int(n.nvmlDeviceGetCurrentClocksEventReasons(h)),
+              n.nvmlDeviceGetPowerUsage(h) / 1000.0, flush=True)
+    except Exception as e:
+        print("err", e, flush=True)
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + clock-event (throttle) reasons sampled DURING the timed region.
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    A helper PROCESS polls NVML every ~1 ms for the whole run (a thread would be starved by the launch
+    loop holding the GIL; `nvidia-smi -lms` is too coarse for a timed region of tens of milliseconds);
+    mark()/stop() keep the samples whose timestamps fall inside the timed region."""
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+            ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
+
+    def __init__(self, gpu_index, pci_bus_id=None):
         self.rows = []
-        self.proc = None
-
-    def start(self):
+        self.sm_max = None
+        self.t0 = self.t1 = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen([sys.executable, "-c", _POLLER, pci_bus_id or "-", str(gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -63,28 +80,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            f = line.split()
+            try:
+                if f[0] == "max":
+                    self.sm_max = float(f[1])
+                elif f[0] != "err":
+                    self.rows.append((float(f[0]), float(f[1]), int(f[2]), float(f[3])))
+            except (ValueError, IndexError):
+                pass
+
+    def wait_ready(self, timeout=20.0):
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout and self.proc.poll() is None:
+            time.sleep(0.01)
+
+    def start(self):
+        self.t0 = time.time()
 
     def stop(self):
+        self.t1 = time.time()
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        time.sleep(0.01)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        rows = [r for r in self.rows if self.t0 <= r[0] <= self.t1]
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": statistics.median(r[1] for r in rows) if rows else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(k for k, b in self.BITS if bits & b), "samples": len(rows),
+                "power_w_max": max(r[3] for r in rows) if rows else None,
+                "source": "NVML polled every ~1 ms by a helper process; samples inside the timed region only"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -203,7 +229,13 @@ def run_cuda_arm(args):
     for _ in range(W):
         env.step()
     stats0 = env.stats.clone()
-    sampler = ClockSampler(local_rank)
+    props = torch.cuda.get_device_properties(dev)
+    try:
+        pci = "%08X:%02X:%02X.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+    except Exception:
+        pci = None
+    sampler = ClockSampler(local_rank, pci)
+    sampler.wait_ready()
     barrier()
     sampler.start()
     t_wall0 = time.perf_counter()
@@ -216,14 +248,15 @@ def run_cuda_arm(args):
     A = dstats[5] / float(E * K)
 
     # ---- end-to-end arm: host action indices in (pinned) -> step -> reward/done out (pinned) ----
-    h_idx = torch.randint(0, 1 << 20, (E,), dtype=torch.int32).pin_memory()
+    # uniformly random u32 fractions (fraction=True): the same uniform self-play policy as the device arm
+    h_idx = torch.randint(-(1 << 31), (1 << 31) - 1, (E,), dtype=torch.int64).to(torch.int32).pin_memory()
     d_idx = env.action_in                                    # persistent device input of VecNardeEnv.step
     h_rew = torch.zeros(E, dtype=torch.float32).pin_memory()
     h_done = torch.zeros(E, dtype=torch.uint8).pin_memory()
 
     def e2e_step():
         d_idx.copy_(h_idx, non_blocking=True)               # H2D: this step's inputs (action indices)
-        obs, rew, term, trunc, info = env.step(d_idx)        # public API call
+        obs, rew, term, trunc, info = env.step(d_idx, fraction=True)   # public API call
         h_rew.copy_(rew, non_blocking=True)                  # D2H: this step's results
         h_done.copy_(env.done, non_blocking=True)
 
@@ -233,6 +266,20 @@ def run_cuda_arm(args):
     ms_e2e = timed_loop(e2e_step, K)
     barrier()
     total_e2e = sum(ms_e2e)
+
+    # ---- end-to-end with the whole Box(198) batch copied to the host as well (a host-side policy) ----
+    h_obs = torch.empty((E, 198), dtype=torch.float32).pin_memory()
+
+    def e2e_obs_step():
+        e2e_step()
+        h_obs.copy_(env.obs, non_blocking=True)
+
+    k_obs = max(3, min(K, 20))
+    for _ in range(2):
+        e2e_obs_step()
+    barrier()
+    ms_e2e_obs = timed_loop(e2e_obs_step, k_obs)
+    barrier()
 
     # ---- config 2 side measurement (4096 lock-step envs, same kernel) ----
     small = VecNardeEnv(4096, seed=SEED, max_actions=args.cap, env_base=0, device=dev)
@@ -283,7 +330,10 @@ def run_cuda_arm(args):
                          "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 5 * E,
                     "ms_per_step": total_e2e_max / K,
-                    "note": "VecNardeEnv.step(action_idx): pinned int32 action indices H2D, reward f32 + done u8 D2H every step; Box(198) stays in HBM for the device-resident policy"},
+                    "note": "VecNardeEnv.step(action_idx, fraction=True): pinned int32 action choices (u32 fractions of the legal list) H2D, reward f32 + done u8 D2H every step; Box(198) stays in HBM for the device-resident policy"},
+            "e2e_obs_to_host": {"value": world * E * k_obs / (sum(ms_e2e_obs) * 1e-3), "unit": UNIT, "steps": k_obs,
+                                "d2h_bytes_per_step": 5 * E + 792 * E, "ms_per_step": sum(ms_e2e_obs) / k_obs,
+                                "note": "same as e2e plus the full Box(198) float32 batch copied D2H every step (PCIe-bound; rank 0's time)"},
             "gpu_launches": K * 2 * len(env._chunks), "wall_ms": wall_ms, "clocks": clocks,
             "config2_4096_envs": {"value": 4096 * len(ms_small) / (sum(ms_small) * 1e-3), "unit": UNIT,
                                   "ms_per_step": sum(ms_small) / len(ms_small)},

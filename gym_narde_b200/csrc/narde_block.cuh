@@ -555,18 +555,16 @@ struct BlockStep {
     sh.part[2][tid] = k == K_ND ? sh.etotal[tid] : 0u;
     sh.part[3][tid] = k == K_D ? sh.etotal[tid] : 0u;
   }
+  // hand-over of order-dependent doubles turns: the list is complete once every CTA is past this
+  // phase, which is when the exact kernel (a programmatic dependent launch) may start
+  static NHD void ph_defer_push(int tid, const Sh& sh, bool valid, int64_t i, const StepFullArgs& A) {
+    if (valid && sh.defer[tid]) A.defer_list[gl_fetch_add(A.defer_count, 1)] = (int32_t)i;
+  }
   static NHD void ph_env_bases(int tid, Sh& sh) {
     sh.ebase[tid] = sh.kind[tid] == K_ND ? sh.base[2][tid] : sh.base[3][tid];
   }
   static NHD uint32_t pick_index(const Sh& sh, int e, int64_t i, uint32_t count, const StepFullArgs& A) {
-    if (count == 0) return 0;
-    if (A.action_idx) {
-      int idx = A.action_idx[i];
-      if (idx < 0) idx = 0;
-      if (idx >= (int)count) idx = (int)count - 1;
-      return (uint32_t)idx;
-    }
-    return mulhi32(sh.rnd[e], count);
+    return pick_action_index(A, i, sh.rnd[e], count);
   }
   // ---- phase 7: write the action lists in canonical order, capture the chosen action ------
   static NHD void ph_emit(int tid, Sh& sh, int64_t row0, const StepFullArgs& A) {
@@ -663,10 +661,7 @@ struct BlockStep {
       if (A.truncated) A.truncated[i] = 0;
       return;
     }
-    if (sh.defer[tid]) {  // handed to the exact CTA-per-env kernel; this kernel leaves the env untouched
-      A.defer_list[gl_fetch_add(A.defer_count, 1)] = (int32_t)i;
-      return;
-    }
+    if (sh.defer[tid]) return;  // handed to the exact CTA-per-env kernel (ph_defer_push); left untouched here
     State s = sh.st[tid];
     int player = s.turn();
     int a = sh.a[tid], b = sh.b[tid];

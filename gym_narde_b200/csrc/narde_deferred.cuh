@@ -274,18 +274,7 @@ struct DeferredStep {
     if (tid != 0) return;
     uint32_t count = sh.depth ? sh.n_cur : 0u;
     sh.count = count;
-    uint32_t idx = 0;
-    if (count) {
-      if (A.action_idx) {
-        int v = A.action_idx[i];
-        if (v < 0) v = 0;
-        if (v >= (int)count) v = (int)count - 1;
-        idx = (uint32_t)v;
-      } else {
-        idx = mulhi32(sh.rnd, count);
-      }
-    }
-    sh.idx = idx;
+    sh.idx = pick_action_index(A, i, sh.rnd, count);
   }
   // safety net (a level overflowed kDefCap; never observed): one thread walks the tree exactly
   static NHD void ph_fallback(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
@@ -297,16 +286,8 @@ struct DeferredStep {
     uint32_t count = (uint32_t)enumerate_turn(P, sh.d, sh.d, ft, sk);
     sh.count = count;
     sh.depth = 4;
-    uint32_t idx = 0;
+    uint32_t idx = pick_action_index(A, i, sh.rnd, count);
     if (count) {
-      if (A.action_idx) {
-        int v = A.action_idx[i];
-        if (v < 0) v = 0;
-        if (v >= (int)count) v = (int)count - 1;
-        idx = (uint32_t)v;
-      } else {
-        idx = mulhi32(sh.rnd, count);
-      }
       PickSink pk = {(int)idx, 0, ACT_EMPTY};
       enumerate_turn(P, sh.d, sh.d, ft, pk);
       sh.chosen = pk.picked;

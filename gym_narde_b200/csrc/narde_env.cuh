@@ -10,6 +10,7 @@ enum : int {
   F_REWARD_MOVER12 = 1,
   F_AUTORESET = 2,
   F_HALF_MOVES_ONLY = 4,
+  F_ACTION_FRACTION = 32,
   DONE_TERMINATED = 1,
   DONE_TRUNCATED = 2,
 };
@@ -77,11 +78,24 @@ struct StepFullArgs {
   // defer_count[0] = number of deferred envs, defer_list[k] = their local indices
   int32_t* defer_count;
   int32_t* defer_list;
-  int32_t* defer_flags;  // optional [n]: 1 where the env was deferred (lets the Box(198) pass skip those rows)
   // optional device-resident step counter (overrides `step`): lets the whole step be replayed as a
   // CUDA graph with frozen kernel arguments
   const uint64_t* step_dev;
 };
+
+// The index of the action to play among `count` legal ones: the caller's action_idx[i] (clamped; or,
+// with F_ACTION_FRACTION, a u32 fraction f -> floor(f * count / 2^32)), else Philox-uniform from rnd.
+NHD uint32_t pick_action_index(const StepFullArgs& A, int64_t i, uint32_t rnd, uint32_t count) {
+  if (count == 0) return 0;
+  if (A.action_idx) {
+    int32_t v = A.action_idx[i];
+    if (A.flags & F_ACTION_FRACTION) return mulhi32((uint32_t)v, count);
+    if (v < 0) v = 0;
+    if (v >= (int32_t)count) v = (int32_t)count - 1;
+    return (uint32_t)v;
+  }
+  return mulhi32(rnd, count);
+}
 
 struct StepFullLocal {  // per-env contributions to the stats vector
   int count;
@@ -128,14 +142,7 @@ NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal
 
   uint64_t act = ACT_EMPTY;
   if (count > 0) {
-    int idx;
-    if (A.action_idx) {
-      idx = A.action_idx[i];
-      if (idx < 0) idx = 0;
-      if (idx >= count) idx = count - 1;
-    } else {
-      idx = (int)mulhi32(rnd.z, (uint32_t)count);
-    }
+    int idx = (int)pick_action_index(A, i, rnd.z, (uint32_t)count);
     if (slice && idx < A.cap) {
       act = slice[idx];
     } else {  // not stored: enumerate again and pick the idx-th

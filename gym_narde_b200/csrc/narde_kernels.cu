@@ -6,6 +6,7 @@
 // shared-memory copy of the CTA's states so that global stores are contiguous 16-byte lanes.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/narde_b200.h"
 #define NARDE_DEBUG_HOOKS 1
@@ -233,7 +234,14 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   __syncthreads();
   PHASE_MARK(5);
   BS::ph_env_totals(tid, sh);
+  if (A.defer_list) {
+    BS::ph_defer_push(tid, sh, valid, i, A);
+    __threadfence();  // the list entry is visible device-wide before this CTA lets the dependent grid go
+  }
   __syncthreads();
+  // Programmatic dependent launch: k_step_deferred may start as soon as every CTA is past this point,
+  // i.e. while the action lists and Box(198) rows of the other envs are still being written.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   BS::ph_scan1(tid, sh);
   __syncthreads();
   BS::ph_scan2(tid, sh);
@@ -247,10 +255,10 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   PHASE_MARK(7);
   StepFullLocal L;
   BS::ph_finish(tid, sh, valid, i, A, L);
-  if (A.defer_flags && valid) A.defer_flags[i] = (int32_t)sh.defer[tid];
   __syncthreads();
   PHASE_MARK(8);
-  if (valid) st_state(lo, hi, i, sh.st[tid]);
+  // deferred envs belong to k_step_deferred, which may already be running: never store their state here
+  if (valid && !sh.defer[tid]) st_state(lo, hi, i, sh.st[tid]);
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
     int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
@@ -292,13 +300,15 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
   __shared__ float4 lut[16];
   obs_lut_init(lut);
   const int tid = threadIdx.x;
-  const int n_def = *A.defer_count;
+  // launched as a programmatic dependent of k_step_full_v2: every CTA of it has published its deferred
+  // envs (fence + trigger) before this grid starts; read the list through L2
+  const int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
 #define DMARK(k)                                                                                      \
   do {                                                                                                \
     if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + (k)] = clock64();      \
   } while (0)
   for (int q = blockIdx.x; q < n_def; q += gridDim.x) {
-    const int64_t i = A.defer_list[q];
+    const int64_t i = reinterpret_cast<volatile const int32_t*>(A.defer_list)[q];
     State s;
     DMARK(0);
     if (tid == 0) s = ld_state(lo, hi, i);
@@ -365,6 +375,8 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
     if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + 7] = sh.count;
   }
 #undef DMARK
+  // stream order: this grid must not complete before its primary has (the next step follows it)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {
@@ -377,24 +389,6 @@ __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint
   __syncthreads();
   int rows = (int)min((int64_t)blockDim.x, n - row0);
   write_obs198_cta(sm, lut, rows, row0, obs198);
-}
-
-// Box(198) pass of the split step: rows of deferred envs are written by k_step_deferred
-__global__ void __launch_bounds__(kThreads) k_obs198_masked(const uint4* lo, const uint4* hi, int64_t n, float* obs198,
-                                                           const int32_t* flags) {
-  __shared__ State sm[kThreads];
-  __shared__ uint32_t skip[kThreads];
-  __shared__ float4 lut[16];
-  int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
-  int64_t i = row0 + threadIdx.x;
-  obs_lut_init(lut);
-  if (i < n) {
-    sm[threadIdx.x] = ld_state(lo, hi, i);
-    skip[threadIdx.x] = (uint32_t)flags[i];
-  }
-  __syncthreads();
-  int rows = (int)min((int64_t)blockDim.x, n - row0);
-  write_obs198_cta(sm, lut, rows, row0, obs198, skip);
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs24(const uint4* lo, const uint4* hi, int64_t n, int32_t* o24) {
@@ -445,9 +439,8 @@ __global__ void __launch_bounds__(kThreads) k_block_rule(const int8_t* boards, i
 }
 
 bool g_deferred_attr_set = false;
-// library-owned side stream + events for the fork/join inside narde_step_full (created once)
-cudaStream_t g_side_stream = nullptr;
-cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+// programmatic dependent launch of the exact kernel (NARDE_NO_PDL=1 in the environment disables it: A/B timing)
+bool g_use_pdl = true;
 
 __global__ void k_advance_counter(uint64_t* ctr) { *ctr += 1; }
 
@@ -460,14 +453,16 @@ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 extern "C" {
 
 int narde_abi_version(void) {
+  static bool env_read = false;
+  if (!env_read) {
+    const char* v = getenv("NARDE_NO_PDL");
+    if (v && v[0] == '1') g_use_pdl = false;
+    env_read = true;
+  }
   // one-time function attributes are set here (outside any stream capture)
   if (!g_deferred_attr_set &&
       cudaFuncSetAttribute(k_step_deferred<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeferredShared)) == cudaSuccess)
     g_deferred_attr_set = true;
-  if (!g_side_stream && cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) == cudaSuccess) {
-    cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming);
-  }
   return NARDE_ABI_VERSION;
 }
 const char* narde_build_arch(void) { return "sm_100a"; }
@@ -542,32 +537,20 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.defer_count = nullptr;
   A.defer_list = nullptr;
   A.step_dev = step_dev;
-  A.defer_flags = nullptr;
   if (flags & NARDE_PER_THREAD_KERNEL) {
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
     return launch_status();
   }
-  // Workspace: [0] = number of deferred envs, [1..n] = their indices, [n+1..2n] = flags.
-  // NARDE_SPLIT_OBS (experimental, measured slower on B200): main kernel without the Box(198) pass, then
-  // the exact kernel for deferred envs and the observation pass of the other envs on two streams.
-  const bool split = workspace && obs198 && g_side_stream && (flags & NARDE_SPLIT_OBS);
+  // Workspace: [0] = number of deferred envs, [1..n] = their indices.
   if (workspace) {
     if ((((uintptr_t)workspace) & 3u) != 0) return -1;
     A.defer_count = workspace;
     A.defer_list = workspace + 1;
-    if (split) A.defer_flags = workspace + 1 + n;
     cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
   }
   k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A,
-                                                                              split ? nullptr : obs198, stats);
-  if (split) {
-    cudaEventRecord(g_ev_fork, (cudaStream_t)stream);
-    cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0);
-    k_obs198_masked<<<grid_for(n), kThreads, 0, g_side_stream>>>((const uint4*)lo, (const uint4*)hi, n, obs198,
-                                                                 A.defer_flags);
-    cudaEventRecord(g_ev_join, g_side_stream);
-  }
+                                                                              obs198, stats);
   if (workspace) {
     const int dyn = (int)sizeof(DeferredShared);
     if (!g_deferred_attr_set) {
@@ -575,9 +558,23 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
       if (e != cudaSuccess) return (int)e;
       g_deferred_attr_set = true;
     }
-    k_step_deferred<512><<<148, 512, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
+    if (g_use_pdl) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(148);
+      cfg.blockDim = dim3(512);
+      cfg.dynamicSmemBytes = (size_t)dyn;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, k_step_deferred<512>, (uint4*)lo, (uint4*)hi, A, obs198, stats);
+      if (e != cudaSuccess) return (int)e;
+    } else {
+      k_step_deferred<512><<<148, 512, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
+    }
   }
-  if (split) cudaStreamWaitEvent((cudaStream_t)stream, g_ev_join, 0);
   return launch_status();
 }
 

@@ -62,7 +62,7 @@ class VecNardeEnv:
         self._chunks = [(b, min(b + per, n)) for b in range(0, n, per)]
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._chunks[1:]]
         # deferred-turn lists (see narde_b200.h: (n + 1) int32 per call)
-        self._workspaces = [torch.zeros(2 * (e - b) + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
+        self._workspaces = [torch.zeros((e - b) + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
         # device-resident copy of step_count: kernel arguments stay frozen, so a step is one graph replay
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.action_in = torch.zeros(n, dtype=torch.int32, device=dev)   # persistent policy input (graph-replayable)
@@ -114,11 +114,14 @@ class VecNardeEnv:
         _cabi.enumerate_actions(self.lo, self.hi, dice, self.actions, self.counts, self.overflow)
         return self.actions, self.counts, self.overflow
 
-    def step(self, actions=None, dice=None):
+    def step(self, actions=None, dice=None, fraction=False):
         """One lock-step turn for all envs.
 
         rules="full":      actions = int32 [N] indices into get_valid_actions (None = uniform random
-                           from the Philox stream); dice = optional [N,2] uint8 override.
+                           from the Philox stream); dice = optional [N,2] uint8 override.  With
+                           fraction=True the int32 values are read as u32 fractions f and env i plays
+                           action floor(f * count_i / 2^32) (a policy that cannot know the counts of a
+                           roll made inside the step, e.g. a host-side sampler).
         rules="reference": actions = int32 [N,2] codes (from*24+to) exactly as NardeEnv.step takes
                            them; dice default to the Philox stream.
         Returns (obs, reward, terminated, truncated, info)."""
@@ -126,12 +129,12 @@ class VecNardeEnv:
         self.step_count += 1
         if self.rules == "full":
             flags = (_cabi.REWARD_MOVER12 if self.reward_mode == "mover12" else 0) | (
-                _cabi.AUTORESET if self.autoreset else 0)
+                _cabi.AUTORESET if self.autoreset else 0) | (_cabi.ACTION_FRACTION if fraction and actions is not None else 0)
             # graphs are replayed only for frozen argument sets: the random-policy step and the step
             # driven by the persistent input buffer `self.action_in`; anything else is launched directly
             graphable = self.use_graph and dice is None and (actions is None or actions is self.action_in)
             if graphable:
-                key = "random" if actions is None else "action_in"
+                key = "random" if actions is None else ("action_in", bool(fraction))
                 g = self._graphs.get(key)
                 if g is None:
                     g = self._capture(actions, dice, flags)

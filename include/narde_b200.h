@@ -43,7 +43,7 @@ extern "C" {
 #define NARDE_REWARD_MOVER12 1   /* reward 1/2 to the mover (narde_env.py:134-141); default: README +1 iff WHITE wins */
 #define NARDE_AUTORESET 2        /* reset a finished environment in the same step (obs = first obs of the new game) */
 #define NARDE_PER_THREAD_KERNEL 8 /* narde_step_full: use the thread-per-env kernel (A/B testing; same results) */
-#define NARDE_SPLIT_OBS 16       /* narde_step_full (experimental): Box(198) pass as a separate kernel on a side stream */
+#define NARDE_ACTION_FRACTION 32  /* narde_step_full: action_idx[i] is a u32 fraction f; plays action floor(f * count / 2^32) */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 
 /* done[i] = 1 when the episode terminated (a player bore off 15 checkers); truncated[i] = 1 when
@@ -104,9 +104,10 @@ int narde_enumerate(const void *lo, const void *hi, const uint8_t *dice, int64_t
  *   choice (action_idx[i], clamped; NULL = Philox-uniform) -> apply -> termination / reward
  *   -> player switch -> optional auto-reset -> Box(198) observation (README.md:44-102).
  * Any of actions, counts, dice_out, obs198, reward, done, truncated, chosen, stats may be NULL.
- * workspace: optional scratch of (2n + 1) int32 owned by the caller.  With it, the rare doubles
+ * workspace: optional scratch of (n + 1) int32 owned by the caller.  With it, the rare doubles
  * turns in which the 6-prime block rule makes the move ORDER matter are handed to a second,
- * CTA-per-environment kernel (same results, shorter tail); without it they are resolved inline.
+ * CTA-per-environment kernel (a programmatic dependent launch that overlaps the tail of the main
+ * kernel; same results, shorter tail); without it they are resolved inline.
  * step_dev: optional device-resident step counter that overrides `step`, so that a captured CUDA
  * graph of the step can be replayed (advance it with narde_advance_counter inside the graph). */
 int narde_step_full(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,

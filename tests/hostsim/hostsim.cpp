@@ -103,7 +103,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
                  uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
                  int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
-                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr, nullptr};
+                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
     StepFullLocal L;
@@ -146,7 +146,7 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
     for (int t = 0; t < BLK; t++) { BS::ph_scan3(t, sh); BS::ph_l2_bases(t, sh); }
     for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh, A.defer_list != nullptr);
-    for (int t = 0; t < BLK; t++) BS::ph_env_totals(t, sh);
+    for (int t = 0; t < BLK; t++) { BS::ph_env_totals(t, sh); BS::ph_defer_push(t, sh, row0 + t < n, row0 + t, A); }
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
     for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_env_bases(t, sh); }
@@ -221,7 +221,7 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
                     uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
                     int32_t flags, int32_t max_episode_steps, int32_t* workspace, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
-                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr, nullptr};
+                    chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
   if (workspace) {
     workspace[0] = 0;
     A.defer_count = workspace;

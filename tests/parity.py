@@ -262,8 +262,11 @@ def check_step_ref_lockstep(backend, n, T, seed):
     return sum(finished)
 
 
-def check_step_full_lockstep(backend, n, T, seed, env_base=77, cap=32, flags=2):
-    """Fused full-rules step (Philox dice + Philox action + auto-reset) vs the oracle."""
+def check_step_full_lockstep(backend, n, T, seed, env_base=77, cap=32, flags=2, action_mode=None):
+    """Fused full-rules step (Philox dice + Philox action + auto-reset) vs the oracle.
+    action_mode: None = Philox-uniform choice inside the step; "index" = caller's int32 indices
+    (negative / too large values are clamped); "fraction" = caller's u32 fractions (flag 32)."""
+    rng = np.random.default_rng(seed ^ 0xAC71)
     lo, hi = backend.reset(n, env_base=env_base, seed=seed, step=0)
     envs = [O.OracleEnv() for _ in range(n)]
     for i, e in enumerate(envs):
@@ -273,7 +276,13 @@ def check_step_full_lockstep(backend, n, T, seed, env_base=77, cap=32, flags=2):
     reward_mode = 1 if (flags & 1) else 0
     idle = [False] * n  # without auto-reset a finished env idles: done stays set, nothing else changes
     for t in range(T):
-        out = backend.step_full(lo, hi, env_base=env_base, seed=seed, step=t + 1, cap=cap, flags=flags)
+        given = None
+        if action_mode == "index":
+            given = rng.integers(-3, 40, n).astype(np.int32)
+        elif action_mode == "fraction":
+            given = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32).view(np.int32)
+        out = backend.step_full(lo, hi, env_base=env_base, seed=seed, step=t + 1, cap=cap, action_idx=given,
+                                flags=flags | (32 if action_mode == "fraction" else 0))
         u = S.unpack_states(lo, hi)
         exp_stats = np.zeros(8, np.int64)
         for i, e in enumerate(envs):
@@ -290,6 +299,10 @@ def check_step_full_lockstep(backend, n, T, seed, env_base=77, cap=32, flags=2):
             acts, nact = O.turn_enumerate(mv, st[1] if pl == 1 else st[2], d1, d2, st[3] if pl == 1 else st[4])
             assert nact == out["counts"][i], (t, i, nact, out["counts"][i])
             idx = (w * nact) >> 32 if nact else 0
+            if nact and action_mode == "index":
+                idx = min(max(int(given[i]), 0), nact - 1)
+            elif nact and action_mode == "fraction":
+                idx = (int(given[i].view(np.uint32)) * nact) >> 32
             obs, rew, done, _ = e.full_step((d1, d2), idx, reward_mode)
             assert rew == out["reward"][i] and done == bool(out["done"][i] & 1), (t, i)
             exp_stats[5] += nact

@@ -221,7 +221,7 @@ class CudaBackend:
         done = t.zeros(n, dtype=t.uint8, device=self.dev)
         stats = t.zeros(8, dtype=t.int64, device=self.dev)
         trunc = t.zeros(n, dtype=t.uint8, device=self.dev)
-        ws = t.zeros(2 * n + 1, dtype=t.int32, device=self.dev) if (getattr(self, "defer", True) and not (flags & 8)) else None
+        ws = t.zeros(n + 1, dtype=t.int32, device=self.dev) if (getattr(self, "defer", True) and not (flags & 8)) else None
         if getattr(self, "per_thread", False):
             flags |= 8  # NARDE_PER_THREAD_KERNEL
         self.cabi.step_full(tlo, thi, env_base, seed, step,

@@ -66,6 +66,12 @@ def test_step_full_lockstep_mover_reward_no_autoreset(hostsim):
     P.check_step_full_lockstep(hostsim, 48, 220, 99, cap=4, flags=1)
 
 
+def test_step_full_caller_actions_index_and_fraction(hostsim):
+    # caller-chosen actions: clamped int32 indices, and u32 fractions of the legal list (flag 32)
+    P.check_step_full_lockstep(hostsim, 64, 150, 31, action_mode="index")
+    P.check_step_full_lockstep(hostsim, 64, 150, 32, action_mode="fraction")
+
+
 def test_obs198(hostsim):
     lo, hi = P.pack_corpus(P.selfplay_corpus(10, 21))
     P.check_obs198(hostsim, lo, hi)

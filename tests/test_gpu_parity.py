@@ -69,6 +69,11 @@ def test_gpu_step_full_mover_reward_no_autoreset(cuda_backend):
     P.check_step_full_lockstep(cuda_backend, 300, 220, 99, cap=4, flags=1)
 
 
+def test_gpu_step_full_caller_actions_index_and_fraction(cuda_backend):
+    P.check_step_full_lockstep(cuda_backend, 512, 150, 31, action_mode="index")
+    P.check_step_full_lockstep(cuda_backend, 512, 150, 32, action_mode="fraction")
+
+
 def test_gpu_obs198(cuda_backend):
     lo, hi = P.pack_corpus(P.selfplay_corpus(30, 113))
     P.check_obs198(cuda_backend, lo, hi)
