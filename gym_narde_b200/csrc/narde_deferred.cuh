@@ -1,13 +1,17 @@
 // narde_deferred.cuh -- exact doubles turns when the 6-prime block rule bites (CTA per env).
 //
-// The block kernel (narde_block.cuh) hands over the rare doubles turns (~0.05% of env steps) in
+// The block kernel (narde_block.cuh) hands over the rare doubles turns (~0.2% of env steps) in
 // which some board of the move tree violates the block rule (narde.py:139-184): there the set of
 // playable multisets depends on the ORDER of the half-moves.  Here one CTA owns one such
 // environment and does what the rule text says, level by level: the multisets of j sources that
 // are reachable by j legal half-moves through legal boards are expanded to level j+1 by every
-// legal half-move (narde.py:64-89), de-duplicated in a shared-memory hash set (the board depends
-// only on the multiset).  The deepest non-empty level (<= 4) is the answer (max-dice rule),
-// sorted by the canonical key; representative orderings come from dbl_order_search.
+// legal half-move (narde.py:64-89).  The board depends only on the multiset, so a level is a SET
+// of multisets, kept as a dense bitmap indexed by the multiset's canonical key (base-24 digits
+// 23 - source, ascending): atomicOr is the de-duplication, the bitmap is already in canonical
+// order, and its population count is the number of legal turns.  The deepest non-empty level
+// (<= 4) is the answer (max-dice rule).  Only the first `cap` actions and the chosen one are
+// materialised (rank -> multiset by a select on the bitmap), with the representative ordering =
+// the first legal ordering when higher sources are tried first.
 //
 // Written as phases like narde_block.cuh; the host harness emulates the CTA.
 #pragma once
@@ -15,18 +19,14 @@
 
 namespace narde {
 
-constexpr int kDefCap = 4096;    // multisets per level (observed maximum ~1500)
-constexpr int kDefHash = 8192;   // open addressing, power of two
+// Multisets of j sources are sorted tuples of digits x = 23 - source (ascending), i.e. j-combinations
+// with repetition of 24 values: C(24+j-1, j) = 24, 300, 2600, 17550 for j = 1..4.  Their rank in
+// lexicographic order (combinatorial number system) is the bitmap index, so the level-4 set takes
+// 549 words instead of 24^4 / 32, and a CTA needs ~16 KB of shared memory.
+constexpr int kDefCap = 2600;                     // multisets per expandable level (<= C(26,3))
+constexpr int kDefBmWords = (17550 + 31) / 32;    // 549
+constexpr int kDefEmit = 256;                     // ranks materialised per emit pass
 
-NHD uint32_t sm_cas(uint32_t* p, uint32_t expect, uint32_t val) {
-#if defined(__CUDA_ARCH__)
-  return atomicCAS(p, expect, val);
-#else
-  uint32_t o = *p;
-  if (o == expect) *p = val;
-  return o;
-#endif
-}
 NHD uint32_t sm_fetch_add(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return atomicAdd(p, v);
@@ -36,25 +36,54 @@ NHD uint32_t sm_fetch_add(uint32_t* p, uint32_t v) {
   return o;
 #endif
 }
+NHD uint32_t sm_fetch_or(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return atomicOr(p, v);
+#else
+  uint32_t o = *p;
+  *p |= v;
+  return o;
+#endif
+}
+NHD void sm_min(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
 
-struct DeferredShared {
+// binomials C(v, i), i = 1..4 (v < 32)
+NHD uint32_t binom(uint32_t v, int i) {
+  switch (i) {
+    case 1: return v;
+    case 2: return v * (v - 1u) / 2u;
+    case 3: return v < 2u ? 0u : v * (v - 1u) * (v - 2u) / 6u;
+    default: return v < 3u ? 0u : v * (v - 1u) * (v - 2u) * (v - 3u) / 24u;
+  }
+}
+NHD uint32_t multiset_total(int j) { return binom((uint32_t)(24 + j - 1), j); }
+
+template <int BLK>
+struct DeferredSharedT {
   State st;
   uint32_t own, opp, nlo0, nlo1, nhi;
   int32_t d, H, player, d1, d2;
   uint32_t rnd;
-  uint32_t n_cur, n_next, depth, overflow, which;  // which: 0 -> level list in a[], 1 -> in b[]
+  uint32_t n_cur, n_next, depth, any4, which;  // which: 0 -> current level list in a[], 1 -> in b[]
   uint32_t count, idx;
   uint64_t chosen;
-  uint32_t part[1024], base[1024], part2[32];
-  // a | b | hash are contiguous: once the search is over, b..hash is reused as a 24^4-bit bitmap
-  uint32_t a[kDefCap], b[kDefCap];
-  uint32_t hash[kDefHash];
+  uint32_t part[BLK], base[BLK], part2[33];
+  uint32_t bm[kDefBmWords];
+  uint32_t ecode[kDefEmit], ebest[kDefEmit];   // emit pass: multisets whose descending order is illegal
+  uint32_t efail[kDefEmit], n_fail;
+  uint16_t a[kDefCap], b[kDefCap];             // level lists (levels 1..3: codes of <= 15 bits)
 };
-static_assert(kDefCap + kDefHash >= (24 * 24 * 24 * 24 + 31) / 32, "bitmap must fit in b + hash");
 
 template <int BLK>
 struct DeferredStep {
-  typedef DeferredShared Sh;
+  typedef DeferredSharedT<BLK> Sh;
+  static constexpr int WARPS = BLK / 32;
 
   static NHD Pos base_pos(const Sh& sh) {
     Pos P;
@@ -83,6 +112,39 @@ struct DeferredStep {
     if (!placed) out = (out << 5) | x;
     return out;
   }
+  // lexicographic rank of the sorted digit tuple among all j-multisets of 24 values: with
+  // y_i = x_i + i (strictly increasing, < n = 24 + j - 1) and z_m = n - 1 - y_{j-1-m},
+  // rank = C(n, j) - 1 - sum_m C(z_m, m + 1)
+  static NHD uint32_t rank_of(uint32_t code, int j) {
+    const uint32_t n = (uint32_t)(24 + j - 1);
+    uint32_t colex = 0;
+    for (int m = 0; m < j; m++) {
+      int i = j - 1 - m;  // digit index, most significant first
+      uint32_t y = ((code >> (5 * (j - 1 - i))) & 31u) + (uint32_t)i;
+      colex += binom(n - 1u - y, m + 1);
+    }
+    return multiset_total(j) - 1u - colex;
+  }
+  static NHD uint32_t code_of_rank(uint32_t r, int j) {
+    const uint32_t n = (uint32_t)(24 + j - 1);
+    uint32_t c = multiset_total(j) - 1u - r, code = 0;
+    for (int m = j - 1; m >= 0; m--) {  // greedy: largest z_m with C(z_m, m+1) <= c
+      uint32_t v = (uint32_t)m, hi = n - 1u;  // binom(., m+1) is non-decreasing: binary search
+      while (v < hi) {
+        uint32_t mid = (v + hi + 1u) >> 1;
+        if (binom(mid, m + 1) <= c)
+          v = mid;
+        else
+          hi = mid - 1u;
+      }
+      c -= binom(v, m + 1);
+      int i = j - 1 - m;                      // z_m belongs to digit i
+      uint32_t x = (n - 1u - v) - (uint32_t)i;
+      code |= x << (5 * (j - 1 - i));
+    }
+    return code;
+  }
+  static NHD uint32_t bm_words(int level) { return (multiset_total(level) + 31u) >> 5; }
 
   // ---- phase 0 (one thread): load, dice, decode ------------------------------------------
   static NHD void ph_init(int tid, Sh& sh, const State& s_in, int64_t i, const StepFullArgs& A) {
@@ -116,111 +178,109 @@ struct DeferredStep {
     sh.n_cur = 1;
     sh.n_next = 0;
     sh.depth = 0;
-    sh.overflow = 0;
+    sh.any4 = 0;
     sh.which = 0;
     sh.count = 0;
     sh.idx = 0;
     sh.chosen = ACT_EMPTY;
+    sh.n_fail = 0;
   }
-  static NHD void ph_clear(int tid, Sh& sh) {
-    for (int k = tid; k < kDefHash; k += BLK) sh.hash[k] = 0;
+  // ---- clear the bitmap of `level` -----------------------------------------------------------
+  static NHD void ph_clear(int tid, Sh& sh, int level) {
+    uint32_t nw = bm_words(level);
+    for (uint32_t k = (uint32_t)tid; k < nw; k += BLK) sh.bm[k] = 0;
     if (tid == 0) sh.n_next = 0;
   }
-  // ---- expand level `level-1` -> `level` ---------------------------------------------------
+  // one legal half-move s from the level-j node (code, board P): test the after-board, mark the child
+  static NHD void visit_child(Sh& sh, uint16_t* nxt, uint32_t code, int j, const Pos& P, int s, bool risky) {
+    if (risky && violates_block(after_mask(P, s, s - sh.d), P.opp)) return;  // narde.py:78-89
+    uint32_t child = insert(code, j, s);
+    uint32_t r = rank_of(child, j + 1);
+    uint32_t bit = 1u << (r & 31u);
+    uint32_t old = sm_fetch_or(&sh.bm[r >> 5], bit);
+    if (old & bit) return;  // this multiset was already reached through another ordering
+    if (j + 1 < 4) {
+      nxt[sm_fetch_add(&sh.n_next, 1u)] = (uint16_t)child;  // distinct multisets: cannot exceed kDefCap
+    } else {
+      sh.any4 = 1u;
+    }
+  }
+  static NHD uint32_t node_board(const Sh& sh, uint32_t code, int j, Pos* Pout, uint32_t* risky) {
+    int src[4];
+    unpack(code, j, src);
+    Pos P = base_pos(sh);
+    int heads = 0;
+    for (int k = 0; k < j; k++) {  // sources descending: arrivals precede departures
+      P.move(src[k], src[k] - sh.d);
+      heads += src[k] == 23;
+    }
+    uint32_t m = cand_mask(P.own, P.opp, sh.d, heads < sh.H);  // narde.py:64-77
+    *risky = violates_block(P.own, P.opp) ? m : (m & (completing_points(P.own, P.opp) << sh.d));
+    *Pout = P;
+    return m;
+  }
+  // ---- expand level `level-1` -> `level`: narrow levels one warp per node (lane = source point),
+  // wide levels one thread per node ---------------------------------------------------------------
   static NHD void ph_expand(int tid, Sh& sh, int level) {
-    const uint32_t* cur = sh.which ? sh.b : sh.a;
-    uint32_t* nxt = sh.which ? sh.a : sh.b;
+    const uint16_t* cur = sh.which ? sh.b : sh.a;
+    uint16_t* nxt = sh.which ? sh.a : sh.b;
     const int j = level - 1;
-    const int d = sh.d, H = sh.H;
-    for (uint32_t pi = (uint32_t)tid; pi < sh.n_cur; pi += BLK) {
-      uint32_t code = cur[pi];
-      int src[4];
-      unpack(code, j, src);
-      Pos P = base_pos(sh);
-      int heads = 0;
-      for (int k = 0; k < j; k++) {  // sources descending: arrivals precede departures
-        P.move(src[k], src[k] - d);
-        heads += src[k] == 23;
+    const uint32_t n_cur = sh.n_cur;
+    Pos P;
+    uint32_t risky;
+    if (n_cur <= (uint32_t)(4 * WARPS)) {
+      const int lane = tid & 31, warp = tid >> 5;
+      if (lane >= 24) return;
+      for (uint32_t pi = (uint32_t)warp; pi < n_cur; pi += WARPS) {
+        uint32_t code = cur[pi];
+        uint32_t m = node_board(sh, code, j, &P, &risky);
+        if ((m >> lane) & 1u) visit_child(sh, nxt, code, j, P, lane, ((risky >> lane) & 1u) != 0);
       }
-      uint32_t m = cand_mask(P.own, P.opp, d, heads < H);  // narde.py:64-77
-      if (m == 0) continue;
-      uint32_t risky = violates_block(P.own, P.opp) ? m : (m & (completing_points(P.own, P.opp) << d));
-      for (; m; m &= m - 1) {
-        int s = ctz32(m);
-        if (((risky >> s) & 1u) && violates_block(after_mask(P, s, s - d), P.opp)) continue;  // narde.py:78-89
-        uint32_t child = insert(code, j, s);
-        uint32_t key = child + 1u;  // 0 = empty slot
-        uint32_t h = (child * 2654435761u) >> (32 - 13);
-        for (;;) {
-          uint32_t o = sm_cas(&sh.hash[h], 0u, key);
-          if (o == 0u) {  // new multiset
-            uint32_t at = sm_fetch_add(&sh.n_next, 1u);
-            if (at < (uint32_t)kDefCap)
-              nxt[at] = child;
-            else
-              sh.overflow = 1;
-            break;
-          }
-          if (o == key) break;  // already present
-          h = (h + 1) & (kDefHash - 1);
+    } else {
+      for (uint32_t pi = (uint32_t)tid; pi < n_cur; pi += BLK) {
+        uint32_t code = cur[pi];
+        uint32_t m = node_board(sh, code, j, &P, &risky);
+        for (; m; m &= m - 1) {
+          int s = ctz32(m);
+          visit_child(sh, nxt, code, j, P, s, ((risky >> s) & 1u) != 0);
         }
       }
     }
   }
-  // returns true when the level is non-empty and the search continues
+  static NHD bool level_found(const Sh& sh, int level) { return level < 4 ? sh.n_next > 0 : sh.any4 != 0; }
   static NHD void ph_advance(int tid, Sh& sh, int level) {
     if (tid != 0) return;
-    if (sh.n_next > 0) {
+    if (!level_found(sh, level)) return;
+    sh.depth = (uint32_t)level;
+    if (level < 4) {
       sh.which ^= 1u;
-      sh.n_cur = sh.n_next < (uint32_t)kDefCap ? sh.n_next : (uint32_t)kDefCap;
-      sh.depth = (uint32_t)level;
+      sh.n_cur = sh.n_next;
     }
   }
-  // ---- sort the final level ascending: set one bit per multiset in a dense bitmap (index = the
-  // base-24 value of the digits, same order as the key), then compact the bitmap in order --------
-  static NHD uint32_t bm_words(const Sh& sh) {
-    uint32_t bits = 1;
-    for (uint32_t k = 0; k < sh.depth; k++) bits *= 24u;
-    return (bits + 31u) >> 5;
-  }
-  static NHD void ph_to_a(int tid, Sh& sh) {  // the final list must live in a[] (b..hash become the bitmap)
-    if (sh.which)
-      for (uint32_t k = (uint32_t)tid; k < sh.n_cur; k += BLK) sh.a[k] = sh.b[k];
-  }
-  static NHD void ph_bm_clear(int tid, Sh& sh) {
-    uint32_t* bm = sh.b;
-    uint32_t nw = bm_words(sh);
-    for (uint32_t k = (uint32_t)tid; k < nw; k += BLK) bm[k] = 0;
-    if (tid == 0) sh.which = 0;
-  }
-  static NHD void ph_bm_set(int tid, Sh& sh) {
-    uint32_t* bm = sh.b;
+  // the search stopped below level 4: the bitmap now belongs to the (empty, all-zero) next level;
+  // set the bits of the deepest level from its list
+  static NHD void ph_rebuild(int tid, Sh& sh) {
+    const uint16_t* cur = sh.which ? sh.b : sh.a;
     int j = (int)sh.depth;
     for (uint32_t k = (uint32_t)tid; k < sh.n_cur; k += BLK) {
-      uint32_t code = sh.a[k], dense = 0;
-      for (int i = 0; i < j; i++) dense = dense * 24u + ((code >> (5 * (j - 1 - i))) & 31u);
-#if defined(__CUDA_ARCH__)
-      atomicOr(&bm[dense >> 5], 1u << (dense & 31u));
-#else
-      bm[dense >> 5] |= 1u << (dense & 31u);
-#endif
+      uint32_t r = rank_of(cur[k], j);
+      sm_fetch_or(&sh.bm[r >> 5], 1u << (r & 31u));
     }
   }
+  // ---- count the final level: per-thread word ranges, block exclusive scan ---------------------
   static NHD void bm_range(const Sh& sh, int tid, uint32_t* w0, uint32_t* w1) {
-    uint32_t nw = bm_words(sh);
+    uint32_t nw = bm_words((int)sh.depth);
     uint32_t per = (nw + BLK - 1) / BLK;
     uint32_t lo = (uint32_t)tid * per, hi = lo + per;
     *w0 = lo < nw ? lo : nw;
     *w1 = hi < nw ? hi : nw;
   }
   static NHD void ph_bm_count(int tid, Sh& sh) {
-    const uint32_t* bm = sh.b;
     uint32_t w0, w1, c = 0;
     bm_range(sh, tid, &w0, &w1);
-    for (uint32_t w = w0; w < w1; w++) c += (uint32_t)popc32(bm[w]);
+    for (uint32_t w = w0; w < w1; w++) c += (uint32_t)popc32(sh.bm[w]);
     sh.part[tid] = c;
   }
-  // block exclusive scan of part[0..BLK) in three short phases (part2 = per-32-group sums)
   static NHD void ph_bm_scan1(int tid, Sh& sh) {
     if (tid < 32) {
       uint32_t r = 0;
@@ -236,75 +296,141 @@ struct DeferredStep {
       sh.part2[k] = r;
       r += t;
     }
+    sh.part2[32] = r;
   }
-  static NHD void ph_bm_scan3(int tid, Sh& sh) {
+  // base[tid] = rank of the first multiset in this thread's word range; also the pick (thread 0)
+  static NHD void ph_bm_scan3(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
     int g = tid / (BLK / 32);
     uint32_t r = sh.part2[g];
     for (int k = g * (BLK / 32); k < tid; k++) r += sh.part[k];
     sh.base[tid] = r;
-  }
-  static NHD void ph_bm_emit(int tid, Sh& sh) {
-    const uint32_t* bm = sh.b;
-    int j = (int)sh.depth;
-    uint32_t w0, w1, at = sh.base[tid];
-    bm_range(sh, tid, &w0, &w1);
-    for (uint32_t w = w0; w < w1; w++) {
-      for (uint32_t m = bm[w]; m; m &= m - 1) {
-        uint32_t dense = (w << 5) + (uint32_t)ctz32(m), code = 0;
-        for (int i = 0; i < j; i++) {  // base-24 digits, least significant first
-          code |= (dense % 24u) << (5 * i);
-          dense /= 24u;
-        }
-        sh.a[at++] = code;
-      }
+    if (tid == 0) {
+      uint32_t count = sh.depth ? sh.part2[32] : 0u;
+      sh.count = count;
+      sh.idx = pick_action_index(A, i, sh.rnd, count);
     }
   }
-  static NHD uint64_t representative(const Sh& sh, uint32_t code) {
-    int src[4], order[4];
-    int j = (int)sh.depth;
-    unpack(code, j, src);
-    Pos P = base_pos(sh);
-    uint64_t act = ACT_EMPTY;
-    if (dbl_order_search(P, src, j, sh.d, sh.H, order))
-      for (int k = 0; k < j; k++) act = act_set(act, k, order[k], order[k] - sh.d);
-    return act;
-  }
-  // ---- pick, write the canonical list -------------------------------------------------------
-  static NHD void ph_pick(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
-    if (tid != 0) return;
-    uint32_t count = sh.depth ? sh.n_cur : 0u;
-    sh.count = count;
-    sh.idx = pick_action_index(A, i, sh.rnd, count);
-  }
-  // safety net (a level overflowed kDefCap; never observed): one thread walks the tree exactly
-  static NHD void ph_fallback(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
-    if (tid != 0) return;
-    Pos P = base_pos(sh);
-    bool ft = sh.H == 2;  // H == 2 only on a first turn (and then d is 3, 4 or 6)
-    uint64_t* slice = A.actions ? A.actions + i * (int64_t)A.cap : nullptr;
-    StoreSink sk = {slice, slice ? A.cap : 0, 1, 0};
-    uint32_t count = (uint32_t)enumerate_turn(P, sh.d, sh.d, ft, sk);
-    sh.count = count;
-    sh.depth = 4;
-    uint32_t idx = pick_action_index(A, i, sh.rnd, count);
-    if (count) {
-      PickSink pk = {(int)idx, 0, ACT_EMPTY};
-      enumerate_turn(P, sh.d, sh.d, ft, pk);
-      sh.chosen = pk.picked;
+  // the multiset of canonical rank r (r < count): select on the bitmap
+  static NHD uint32_t select_code(const Sh& sh, uint32_t r) {
+    int lo = 0, hi = BLK - 1;
+    while (lo < hi) {  // last thread range whose first rank is <= r
+      int mid = (lo + hi + 1) >> 1;
+      if (sh.base[mid] <= r)
+        lo = mid;
+      else
+        hi = mid - 1;
     }
-    sh.idx = idx;
+    uint32_t w0, w1, k = r - sh.base[lo];
+    bm_range(sh, lo, &w0, &w1);
+    uint32_t w = w0, word = sh.bm[w];
+    for (;;) {
+      uint32_t c = (uint32_t)popc32(word);
+      if (k < c) break;
+      k -= c;
+      word = sh.bm[++w];
+    }
+    for (; k; k--) word &= word - 1u;
+    return code_of_rank((w << 5) + (uint32_t)ctz32(word), (int)sh.depth);
   }
-  static NHD void ph_emit(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
-    const uint32_t* cur = sh.which ? sh.b : sh.a;
+  // ---- materialise the first `cap` actions of the canonical list and the chosen one -------------
+  // Representative ordering = the lexicographically first legal ordering of the (descending) sources,
+  // higher sources tried first.  All <= 4! orderings of a multiset are tested in parallel, one
+  // (rank, permutation) item per thread, and the smallest legal permutation index wins.
+  static NHD uint32_t emit_total(const Sh& sh, const StepFullArgs& A) {  // ranks to materialise (+1: the chosen one)
+    uint32_t n = sh.count;
+    uint32_t lim = A.actions ? (n < (uint32_t)A.cap ? n : (uint32_t)A.cap) : 0u;
+    return lim + ((n && sh.idx >= lim) ? 1u : 0u);
+  }
+  static NHD uint32_t emit_rank(const Sh& sh, const StepFullArgs& A, uint32_t k) {
+    uint32_t n = sh.count;
+    uint32_t lim = A.actions ? (n < (uint32_t)A.cap ? n : (uint32_t)A.cap) : 0u;
+    return k < lim ? k : sh.idx;
+  }
+  static NHD bool sequence_legal(const Sh& sh, const int* order, int j) {
+    Pos P = base_pos(sh);
+    int heads = 0;
+    for (int t = 0; t < j; t++) {
+      int s = order[t];
+      uint32_t m = cand_mask(P.own, P.opp, sh.d, heads < sh.H);
+      if (!((m >> s) & 1u)) return false;
+      P.move(s, s - sh.d);
+      heads += s == 23;
+      if (violates_block(P.own, P.opp)) return false;
+    }
+    return true;
+  }
+  static NHD void emit_store(Sh& sh, int64_t i, const StepFullArgs& A, uint32_t k, const int* order, int j) {
     uint64_t* slice = A.actions ? A.actions + i * (int64_t)A.cap : nullptr;
     uint32_t n = sh.count;
     uint32_t lim = slice ? (n < (uint32_t)A.cap ? n : (uint32_t)A.cap) : 0u;
-    for (uint32_t k = (uint32_t)tid; k < lim; k += BLK) {
-      uint64_t act = representative(sh, cur[k]);
-      slice[k] = act;
-      if (k == sh.idx) sh.chosen = act;
+    uint64_t act = ACT_EMPTY;
+    for (int t = 0; t < j; t++) act = act_set(act, t, order[t], order[t] - sh.d);
+    if (k < lim) slice[k] = act;
+    if (emit_rank(sh, A, k) == sh.idx) sh.chosen = act;
+  }
+  // pass over emit slots [k0, k0 + kDefEmit): rank -> multiset; descending order legal (the common
+  // case) -> written at once, else queued for the parallel ordering search
+  static NHD void ph_emit_select(int tid, Sh& sh, int64_t i, const StepFullArgs& A, uint32_t k0) {
+    uint32_t total = emit_total(sh, A);
+    const int j = (int)sh.depth;
+    for (uint32_t k = k0 + (uint32_t)tid; k < total && k < k0 + (uint32_t)kDefEmit; k += BLK) {
+      uint32_t code = select_code(sh, emit_rank(sh, A, k));
+      int src[4];
+      unpack(code, j, src);
+      if (sequence_legal(sh, src, j)) {
+        emit_store(sh, i, A, k, src, j);
+      } else {
+        uint32_t f = sm_fetch_add(&sh.n_fail, 1u);
+        sh.efail[f] = k;
+        sh.ecode[f] = code;
+        sh.ebest[f] = 0xFFFFFFFFu;
+      }
     }
-    if (tid == 0 && n && sh.idx >= lim) sh.chosen = representative(sh, cur[sh.idx]);
+  }
+  static NHD void perm_order(const int* src, int j, uint32_t perm, int* order) {  // perm-th ordering, lexicographic
+    uint32_t used = 0, f = 1;
+    for (int k = 2; k < j; k++) f *= (uint32_t)k;  // (j-1)!
+    for (int pos = 0; pos < j; pos++) {
+      uint32_t pick = perm / f;
+      perm -= pick * f;
+      if (j - 1 - pos > 0) f /= (uint32_t)(j - 1 - pos);
+      int c = 0;
+      for (int e = 0; e < j; e++) {
+        if ((used >> e) & 1u) continue;
+        if ((uint32_t)c == pick) {
+          order[pos] = src[e];
+          used |= 1u << e;
+          break;
+        }
+        c++;
+      }
+    }
+  }
+  static NHD void ph_emit_test(int tid, Sh& sh) {
+    const int j = (int)sh.depth;
+    uint32_t nperm = 1;
+    for (int k = 2; k <= j; k++) nperm *= (uint32_t)k;
+    for (uint32_t item = (uint32_t)tid; item < sh.n_fail * nperm; item += BLK) {
+      uint32_t f = item / nperm, perm = item - f * nperm;
+      int src[4], order[4];
+      unpack(sh.ecode[f], j, src);
+      perm_order(src, j, perm, order);
+      if (sequence_legal(sh, order, j)) sm_min(&sh.ebest[f], perm);
+    }
+  }
+  static NHD void ph_emit_write(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
+    const int j = (int)sh.depth;
+    for (uint32_t f = (uint32_t)tid; f < sh.n_fail; f += BLK) {
+      int src[4], order[4];
+      unpack(sh.ecode[f], j, src);
+      uint32_t perm = sh.ebest[f];
+      if (perm == 0xFFFFFFFFu) perm = 0;  // unreachable: the multiset was reached by a legal sequence
+      perm_order(src, j, perm, order);
+      emit_store(sh, i, A, sh.efail[f], order, j);
+    }
+  }
+  static NHD void ph_emit_reset(int tid, Sh& sh) {
+    if (tid == 0) sh.n_fail = 0;
   }
 };
 

@@ -20,6 +20,8 @@ using namespace narde;
 namespace {
 
 constexpr int kThreads = 128;
+constexpr int kDeferredThreads = 512;  // exact-doubles kernel: one 512-thread CTA per env at a time, ~20 KB shared memory
+constexpr int kDeferredGrid = 148 * 2;
 
 __device__ __forceinline__ State ld_state(const uint4* __restrict__ lo, const uint4* __restrict__ hi, int64_t i) {
   uint4 a = lo[i], b = hi[i];
@@ -295,8 +297,7 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
   typedef DeferredStep<BLK> DS;
   StepFullArgs A = A_in;
   if (A.step_dev) A.step = *A.step_dev;
-  extern __shared__ __align__(16) unsigned char dsm_raw[];
-  DeferredShared& sh = *reinterpret_cast<DeferredShared*>(dsm_raw);
+  __shared__ DeferredSharedT<BLK> sh;
   __shared__ float4 lut[16];
   obs_lut_init(lut);
   const int tid = threadIdx.x;
@@ -316,40 +317,40 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
     __syncthreads();
     DMARK(1);
     for (int level = 1; level <= 4; level++) {
-      DS::ph_clear(tid, sh);
+      DS::ph_clear(tid, sh, level);
       __syncthreads();
       DS::ph_expand(tid, sh, level);
       __syncthreads();
-      bool more = sh.n_next > 0;
-      __syncthreads();
+      bool more = DS::level_found(sh, level);
       DS::ph_advance(tid, sh, level);
       __syncthreads();
       if (!more) break;
     }
     DMARK(2);
-    if (sh.overflow) {
-      DS::ph_fallback(tid, sh, i, A);
-    } else {
-      DS::ph_to_a(tid, sh);
+    if (sh.depth > 0 && sh.depth < 4) {  // the bitmap holds the (empty) next level: rebuild the deepest one
+      DS::ph_rebuild(tid, sh);
       __syncthreads();
-      DS::ph_bm_clear(tid, sh);
+    }
+    DS::ph_bm_count(tid, sh);
+    __syncthreads();
+    DS::ph_bm_scan1(tid, sh);
+    __syncthreads();
+    DS::ph_bm_scan2(tid, sh);
+    __syncthreads();
+    DS::ph_bm_scan3(tid, sh, i, A);
+    __syncthreads();
+    DMARK(3);
+    for (uint32_t k0 = 0; k0 < DS::emit_total(sh, A); k0 += kDefEmit) {  // passes of kDefEmit ranks (one for cap <= 255)
+      DS::ph_emit_select(tid, sh, i, A, k0);
       __syncthreads();
-      DS::ph_bm_set(tid, sh);
-      __syncthreads();
-      DS::ph_bm_count(tid, sh);
-      __syncthreads();
-      DS::ph_bm_scan1(tid, sh);
-      __syncthreads();
-      DS::ph_bm_scan2(tid, sh);
-      __syncthreads();
-      DS::ph_bm_scan3(tid, sh);
-      __syncthreads();
-      DS::ph_bm_emit(tid, sh);
-      __syncthreads();
-      DMARK(3);
-      DS::ph_pick(tid, sh, i, A);
-      __syncthreads();
-      DS::ph_emit(tid, sh, i, A);
+      if (sh.n_fail) {  // some multisets cannot be played highest-source-first: search their orderings
+        DS::ph_emit_test(tid, sh);
+        __syncthreads();
+        DS::ph_emit_write(tid, sh, i, A);
+        __syncthreads();
+        DS::ph_emit_reset(tid, sh);
+        __syncthreads();
+      }
     }
     __syncthreads();
     DMARK(4);
@@ -438,7 +439,6 @@ __global__ void __launch_bounds__(kThreads) k_block_rule(const int8_t* boards, i
   out[i] = violates_block(own, opp) ? 1 : 0;
 }
 
-bool g_deferred_attr_set = false;
 // programmatic dependent launch of the exact kernel (NARDE_NO_PDL=1 in the environment disables it: A/B timing)
 bool g_use_pdl = true;
 
@@ -460,9 +460,6 @@ int narde_abi_version(void) {
     env_read = true;
   }
   // one-time function attributes are set here (outside any stream capture)
-  if (!g_deferred_attr_set &&
-      cudaFuncSetAttribute(k_step_deferred<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeferredShared)) == cudaSuccess)
-    g_deferred_attr_set = true;
   return NARDE_ABI_VERSION;
 }
 const char* narde_build_arch(void) { return "sm_100a"; }
@@ -552,27 +549,21 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A,
                                                                               obs198, stats);
   if (workspace) {
-    const int dyn = (int)sizeof(DeferredShared);
-    if (!g_deferred_attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_step_deferred<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-      if (e != cudaSuccess) return (int)e;
-      g_deferred_attr_set = true;
-    }
     if (g_use_pdl) {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(148);
-      cfg.blockDim = dim3(512);
-      cfg.dynamicSmemBytes = (size_t)dyn;
+      cfg.gridDim = dim3(kDeferredGrid);
+      cfg.blockDim = dim3(kDeferredThreads);
+      cfg.dynamicSmemBytes = 0;
       cfg.stream = (cudaStream_t)stream;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, k_step_deferred<512>, (uint4*)lo, (uint4*)hi, A, obs198, stats);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, k_step_deferred<kDeferredThreads>, (uint4*)lo, (uint4*)hi, A, obs198, stats);
       if (e != cudaSuccess) return (int)e;
     } else {
-      k_step_deferred<512><<<148, 512, dyn, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
+      k_step_deferred<kDeferredThreads><<<kDeferredGrid, kDeferredThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, A, obs198, stats);
     }
   }
   return launch_status();

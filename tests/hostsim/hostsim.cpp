@@ -174,31 +174,31 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
 template <int BLK>
 static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float* obs198, int64_t* stats) {
   typedef DeferredStep<BLK> DS;
-  static DeferredShared sh;
+  static DeferredSharedT<BLK> sh;
   for (int q = 0; q < A.defer_count[0]; q++) {
     int64_t i = A.defer_list[q];
     State s = load_state(lo, hi, i);
     for (int t = 0; t < BLK; t++) DS::ph_init(t, sh, s, i, A);
     for (int level = 1; level <= 4; level++) {
-      for (int t = 0; t < BLK; t++) DS::ph_clear(t, sh);
+      for (int t = 0; t < BLK; t++) DS::ph_clear(t, sh, level);
       for (int t = BLK - 1; t >= 0; t--) DS::ph_expand(t, sh, level);
-      bool more = sh.n_next > 0;
+      bool more = DS::level_found(sh, level);
       for (int t = 0; t < BLK; t++) DS::ph_advance(t, sh, level);
       if (!more) break;
     }
-    if (sh.overflow) {
-      for (int t = 0; t < BLK; t++) DS::ph_fallback(t, sh, i, A);
-    } else {
-      for (int t = 0; t < BLK; t++) DS::ph_to_a(t, sh);
-      for (int t = 0; t < BLK; t++) DS::ph_bm_clear(t, sh);
-      for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_set(t, sh);
-      for (int t = 0; t < BLK; t++) DS::ph_bm_count(t, sh);
-      for (int t = 0; t < BLK; t++) DS::ph_bm_scan1(t, sh);
-      for (int t = 0; t < BLK; t++) DS::ph_bm_scan2(t, sh);
-      for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_scan3(t, sh);
-      for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_emit(t, sh);
-      for (int t = 0; t < BLK; t++) DS::ph_pick(t, sh, i, A);
-      for (int t = BLK - 1; t >= 0; t--) DS::ph_emit(t, sh, i, A);
+    if (sh.depth > 0 && sh.depth < 4)
+      for (int t = BLK - 1; t >= 0; t--) DS::ph_rebuild(t, sh);
+    for (int t = 0; t < BLK; t++) DS::ph_bm_count(t, sh);
+    for (int t = 0; t < BLK; t++) DS::ph_bm_scan1(t, sh);
+    for (int t = 0; t < BLK; t++) DS::ph_bm_scan2(t, sh);
+    for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_scan3(t, sh, i, A);
+    for (uint32_t k0 = 0; k0 < DS::emit_total(sh, A); k0 += kDefEmit) {
+      for (int t = BLK - 1; t >= 0; t--) DS::ph_emit_select(t, sh, i, A, k0);
+      if (sh.n_fail) {
+        for (int t = 0; t < BLK; t++) DS::ph_emit_test(t, sh);
+        for (int t = BLK - 1; t >= 0; t--) DS::ph_emit_write(t, sh, i, A);
+        for (int t = 0; t < BLK; t++) DS::ph_emit_reset(t, sh);
+      }
     }
     StepFullLocal L;
     State st = sh.st;

@@ -40,7 +40,7 @@ print("kernel span cycles per step (max end - min start, per-SM clocks differ sl
 
 dd = full[:, 2048:2048 + 148]
 ok = dd[:, :, 6] > dd[:, :, 0]
-dn = ["init", "search", "order", "pick+emit", "complete", "obs"]
+dn = ["init", "search", "count+scan", "emit", "complete", "obs"]
 for st in range(dd.shape[0]):
     x = dd[st][ok[st]]
     if len(x) == 0:
