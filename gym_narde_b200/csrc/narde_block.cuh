@@ -47,6 +47,24 @@ NHD void sm_max(uint32_t* p, uint32_t v) {
 #endif
 }
 
+// One sink for the rare per-thread walks (stores the first `cap`, remembers ordinal `want`), and the
+// walk itself out of line: the code exists once instead of once per (sink, variant) combination.
+struct WalkSink {
+  uint64_t* out;
+  int cap, want, n;
+  uint64_t picked;
+  NHD void operator()(uint64_t a) {
+    if (n < cap) out[n] = a;
+    if (n == want) picked = a;
+    n++;
+  }
+};
+NHD_NOINLINE int walk_short_double(const Pos& P, int d, bool first_turn, int H, int target, bool known, WalkSink& sink) {
+  if (known) return enum_double_at(P, d, H, target, sink);
+  int depth;
+  return enum_double(P, d, first_turn, !block_rule_irrelevant(P, d, d), sink, &depth);
+}
+
 constexpr int kL1Cap = 1024;  // level-1 doubles items a CTA can hold (128 envs x <= 15 sources, never reached)
 
 template <int BLK>
@@ -111,7 +129,9 @@ struct ItemIter {  // items (parent e, bit p) over masks[e], parents ascending, 
   }
 };
 
-template <int BLK>
+// DEFER = true: order-dependent doubles turns are handed to the exact CTA-per-env kernel (the caller
+// gave a workspace) and the inline exact walk is not even compiled into the kernel (smaller code).
+template <int BLK, bool DEFER = true>
 struct BlockStep {
   typedef BlockShared<BLK> Sh;
   static constexpr int PER = BLK / 32;  // partial sums per scan lane
@@ -162,7 +182,7 @@ struct BlockStep {
       d1 = die_from_word(rnd.x);
       d2 = die_from_word(rnd.y);
     }
-    sh.rnd[tid] = rnd.z;
+    sh.rnd[tid] = A.action_idx ? (uint32_t)A.action_idx[i] : rnd.z;  // the policy's choice, or the uniform word
     sh.d1[tid] = (uint8_t)d1;
     sh.d2[tid] = (uint8_t)d2;
     int player = s_in.turn();
@@ -472,7 +492,8 @@ struct BlockStep {
   }
 
   // ---- phase 3: ND rows -> pres ; doubles level-1 items -> second-source masks -------------
-  static NHD void ph_rows(int tid, Sh& sh, bool deferral) {
+  static NHD void ph_rows(int tid, Sh& sh) {
+    constexpr bool deferral = DEFER;
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
     ItemIter<uint32_t> it;
@@ -513,7 +534,8 @@ struct BlockStep {
     if (tid == 0) sh.d2base[sh.n_l1] = sh.ws[1][32];
   }
   // ---- phase 5: counts per item -> chunk sums (lanes 0/1) and per-env totals ----------------
-  static NHD void ph_count(int tid, Sh& sh, bool deferral) {
+  static NHD void ph_count(int tid, Sh& sh) {
+    constexpr bool deferral = DEFER;
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
     ItemIter<uint32_t> it;
@@ -535,8 +557,8 @@ struct BlockStep {
         e = sh.l1env[j];
         int s1 = sh.l1src[j];
         uint32_t c;
-        if (sh.blk[e] && !deferral) {
-          c = dbl_count2_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p);
+        if (!deferral && sh.blk[e]) {
+          if constexpr (!DEFER) c = dbl_count2_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p);
         } else {
           uint32_t deep = 0, taint = 0;
           c = dbl_count2(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p, &deep, sh.blk[e] != 0, &taint);
@@ -564,7 +586,7 @@ struct BlockStep {
     sh.ebase[tid] = sh.kind[tid] == K_ND ? sh.base[2][tid] : sh.base[3][tid];
   }
   static NHD uint32_t pick_index(const Sh& sh, int e, int64_t i, uint32_t count, const StepFullArgs& A) {
-    return pick_action_index(A, i, sh.rnd[e], count);
+    return pick_from_word(A, sh.rnd[e], count);
   }
   // ---- phase 7: write the action lists in canonical order, capture the chosen action ------
   static NHD void ph_emit(int tid, Sh& sh, int64_t row0, const StepFullArgs& A) {
@@ -624,22 +646,27 @@ struct BlockStep {
         Pos P = pos_of(sh, e);
         int d = sh.a[e], H = head_budget(sh, e);
         bool store = slice && (int)off < A.cap;
-        bool exact = sh.blk[e] != 0 && !A.defer_list;
+        bool exact = !DEFER && sh.blk[e] != 0;
         if (store) {
           if (exact) {
-            G += dbl_exact2<true>(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
+            if constexpr (!DEFER) G += dbl_exact2<true>(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
           } else {
             G += dbl_emit2(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
           }
         } else {  // nothing to store: count, and walk again only if the chosen index is inside
-          uint32_t deep;
-          uint32_t cnt = exact ? dbl_count2_exact(P, d, H, s1, p) : dbl_count2(P, d, H, s1, p, &deep);
+          uint32_t deep, cnt = 0;
+          if (exact) {
+            if constexpr (!DEFER) cnt = dbl_count2_exact(P, d, H, s1, p);
+          } else {
+            cnt = dbl_count2(P, d, H, s1, p, &deep);
+          }
           G += cnt;
           if (idx >= off && idx < off + cnt) {
-            if (exact)
-              dbl_exact2<true>(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
-            else
+            if (exact) {
+              if constexpr (!DEFER) dbl_exact2<true>(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
+            } else {
               dbl_emit2(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
+            }
           }
         }
       }
@@ -688,30 +715,33 @@ struct BlockStep {
       Pos P = pos_of(sh, tid);
       bool ft = sh.first[tid] != 0;
       int target = (int)sh.maxd[tid];
-      bool known = (!sh.blk[tid] || A.defer_list) && sh.n_l1 > 0;  // depth found by the item phases
-      if (known && target == 0) {
-        count = 0;
-      } else if (slice) {
-        StoreSink sk = {slice, A.cap, 1, 0};
-        count = known ? (uint32_t)enum_double_at(P, a, head_budget(sh, tid), target, sk)
-                      : (uint32_t)enumerate_turn(P, a, b, ft, sk);
-      } else {
-        CountSink ck;
-        count = known ? (uint32_t)enum_double_at(P, a, head_budget(sh, tid), target, ck)
-                      : (uint32_t)enumerate_turn(P, a, b, ft, ck);
-      }
+      bool known = (!sh.blk[tid] || DEFER) && sh.n_l1 > 0;  // depth found by the item phases
       act = ACT_EMPTY;
-      if (count) {
-        uint32_t idx = pick_index(sh, tid, i, count, A);
-        if (slice && (int)idx < A.cap) {
-          act = slice[idx];
-        } else {
-          PickSink pk = {(int)idx, 0, ACT_EMPTY};
-          if (known)
-            enum_double_at(P, a, head_budget(sh, tid), target, pk);
-          else
-            enumerate_turn(P, a, b, ft, pk);
-          act = pk.picked;
+      if (sh.dmask[tid] == 0u || (known && target == 0)) {
+        count = 0;  // no playable die: the turn is passed
+      } else {
+        // store + count pass; a second (pick) pass only when the chosen action was not stored.  The
+        // common case (depth known) is inlined once inside this two-trip loop, the rest out of line.
+        WalkSink sk = {slice, slice ? A.cap : 0, -1, 0, ACT_EMPTY};
+        const int H = head_budget(sh, tid);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+          int n = known ? enum_double_at(P, a, H, target, sk) : walk_short_double(P, a, ft, H, target, false, sk);
+          if (pass == 1) {
+            act = sk.picked;
+            break;
+          }
+          count = (uint32_t)n;
+          if (n == 0) break;
+          uint32_t idx = pick_index(sh, tid, i, count, A);
+          if (slice && (int)idx < A.cap) {
+            act = slice[idx];
+            break;
+          }
+          sk.out = nullptr;
+          sk.cap = 0;
+          sk.want = (int)idx;
+          sk.n = 0;
         }
       }
     }

@@ -228,22 +228,20 @@ struct DeferredStep {
     const uint32_t n_cur = sh.n_cur;
     Pos P;
     uint32_t risky;
-    if (n_cur <= (uint32_t)(4 * WARPS)) {
-      const int lane = tid & 31, warp = tid >> 5;
-      if (lane >= 24) return;
-      for (uint32_t pi = (uint32_t)warp; pi < n_cur; pi += WARPS) {
-        uint32_t code = cur[pi];
-        uint32_t m = node_board(sh, code, j, &P, &risky);
-        if ((m >> lane) & 1u) visit_child(sh, nxt, code, j, P, lane, ((risky >> lane) & 1u) != 0);
-      }
-    } else {
-      for (uint32_t pi = (uint32_t)tid; pi < n_cur; pi += BLK) {
-        uint32_t code = cur[pi];
-        uint32_t m = node_board(sh, code, j, &P, &risky);
-        for (; m; m &= m - 1) {
-          int s = ctz32(m);
-          visit_child(sh, nxt, code, j, P, s, ((risky >> s) & 1u) != 0);
-        }
+    // narrow level: node = warp, one candidate source per lane; wide level: node = thread, all candidates
+    const bool narrow = n_cur <= (uint32_t)(4 * WARPS);
+    const int lane = tid & 31;
+    if (narrow && lane >= 24) return;
+    const uint32_t start = narrow ? (uint32_t)(tid >> 5) : (uint32_t)tid, stride = narrow ? (uint32_t)WARPS : (uint32_t)BLK;
+    const uint32_t lane_mask = narrow ? (1u << lane) : 0xFFFFFFu;
+#pragma unroll 1
+    for (uint32_t pi = start; pi < n_cur; pi += stride) {
+      uint32_t code = cur[pi];
+      uint32_t m = node_board(sh, code, j, &P, &risky) & lane_mask;
+#pragma unroll 1
+      for (; m; m &= m - 1) {
+        int s = ctz32(m);
+        visit_child(sh, nxt, code, j, P, s, ((risky >> s) & 1u) != 0);
       }
     }
   }
@@ -311,7 +309,7 @@ struct DeferredStep {
     }
   }
   // the multiset of canonical rank r (r < count): select on the bitmap
-  static NHD uint32_t select_code(const Sh& sh, uint32_t r) {
+  static NHD_NOINLINE uint32_t select_code(const Sh& sh, uint32_t r) {
     int lo = 0, hi = BLK - 1;
     while (lo < hi) {  // last thread range whose first rank is <= r
       int mid = (lo + hi + 1) >> 1;
@@ -346,7 +344,7 @@ struct DeferredStep {
     uint32_t lim = A.actions ? (n < (uint32_t)A.cap ? n : (uint32_t)A.cap) : 0u;
     return k < lim ? k : sh.idx;
   }
-  static NHD bool sequence_legal(const Sh& sh, const int* order, int j) {
+  static NHD_NOINLINE bool sequence_legal(const Sh& sh, const int* order, int j) {
     Pos P = base_pos(sh);
     int heads = 0;
     for (int t = 0; t < j; t++) {
@@ -387,7 +385,7 @@ struct DeferredStep {
       }
     }
   }
-  static NHD void perm_order(const int* src, int j, uint32_t perm, int* order) {  // perm-th ordering, lexicographic
+  static NHD_NOINLINE void perm_order(const int* src, int j, uint32_t perm, int* order) {  // perm-th ordering, lexicographic
     uint32_t used = 0, f = 1;
     for (int k = 2; k < j; k++) f *= (uint32_t)k;  // (j-1)!
     for (int pos = 0; pos < j; pos++) {

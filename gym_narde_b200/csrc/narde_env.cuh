@@ -85,16 +85,19 @@ struct StepFullArgs {
 
 // The index of the action to play among `count` legal ones: the caller's action_idx[i] (clamped; or,
 // with F_ACTION_FRACTION, a u32 fraction f -> floor(f * count / 2^32)), else Philox-uniform from rnd.
-NHD uint32_t pick_action_index(const StepFullArgs& A, int64_t i, uint32_t rnd, uint32_t count) {
+// word = action_idx[i] when the caller gave actions, else the Philox word of the turn
+NHD uint32_t pick_from_word(const StepFullArgs& A, uint32_t word, uint32_t count) {
   if (count == 0) return 0;
-  if (A.action_idx) {
-    int32_t v = A.action_idx[i];
-    if (A.flags & F_ACTION_FRACTION) return mulhi32((uint32_t)v, count);
+  if (A.action_idx && !(A.flags & F_ACTION_FRACTION)) {
+    int32_t v = (int32_t)word;
     if (v < 0) v = 0;
     if (v >= (int32_t)count) v = (int32_t)count - 1;
     return (uint32_t)v;
   }
-  return mulhi32(rnd, count);
+  return mulhi32(word, count);
+}
+NHD uint32_t pick_action_index(const StepFullArgs& A, int64_t i, uint32_t rnd, uint32_t count) {
+  return pick_from_word(A, A.action_idx ? (uint32_t)A.action_idx[i] : rnd, count);
 }
 
 struct StepFullLocal {  // per-env contributions to the stats vector

@@ -196,10 +196,10 @@ __device__ unsigned long long* g_dbg_clk = nullptr;
 
 // Fused full-rules step, CTA-cooperative (narde_block.cuh): the phases run with a CTA barrier
 // between them; everything between the state load and the Box(198) store stays in shared memory.
-template <int BLK>
+template <int BLK, bool DEFER>
 __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int64_t n, StepFullArgs A_in, float* obs198,
                                                       int64_t* stats) {
-  typedef BlockStep<BLK> BS;
+  typedef BlockStep<BLK, DEFER> BS;
   StepFullArgs A = A_in;
   if (A.step_dev) A.step = *A.step_dev;
   __shared__ BlockShared<BLK> sh;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_item_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(2);
-  BS::ph_rows(tid, sh, A.defer_list != nullptr);
+  BS::ph_rows(tid, sh);
   __syncthreads();
   PHASE_MARK(3);
   BS::ph_scan1(tid, sh);
@@ -232,11 +232,11 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_l2_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(4);
-  BS::ph_count(tid, sh, A.defer_list != nullptr);
+  BS::ph_count(tid, sh);
   __syncthreads();
   PHASE_MARK(5);
   BS::ph_env_totals(tid, sh);
-  if (A.defer_list) {
+  if (DEFER) {
     BS::ph_defer_push(tid, sh, valid, i, A);
     __threadfence();  // the list entry is visible device-wide before this CTA lets the dependent grid go
   }
@@ -546,8 +546,10 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
   }
-  k_step_full_v2<128><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A,
-                                                                              obs198, stats);
+  if (workspace)
+    k_step_full_v2<128, true><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
+  else
+    k_step_full_v2<128, false><<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
   if (workspace) {
     if (g_use_pdl) {
       cudaLaunchConfig_t cfg = {};

@@ -125,9 +125,9 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
 
 // CTA-cooperative step (narde_block.cuh) emulated phase by phase: every phase runs for all tids
 // of a block before the next one starts, which is what __syncthreads() guarantees on the GPU.
-template <int BLK>
+template <int BLK, bool DEFER>
 static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs& A, float* obs198, int64_t* stats) {
-  typedef BlockStep<BLK> BS;
+  typedef BlockStep<BLK, DEFER> BS;
   static BlockShared<BLK> sh;
   for (int64_t row0 = 0; row0 < n; row0 += BLK) {
     for (int t = 0; t < BLK; t++) {
@@ -141,12 +141,12 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
     for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_item_bases(t, sh); }
-    for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh, A.defer_list != nullptr);
+    for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
     for (int t = 0; t < BLK; t++) { BS::ph_scan3(t, sh); BS::ph_l2_bases(t, sh); }
-    for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh, A.defer_list != nullptr);
-    for (int t = 0; t < BLK; t++) { BS::ph_env_totals(t, sh); BS::ph_defer_push(t, sh, row0 + t < n, row0 + t, A); }
+    for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh);
+    for (int t = 0; t < BLK; t++) { BS::ph_env_totals(t, sh); if (DEFER) BS::ph_defer_push(t, sh, row0 + t < n, row0 + t, A); }
     for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
     for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_env_bases(t, sh); }
@@ -227,7 +227,10 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     A.defer_count = workspace;
     A.defer_list = workspace + 1;
   }
-  step_full_v2_host<128>(lo, hi, n, A, obs198, stats);
+  if (workspace)
+    step_full_v2_host<128, true>(lo, hi, n, A, obs198, stats);
+  else
+    step_full_v2_host<128, false>(lo, hi, n, A, obs198, stats);
   if (workspace) step_deferred_host<512>(lo, hi, A, obs198, stats);
   return 0;
 }
