@@ -2,15 +2,24 @@
 //
 // Architecture = the reference's DecomposedDQN.forward(x) (train_deepq_pytorch.py:184-236) with
 // state_size = 198:  x[K,198] -> Linear(198,256)+ReLU -> Linear(256,256)+ReLU -> Linear(256,576).
-// One CTA owns a tile of 128 rows and runs all three layers back to back without leaving the SM:
-//   * operands are bf16 in shared memory in the canonical K-major "interleave" (no-swizzle) UMMA
-//     layout (8x8 core matrices of 128 B); activations are written there directly by the epilogue,
-//     weights arrive pre-packed in that layout as contiguous 32 KB stages via cp.async.bulk (TMA
-//     1-D bulk copy) completing on an mbarrier;
-//   * tcgen05.mma (cta_group::1, kind::f16, M=128, N<=256, K=16) issued by one thread, fp32
-//     accumulators in tensor memory (256 columns per 128x256 block);
-//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp), + bias, ReLU, bf16, back to shared
-//     memory as the next layer's A operand; the last layer streams fp32 Q-values to HBM.
+//
+// One persistent CTA per SM keeps TWO 128-row tiles ("slots") in flight, out of phase: while the
+// tensor core runs one slot's layer, the other slot's accumulator is drained.  Warp roles:
+//   warp 0 (one lane)  weight producer: packed bf16 weight stages (N x 32 K, 16 KB) stream from L2
+//                      through a 4-deep ring with cp.async.bulk (TMA 1-D bulk copy) + mbarriers;
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N<=256, K=16, operands
+//                      in shared memory (K-major "interleave" no-swizzle layout), fp32 accumulators
+//                      in tensor memory (256 columns per slot, all 512 allocated);
+//   warps 2-9 / 10-17  epilogue group of slot 0 / slot 1 (TMEM lane quarter = warp & 3, two warps per
+//                      quarter splitting the columns; TMEM loads software-pipelined): builds the
+//                      slot's input tile (fp32 Box(198) rows converted to bf16, or the Box(198)
+//                      encoding computed on the fly from 32-byte packed states), then per layer
+//                      tcgen05.ld -> +bias -> ReLU -> bf16 -> back into the SAME shared-memory tile
+//                      (the MMAs that read it have completed); the last layer either streams fp32
+//                      Q-values to HBM through a per-warp transpose buffer (coalesced 16-byte lanes)
+//                      or reduces them to max_a Q(s', a) per row (the afterstate score).
+// Per slot the hand-offs are two mbarriers: slot_ready (256 epilogue threads -> MMA issuer: operand
+// tile written / accumulator drained) and acc_full (tcgen05.commit -> epilogue group).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,23 +28,52 @@
 
 namespace {
 
-constexpr int kRows = 128;       // rows per CTA (UMMA M)
-constexpr int kIn = 198;         // Box(198)
-constexpr int kK = 256;          // padded K of every layer
-constexpr int kH = 256;          // hidden width
-constexpr int kOut = 576;        // move space (24*24)
-constexpr int kKC = 64;          // K elements per weight stage
-constexpr int kStages = 3;       // weight stages in flight
-constexpr int kStageBytes = 256 * kKC * 2;  // 32 KB: a 256-row (N) x 64 (K) bf16 block
-constexpr int kABytes = kRows * kK * 2;     // 64 KB activation tile
-constexpr int kThreads = 512;      // 16 warps: TMEM lane quarter = warp & 3, column group = warp >> 2
+constexpr int kRows = 128;        // rows per slot (UMMA M)
+constexpr int kIn = 198;          // Box(198)
+constexpr int kK1 = 208;          // layer-1 K padded to a multiple of 16
+constexpr int kH = 256;           // hidden width
+constexpr int kOut = 576;         // move space (24*24)
+constexpr int kKC = 32;           // K elements per weight stage
+constexpr int kStagesQ = 3;       // weight stages in flight when fp32 Q-values are stored (transpose buffers need room)
+constexpr int kStagesMax = 5;     // ... when only the row maximum is kept
+constexpr int kStageBytes = 256 * kKC * 2;   // 16 KB: a 256-row (N) x 32 (K) bf16 block
+constexpr int kABytes = kRows * kH * 2;      // 64 KB operand tile per slot
+constexpr int kEpiWarps = 16;                  // 8 per slot
+constexpr int kThreads = 64 + kEpiWarps * 32;  // 576
+constexpr int kStageCols = 16;                 // fp32 Q columns transposed per pass
+constexpr int kStageStride = 20;               // floats per staged row (conflict-free 16-byte lanes)
+constexpr int kStagingBytes = kEpiWarps * 32 * kStageStride * 4;  // 40 KB
+constexpr int kBiasFloats = kH + kH + kOut;    // 1088
 
-// shared memory map (dynamic): [A0 | A1 | B stages | barriers]
-constexpr int kSmemA0 = 0;
-constexpr int kSmemA1 = kSmemA0 + kABytes;
-constexpr int kSmemB = kSmemA1 + kABytes;
-constexpr int kSmemBar = kSmemB + kStages * kStageBytes;
-constexpr int kSmemBytes = kSmemBar + 128;
+// shared memory map (dynamic): [A slot 0 | A slot 1 | bias | lut | barriers | staging / exchange | weight ring]
+constexpr int kSmemA = 0;                                   // 2 slots
+constexpr int kSmemBias = kSmemA + 2 * kABytes;
+constexpr int kSmemLut = kSmemBias + kBiasFloats * 4;       // 16 x u64 point-feature table
+constexpr int kSmemBar = kSmemLut + 16 * 8;
+constexpr int kSmemStaging = kSmemBar + 16 * 8;
+template <bool OUT_MAX>
+struct Map {
+  static constexpr int stages = OUT_MAX ? kStagesMax : kStagesQ;
+  static constexpr int staging = OUT_MAX ? 1024 : kStagingBytes;   // max mode: 2 x 128 floats of exchange
+  static constexpr int b = kSmemStaging + staging;                 // weight ring (16-byte aligned)
+  static constexpr int bytes = b + stages * kStageBytes;
+};
+
+// the five GEMM jobs of a tile: (weight block, N, K, bias offset, output column offset)
+struct Job {
+  int w_off;   // byte offset of the block's packed stages
+  int nb;      // output columns of the block (UMMA N)
+  int k;       // reduction length
+  int b_off;   // bias offset (floats)
+  int col0;    // first output column (layer 3 only)
+};
+__device__ __constant__ Job c_jobs[5] = {
+    {0, 256, kK1, 0, 0},
+    {256 * kK1 * 2, 256, kH, 256, 0},
+    {256 * kK1 * 2 + 256 * kH * 2, 256, kH, 512, 0},
+    {256 * kK1 * 2 + 2 * 256 * kH * 2, 256, kH, 768, 256},
+    {256 * kK1 * 2 + 3 * 256 * kH * 2, 64, kH, 1024, 512},
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -44,6 +82,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -97,7 +138,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
 }
 
 // byte offset of element (row r, k) in a K-major interleave tile of `rows` rows:
@@ -105,205 +154,391 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ uint32_t tile_off(int rows, int r, int k) {
   return (uint32_t)((k >> 3) * (rows * 16) + (r >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
 }
-
-struct Layer {
-  const uint8_t* w;   // packed stages: for each N block (<=256 rows), for each K chunk of 64: contiguous block
-  const float* bias;
-  int n_out;          // 256, 256, 576
-};
-
-// One GEMM block: D[128 x nb] = A[128 x 256] * Wblock^T, weights streamed through the stage ring.
-// `it` is the running stage counter (ring position / mbarrier phase), shared by all layers.
-__device__ __forceinline__ void gemm_block(uint32_t a_saddr, const uint8_t* wblk, int nb, uint32_t tmem_d, uint32_t bsm,
-                                           uint32_t bar_full, uint32_t bar_empty, uint32_t bar_acc, uint32_t& it,
-                                           uint32_t& acc_phase, int tid) {
-  const int n_chunks = kK / kKC;              // 4
-  const uint32_t stage_bytes = (uint32_t)nb * kKC * 2;
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc(kRows, nb);
-    // prologue: fill up to kStages stages
-    int issued = 0;
-    for (; issued < n_chunks && issued < kStages; issued++) {
-      uint32_t s = (it + issued) % kStages, ph = ((it + issued) / kStages) & 1u;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-      mbar_expect_tx(bar_full + 8 * s, stage_bytes);
-      bulk_g2s(bsm + s * kStageBytes, wblk + (size_t)issued * stage_bytes, stage_bytes, bar_full + 8 * s);
-    }
-    for (int c = 0; c < n_chunks; c++) {
-      uint32_t s = (it + c) % kStages, ph = ((it + c) / kStages) & 1u;
-      mbar_wait(bar_full + 8 * s, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < kKC / 16; kk++) {
-        // A: k chunk index (c*64 + kk*16)/8 ; LBO = rows*16 (K direction), SBO = 128 (row groups)
-        uint64_t ad = make_desc(a_saddr + (uint32_t)((c * kKC + kk * 16) >> 3) * (kRows * 16), kRows * 16, 128);
-        uint64_t bd = make_desc(bsm + s * kStageBytes + (uint32_t)((kk * 16) >> 3) * (nb * 16), nb * 16, 128);
-        umma(tmem_d, ad, bd, idesc, (c | kk) ? 1u : 0u);
-      }
-      umma_commit(bar_empty + 8 * s);          // frees the stage when these MMAs have read it
-      if (issued < n_chunks) {                 // refill the ring
-        uint32_t s2 = (it + issued) % kStages, ph2 = ((it + issued) / kStages) & 1u;
-        mbar_wait(bar_empty + 8 * s2, ph2 ^ 1u);
-        mbar_expect_tx(bar_full + 8 * s2, stage_bytes);
-        bulk_g2s(bsm + s2 * kStageBytes, wblk + (size_t)issued * stage_bytes, stage_bytes, bar_full + 8 * s2);
-        issued++;
-      }
-    }
-    umma_commit(bar_acc);                      // accumulator complete
-  }
-  it += n_chunks;
-  mbar_wait(bar_acc, acc_phase);
-  acc_phase ^= 1u;
-  tc_fence_after();
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-k_mlp_forward(const float* __restrict__ x, int64_t rows, Layer L1, Layer L2, Layer L3, float* __restrict__ q) {
+// np.float32(n / 15.0): the Box(198) "off" feature (README.md:44-102), same table as the env kernels
+__device__ __constant__ float c_mlp_off15[16] = {
+    (float)(0.0 / 15.0),  (float)(1.0 / 15.0),  (float)(2.0 / 15.0),  (float)(3.0 / 15.0),
+    (float)(4.0 / 15.0),  (float)(5.0 / 15.0),  (float)(6.0 / 15.0),  (float)(7.0 / 15.0),
+    (float)(8.0 / 15.0),  (float)(9.0 / 15.0),  (float)(10.0 / 15.0), (float)(11.0 / 15.0),
+    (float)(12.0 / 15.0), (float)(13.0 / 15.0), (float)(14.0 / 15.0), (float)(15.0 / 15.0)};
+
+struct Params {
+  const float* x;        // [rows,198] fp32 (IN_STATES = false)
+  const uint4* lo;       // packed states (IN_STATES = true), include/narde_b200.h layout
+  const uint4* hi;
+  int64_t rows;
+  const uint8_t* w;      // packed weight stages
+  const float* bias;     // 1088 floats
+  float* q;              // [rows,576] fp32 (OUT_MAX = false)
+  float* score;          // [rows] fp32 max_a Q (OUT_MAX = true)
+};
+
+// ---- operand tile of one slot from fp32 rows: coalesced float2 loads (4 rows = 16 loads in flight per
+// thread), bf16 pairs into the tile; the group's 8 warps take 16 rows each ----
+__device__ __forceinline__ void load_x_tile(uint8_t* a_tile, const float* __restrict__ x, int64_t row0, int64_t rows,
+                                            int gwarp, int lane) {
+#pragma unroll 1
+  for (int rb = 0; rb < 16; rb += 4) {
+    float2 v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t gr = row0 + gwarp * 16 + rb + u;
+      const float2* src = reinterpret_cast<const float2*>(x + gr * kIn);  // rows are 792 B: 8-byte aligned
+#pragma unroll
+      for (int it = 0; it < 4; it++) {
+        const int p = it * 32 + lane;  // float2 index: k = 2p
+        v[u][it] = (gr < rows && p < kIn / 2) ? __ldg(src + p) : make_float2(0.0f, 0.0f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = gwarp * 16 + rb + u;
+#pragma unroll
+      for (int it = 0; it < 4; it++) {
+        const int p = it * 32 + lane;
+        if (p < kK1 / 2) *reinterpret_cast<uint32_t*>(a_tile + tile_off(kRows, r, 2 * p)) = pack_bf16(v[u][it].x, v[u][it].y);
+      }
+    }
+  }
+}
+
+// ---- operand tile of one slot from packed states: Box(198) (README.md:44-102) computed on the fly ----
+// 256 threads per slot: thread t encodes points [12h, 12h+12) of row t & 127, h = t >> 7
+__device__ __forceinline__ void load_state_tile(uint8_t* a_tile, const uint4* __restrict__ lo, const uint4* __restrict__ hi,
+                                                int64_t row0, int64_t rows, int t, const uint64_t* lut) {
+  const int r = t & 127, h = t >> 7;
+  const int64_t gr = row0 + r;
+  uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (gr < rows) {
+    uint4 a = __ldg(lo + gr), b = __ldg(hi + gr);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  }
+#pragma unroll
+  for (int pp = 0; pp < 12; pp++) {
+    const int p = h * 12 + pp;
+    const int v = (int)(int8_t)((w[p >> 2] >> ((p & 3) * 8)) & 0xFF);
+    const uint64_t fw = lut[v > 0 ? v : 0], fb = lut[v < 0 ? -v : 0];
+    // WHITE features k = 4p..4p+3: one aligned 8-byte lane
+    *reinterpret_cast<uint2*>(a_tile + tile_off(kRows, r, 4 * p)) = make_uint2((uint32_t)fw, (uint32_t)(fw >> 32));
+    // BLACK features k = 98+4p..: two 4-byte halves (the second may fall into the next 8-wide K chunk)
+    *reinterpret_cast<uint32_t*>(a_tile + tile_off(kRows, r, 98 + 4 * p)) = (uint32_t)fb;
+    *reinterpret_cast<uint32_t*>(a_tile + tile_off(kRows, r, 100 + 4 * p)) = (uint32_t)(fb >> 32);
+  }
+  if (h) return;
+  const int off_w = (int)(w[6] & 0xFF), off_b = (int)((w[6] >> 8) & 0xFF), turn = (int)(int8_t)((w[6] >> 16) & 0xFF);
+  *reinterpret_cast<uint32_t*>(a_tile + tile_off(kRows, r, 96)) = pack_bf16(0.0f, c_mlp_off15[off_w & 15]);
+  *reinterpret_cast<uint32_t*>(a_tile + tile_off(kRows, r, 194)) = pack_bf16(0.0f, c_mlp_off15[off_b & 15]);
+  *reinterpret_cast<uint32_t*>(a_tile + tile_off(kRows, r, 196)) =
+      gr < rows ? (turn == 1 ? pack_bf16(1.0f, 0.0f) : pack_bf16(0.0f, 1.0f)) : 0u;
+#pragma unroll
+  for (int k = kIn; k < kK1; k += 2) *reinterpret_cast<uint32_t*>(a_tile + tile_off(kRows, r, k)) = 0u;
+}
+
+template <bool IN_STATES, bool OUT_MAX>
+__global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t a0 = sbase + kSmemA0, a1 = sbase + kSmemA1, bsm = sbase + kSmemB;
-  const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kStages, bar_acc = bar_empty + 8 * kStages;
+  constexpr int kStages = Map<OUT_MAX>::stages;
+  const uint32_t bsm = sbase + Map<OUT_MAX>::b;
+  const uint32_t bar_full = sbase + kSmemBar, bar_empty = bar_full + 8 * kStages;
+  const uint32_t bar_acc = bar_empty + 8 * kStages;      // [2] accumulator of slot s complete
+  const uint32_t bar_ready = bar_acc + 16;                // [2] slot s: operand tile written / accumulator drained
+  float* s_bias = reinterpret_cast<float*>(smem + kSmemBias);
+  uint64_t* s_lut = reinterpret_cast<uint64_t*>(smem + kSmemLut);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(bar_acc + 8 * s, 1);
+      mbar_init(bar_ready + 8 * s, 256);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {  // one warp allocates 256 TMEM columns (128 lanes x 256 fp32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)));
+  if (warp == 0) {  // one warp allocates all 512 TMEM columns (two 128 x 256 fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int k = tid; k < kBiasFloats; k += kThreads) s_bias[k] = P.bias[k];
+  if (tid < 16) {  // point-feature table: n -> bf16 [n>=1, n>=2, n>=3, (n-3)/2]
+    const int n = tid;
+    uint32_t a = pack_bf16(n >= 1 ? 1.0f : 0.0f, n >= 2 ? 1.0f : 0.0f);
+    uint32_t b = pack_bf16(n >= 3 ? 1.0f : 0.0f, n > 3 ? (float)(n - 3) * 0.5f : 0.0f);
+    s_lut[n] = (uint64_t)a | ((uint64_t)b << 32);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  uint32_t it = 0, acc_phase = 0;
-  for (int64_t tile = blockIdx.x; tile * kRows < rows; tile += gridDim.x) {
-    const int64_t row0 = tile * kRows;
-    // ---- stage X: fp32 [128,198] -> bf16 K-major interleave tile in A0 (K padded to 256 with zeros)
-    for (int idx = tid; idx < kRows * (kK / 8); idx += kThreads) {
-      int r = idx & (kRows - 1), kc = idx / kRows;  // consecutive threads -> consecutive rows (conflict-free stores)
-      int64_t gr = row0 + r;
-      __nv_bfloat16 h[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        int k = kc * 8 + j;
-        float v = (gr < rows && k < kIn) ? x[gr * kIn + k] : 0.0f;
-        h[j] = __float2bfloat16(v);
-      }
-      *reinterpret_cast<uint4*>(smem + kSmemA0 + tile_off(kRows, r, kc * 8)) = *reinterpret_cast<uint4*>(h);
-    }
-    fence_async_smem();
-    __syncthreads();
+  const int64_t n_tiles = (P.rows + kRows - 1) / kRows;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
 
-    // ---- layer 1: A0 -> A1, layer 2: A1 -> A0 ----
-#pragma unroll 1
-    for (int layer = 0; layer < 2; layer++) {
-      const Layer& L = layer == 0 ? L1 : L2;
-      const uint32_t a_in = layer == 0 ? a0 : a1;
-      uint8_t* a_out = smem + (layer == 0 ? kSmemA1 : kSmemA0);
-      gemm_block(a_in, L.w, kH, tmem, bsm, bar_full, bar_empty, bar_acc, it, acc_phase, tid);
-      // epilogue: row = TMEM lane = (warp & 3) * 32 + lane; the 4 column groups (warp >> 2) take 64 columns each
-      const int r = (warp & 3) * 32 + (tid & 31);
-      const int cg = warp >> 2;
-#pragma unroll 1
-      for (int cb = cg * 2; cb < cg * 2 + 2; cb++) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32), v);
-        const float4* b4 = reinterpret_cast<const float4*>(L.bias + cb * 32);
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
-          float f0 = __uint_as_float(v[g * 8 + 0]) + ba.x, f1 = __uint_as_float(v[g * 8 + 1]) + ba.y;
-          float f2 = __uint_as_float(v[g * 8 + 2]) + ba.z, f3 = __uint_as_float(v[g * 8 + 3]) + ba.w;
-          float f4 = __uint_as_float(v[g * 8 + 4]) + bb.x, f5 = __uint_as_float(v[g * 8 + 5]) + bb.y;
-          float f6 = __uint_as_float(v[g * 8 + 6]) + bb.z, f7 = __uint_as_float(v[g * 8 + 7]) + bb.w;
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(f0, 0.0f), fmaxf(f1, 0.0f));
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(f2, 0.0f), fmaxf(f3, 0.0f));
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(f4, 0.0f), fmaxf(f5, 0.0f));
-          __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(f6, 0.0f), fmaxf(f7, 0.0f));
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&p0);
-          pk.y = *reinterpret_cast<uint32_t*>(&p1);
-          pk.z = *reinterpret_cast<uint32_t*>(&p2);
-          pk.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(a_out + tile_off(kRows, r, cb * 32 + g * 8)) = pk;
-        }
-      }
-      tc_fence_before();
-      fence_async_smem();
-      __syncthreads();
-      tc_fence_after();
-    }
-
-    // ---- layer 3: A0 -> Q[128,576] fp32 in HBM, N blocks of 256, 256, 64 ----
-#pragma unroll 1
-    for (int nb0 = 0; nb0 < kOut; nb0 += 256) {
-      const int nb = kOut - nb0 < 256 ? kOut - nb0 : 256;
-      gemm_block(a0, L3.w + (size_t)nb0 * kK * 2, nb, tmem, bsm, bar_full, bar_empty, bar_acc, it, acc_phase, tid);
-      const int64_t gr = row0 + (warp & 3) * 32 + (tid & 31);
-      const int cg = warp >> 2, per = nb >= 128 ? nb / 128 : 1;  // 32-column chunks per column group
-#pragma unroll 1
-      for (int cb = cg * per; cb < cg * per + per && cb * 32 < nb; cb++) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cb * 32), v);
-        if (gr < rows) {
-          float* dst = q + gr * kOut + nb0 + cb * 32;
-          const float4* b4 = reinterpret_cast<const float4*>(L3.bias + nb0 + cb * 32);
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float4 b = __ldg(b4 + j), o;
-            o.x = __uint_as_float(v[4 * j]) + b.x;
-            o.y = __uint_as_float(v[4 * j + 1]) + b.y;
-            o.z = __uint_as_float(v[4 * j + 2]) + b.z;
-            o.w = __uint_as_float(v[4 * j + 3]) + b.w;
-            *reinterpret_cast<float4*>(dst + 4 * j) = o;
+  if (warp == 0) {
+    // ===== weight producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int j = 0; j < 5; j++) {
+          const Job jb = c_jobs[j];
+          for (int slot = 0; slot < 2; slot++) {
+            if (pair * 2 + slot >= n_tiles) continue;
+            const uint8_t* src = P.w + jb.w_off;
+            for (int k0 = 0; k0 < jb.k; k0 += kKC) {
+              const int klen = jb.k - k0 < kKC ? jb.k - k0 : kKC;
+              const uint32_t bytes = (uint32_t)(jb.nb * klen * 2);
+              const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+              mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+              mbar_expect_tx(bar_full + 8 * s, bytes);
+              bulk_g2s(bsm + s * kStageBytes, src, bytes, bar_full + 8 * s);
+              src += bytes;
+              it++;
+            }
           }
         }
       }
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t it = 0, ready_phase[2] = {0, 0};
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int j = 0; j < 5; j++) {
+          const Job jb = c_jobs[j];
+          const uint32_t idesc = make_idesc(kRows, jb.nb);
+          for (int slot = 0; slot < 2; slot++) {
+            if (pair * 2 + slot >= n_tiles) continue;
+            mbar_wait(bar_ready + 8 * slot, ready_phase[slot]);
+            ready_phase[slot] ^= 1u;
+            tc_fence_after();
+            const uint32_t a_saddr = sbase + kSmemA + slot * kABytes;
+            const uint32_t tmem_d = tmem + (uint32_t)(slot * 256);
+            for (int k0 = 0; k0 < jb.k; k0 += kKC) {
+              const int klen = jb.k - k0 < kKC ? jb.k - k0 : kKC;
+              const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+              mbar_wait(bar_full + 8 * s, ph);
+              tc_fence_after();
+              for (int kk = 0; kk < klen; kk += 16) {
+                uint64_t ad = make_desc(a_saddr + (uint32_t)((k0 + kk) >> 3) * (kRows * 16), kRows * 16, 128);
+                uint64_t bd = make_desc(bsm + s * kStageBytes + (uint32_t)(kk >> 3) * (jb.nb * 16), jb.nb * 16, 128);
+                umma(tmem_d, ad, bd, idesc, (k0 | kk) ? 1u : 0u);
+              }
+              umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
+              it++;
+            }
+            umma_commit(bar_acc + 8 * slot);   // accumulator of this job complete
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue groups =====
+    const int e = warp - 2;                   // 0..15
+    const int slot = e >> 3;                  // group 0: warps 2-9, group 1: warps 10-17
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (e & 7) >> 2;            // which half of the columns (two warps share a quarter)
+    const int gwarp = e & 7;                  // warp index inside the group
+    const int gtid = gwarp * 32 + lane;       // thread index inside the group (0..255)
+    const int r = quarter * 32 + lane;        // tile row = TMEM lane
+    uint8_t* a_tile = smem + kSmemA + slot * kABytes;
+    float* stage = reinterpret_cast<float*>(smem + kSmemStaging) + e * 32 * kStageStride;
+    const uint32_t tmem_row = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 256);
+    uint32_t acc_phase = 0;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = pair * 2 + slot;
+      if (tile >= n_tiles) continue;
+      const int64_t row0 = tile * kRows;
+      if (IN_STATES)
+        load_state_tile(a_tile, P.lo, P.hi, row0, P.rows, gtid, s_lut);
+      else
+        load_x_tile(a_tile, P.x, row0, P.rows, gwarp, lane);
+      fence_async_smem();
+      mbar_arrive(bar_ready + 8 * slot);
+      float best = -3.0e38f;
+#pragma unroll 1
+      for (int j = 0; j < 5; j++) {
+        const Job jb = c_jobs[j];
+        mbar_wait(bar_acc + 8 * slot, acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after();
+        const int ncol = jb.nb >> 1;          // this warp's share of the block's columns
+        const int cbase = half * ncol;
+        if (j < 2 || OUT_MAX) {
+          // 32-column chunks, the TMEM load of chunk c+1 in flight while chunk c is processed
+          uint32_t va[32], vb[32];
+          const int nch = ncol >> 5;          // 4 (N = 256) or 1 (N = 64)
+          tmem_ld32(tmem_row + (uint32_t)cbase, va);
+#pragma unroll 1
+          for (int c = 0; c < nch; c += 2) {
+            tmem_wait_ld();
+            if (c + 1 < nch) tmem_ld32(tmem_row + (uint32_t)(cbase + (c + 1) * 32), vb);
+            {
+              const int col = cbase + c * 32;
+              const float4* b4 = reinterpret_cast<const float4*>(s_bias + jb.b_off + col);
+              if (j < 2) {  // hidden layer: + bias, ReLU, bf16, back into the slot's operand tile
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                  const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+                  uint4 pk;
+                  pk.x = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 0]) + ba.x, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 1]) + ba.y, 0.0f));
+                  pk.y = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 2]) + ba.z, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 3]) + ba.w, 0.0f));
+                  pk.z = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 4]) + bb.x, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 5]) + bb.y, 0.0f));
+                  pk.w = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 6]) + bb.z, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 7]) + bb.w, 0.0f));
+                  *reinterpret_cast<uint4*>(a_tile + tile_off(kRows, r, col + g * 8)) = pk;
+                }
+              } else {      // afterstate score: running max over the row's Q-values
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                  const float4 bq = b4[g];
+                  best = fmaxf(best, fmaxf(fmaxf(__uint_as_float(va[g * 4 + 0]) + bq.x, __uint_as_float(va[g * 4 + 1]) + bq.y),
+                                           fmaxf(__uint_as_float(va[g * 4 + 2]) + bq.z, __uint_as_float(va[g * 4 + 3]) + bq.w)));
+                }
+              }
+            }
+            if (c + 1 < nch) {
+              tmem_wait_ld();
+              if (c + 2 < nch) tmem_ld32(tmem_row + (uint32_t)(cbase + (c + 2) * 32), va);
+              const int col = cbase + (c + 1) * 32;
+              const float4* b4 = reinterpret_cast<const float4*>(s_bias + jb.b_off + col);
+              if (j < 2) {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                  const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+                  uint4 pk;
+                  pk.x = pack_bf16(fmaxf(__uint_as_float(vb[g * 8 + 0]) + ba.x, 0.0f), fmaxf(__uint_as_float(vb[g * 8 + 1]) + ba.y, 0.0f));
+                  pk.y = pack_bf16(fmaxf(__uint_as_float(vb[g * 8 + 2]) + ba.z, 0.0f), fmaxf(__uint_as_float(vb[g * 8 + 3]) + ba.w, 0.0f));
+                  pk.z = pack_bf16(fmaxf(__uint_as_float(vb[g * 8 + 4]) + bb.x, 0.0f), fmaxf(__uint_as_float(vb[g * 8 + 5]) + bb.y, 0.0f));
+                  pk.w = pack_bf16(fmaxf(__uint_as_float(vb[g * 8 + 6]) + bb.z, 0.0f), fmaxf(__uint_as_float(vb[g * 8 + 7]) + bb.w, 0.0f));
+                  *reinterpret_cast<uint4*>(a_tile + tile_off(kRows, r, col + g * 8)) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                  const float4 bq = b4[g];
+                  best = fmaxf(best, fmaxf(fmaxf(__uint_as_float(vb[g * 4 + 0]) + bq.x, __uint_as_float(vb[g * 4 + 1]) + bq.y),
+                                           fmaxf(__uint_as_float(vb[g * 4 + 2]) + bq.z, __uint_as_float(vb[g * 4 + 3]) + bq.w)));
+                }
+              }
+            }
+          }
+          if (j < 2) fence_async_smem();
+          if (OUT_MAX && j == 4) {
+            // the two warps of a quarter hold the max over their column halves: combine through shared memory
+            float* xch = reinterpret_cast<float*>(smem + kSmemStaging) + slot * 128;
+            if (half == 1) xch[r] = best;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");  // the slot's 8 epilogue warps
+            if (half == 0 && row0 + r < P.rows) P.score[row0 + r] = fmaxf(best, xch[r]);
+          }
+        } else {
+          // fp32 Q-values: 16 columns at a time through the warp's transpose buffer, then coalesced
+          // 16-byte lanes: 8 rows x 64 B per store instruction; the next TMEM load is in flight meanwhile
+          uint32_t v[16];
+          const int nch = ncol / kStageCols;
+          tmem_ld16(tmem_row + (uint32_t)cbase, v);
+#pragma unroll 1
+          for (int c = 0; c < nch; c++) {
+            tmem_wait_ld();
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+              *reinterpret_cast<float4*>(stage + lane * kStageStride + g * 4) =
+                  make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                              __uint_as_float(v[g * 4 + 3]));
+            if (c + 1 < nch) tmem_ld16(tmem_row + (uint32_t)(cbase + (c + 1) * kStageCols), v);
+            __syncwarp();
+            const int c4 = (lane & 3) * 4, col = cbase + c * kStageCols + c4;
+            const float4 bv = *reinterpret_cast<const float4*>(s_bias + jb.b_off + col);
+#pragma unroll
+            for (int rb = 0; rb < 4; rb++) {
+              const int rr = rb * 8 + (lane >> 2);
+              float4 o = *reinterpret_cast<const float4*>(stage + rr * kStageStride + c4);
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              const int64_t gr = row0 + quarter * 32 + rr;
+              if (gr < P.rows) *reinterpret_cast<float4*>(P.q + gr * kOut + jb.col0 + col) = o;
+            }
+            __syncwarp();
+          }
+        }
+        if (j < 4) {  // accumulator drained (and operand tile rewritten): the slot's next job may start
+          tc_fence_before();
+          mbar_arrive(bar_ready + 8 * slot);
+        }
+      }
+      tc_fence_before();  // the next tile's "ready" arrival follows the x load above
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
-bool g_mlp_attr_set = false;
+bool g_mlp_attr_set[4] = {false, false, false, false};
+
+template <bool IN_STATES, bool OUT_MAX>
+int launch_mlp(const Params& P, void* stream) {
+  const int which = (IN_STATES ? 2 : 0) + (OUT_MAX ? 1 : 0);
+  if (!g_mlp_attr_set[which]) {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp<IN_STATES, OUT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Map<OUT_MAX>::bytes);
+    if (e != cudaSuccess) return (int)e;
+    g_mlp_attr_set[which] = true;
+  }
+  int64_t tiles = (P.rows + kRows - 1) / kRows, pairs = (tiles + 1) / 2;
+  int grid = (int)(pairs < 148 ? pairs : 148);
+  k_mlp<IN_STATES, OUT_MAX><<<grid, kThreads, Map<OUT_MAX>::bytes, (cudaStream_t)stream>>>(P);
+  return (int)cudaGetLastError();
+}
+
+bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 }  // namespace
 
 extern "C" {
 
-// Packed weight layout (see gym_narde_b200/mlp.py:pack_weights): three layers back to back; per
-// layer, per N block of <= 256 output rows, per K chunk of 64: nb x 64 bf16 in the K-major
-// interleave layout (offset = (k/8)*(nb*16) + (n/8)*128 + (n%8)*16 + (k%8)*2), K padded to 256.
+// Packed weight layout (gym_narde_b200/mlp.py:pack_weights): five blocks back to back -- layer 1
+// (N=256, K=208), layer 2 (256, 256), layer 3 columns 0-255, 256-511, 512-575 (K=256) -- each as
+// K stages of 32 (the last stage of layer 1 is 16): nb x klen bf16 in the K-major interleave layout
+// (offset(n, k) = (k/8)*(nb*16) + (n/8)*128 + (n%8)*16 + (k%8)*2).  bias: 256 + 256 + 576 floats.
 int narde_mlp_forward(const float* x, int64_t rows, const void* wpack, const float* bias, float* q, void* stream) {
   if (rows == 0) return 0;
   if (rows < 0 || !x || !wpack || !bias || !q) return -1;
-  if ((((uintptr_t)wpack) & 15u) != 0 || (((uintptr_t)q) & 15u) != 0) return -1;
-  if (!g_mlp_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_mlp_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    g_mlp_attr_set = true;
-  }
-  const uint8_t* w = (const uint8_t*)wpack;
-  Layer L1 = {w, bias, kH};
-  Layer L2 = {w + (size_t)kH * kK * 2, bias + kH, kH};
-  Layer L3 = {w + (size_t)2 * kH * kK * 2, bias + 2 * kH, kOut};
-  int64_t tiles = (rows + kRows - 1) / kRows;
-  int grid = (int)(tiles < 148 ? tiles : 148);
-  k_mlp_forward<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(x, rows, L1, L2, L3, q);
-  return (int)cudaGetLastError();
+  if (!aligned16(wpack) || !aligned16(q) || (((uintptr_t)x) & 7u) != 0) return -1;
+  Params P = {x, nullptr, nullptr, rows, (const uint8_t*)wpack, bias, q, nullptr};
+  return launch_mlp<false, false>(P, stream);
+}
+
+int narde_mlp_score(const float* x, int64_t rows, const void* wpack, const float* bias, float* score, void* stream) {
+  if (rows == 0) return 0;
+  if (rows < 0 || !x || !wpack || !bias || !score) return -1;
+  if (!aligned16(wpack) || (((uintptr_t)x) & 7u) != 0) return -1;
+  Params P = {x, nullptr, nullptr, rows, (const uint8_t*)wpack, bias, nullptr, score};
+  return launch_mlp<false, true>(P, stream);
+}
+
+int narde_mlp_forward_states(const void* lo, const void* hi, int64_t rows, const void* wpack, const float* bias, float* q,
+                             void* stream) {
+  if (rows == 0) return 0;
+  if (rows < 0 || !lo || !hi || !wpack || !bias || !q) return -1;
+  if (!aligned16(wpack) || !aligned16(q) || !aligned16(lo) || !aligned16(hi)) return -1;
+  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, (const uint8_t*)wpack, bias, q, nullptr};
+  return launch_mlp<true, false>(P, stream);
+}
+
+int narde_mlp_score_states(const void* lo, const void* hi, int64_t rows, const void* wpack, const float* bias, float* score,
+                           void* stream) {
+  if (rows == 0) return 0;
+  if (rows < 0 || !lo || !hi || !wpack || !bias || !score) return -1;
+  if (!aligned16(wpack) || !aligned16(lo) || !aligned16(hi)) return -1;
+  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, (const uint8_t*)wpack, bias, nullptr, score};
+  return launch_mlp<true, true>(P, stream);
 }
 
 }  // extern "C"

@@ -13,19 +13,20 @@ import numpy as np
 
 from . import _cabi
 
-IN, HID, OUT, KPAD, KC = 198, 256, 576, 256, 64
+IN, HID, OUT, K1, KC = 198, 256, 576, 208, 32
 
 
 def _pack_block(w_blk):
-    """w_blk: [nb, 256] float32 (K padded) -> bytes of 4 K-chunk stages in K-major interleave layout:
-    offset(n, k) = (k//8)*(nb*16) + (n//8)*128 + (n%8)*16 + (k%8)*2 within a stage of nb x 64."""
+    """w_blk: [nb, K] float32 (K a multiple of 16) -> bf16 stages of 32 K (the last may be 16) in the K-major
+    interleave layout: offset(n, k) = (k//8)*(nb*16) + (n//8)*128 + (n%8)*16 + (k%8)*2 within a stage."""
     import torch
 
-    nb = w_blk.shape[0]
+    nb, k = w_blk.shape
     stages = []
-    for c in range(KPAD // KC):
-        s = w_blk[:, c * KC:(c + 1) * KC].to(torch.bfloat16)          # [nb, 64]
-        s = s.reshape(nb // 8, 8, KC // 8, 8).permute(2, 0, 1, 3)      # [kchunk, rowgroup, row, k]
+    for k0 in range(0, k, KC):
+        klen = min(KC, k - k0)
+        s = w_blk[:, k0:k0 + klen].to(torch.bfloat16)                   # [nb, klen]
+        s = s.reshape(nb // 8, 8, klen // 8, 8).permute(2, 0, 1, 3)      # [kchunk, rowgroup, row, k]
         stages.append(s.contiguous().view(torch.int16).reshape(-1))
     return torch.cat(stages)
 
@@ -35,7 +36,7 @@ def pack_weights(w1, b1, w2, b2, w3, b3):
     import torch
 
     assert tuple(w1.shape) == (HID, IN) and tuple(w2.shape) == (HID, HID) and tuple(w3.shape) == (OUT, HID)
-    w1p = torch.zeros((HID, KPAD), dtype=torch.float32, device=w1.device)
+    w1p = torch.zeros((HID, K1), dtype=torch.float32, device=w1.device)
     w1p[:, :IN] = w1.float()
     parts = [_pack_block(w1p), _pack_block(w2.float())]
     for n0 in range(0, OUT, 256):
@@ -46,13 +47,16 @@ def pack_weights(w1, b1, w2, b2, w3, b3):
 
 
 class AfterstateMLP:
-    """q = forward(x): x float32 [K,198] on the GPU -> float32 [K,576] (move1 Q-values)."""
+    """DecomposedDQN.forward(x) with state_size 198 on the tcgen05 tensor cores.
+
+    forward(x)            x float32 [K,198]            -> q float32 [K,576]   (move1 Q-values)
+    score(x)              x float32 [K,198]            -> max_a q[:, a]  float32 [K]
+    forward_states(lo,hi) packed states [K,16] uint8 x2 -> q   (Box(198) encoded inside the kernel)
+    score_states(lo,hi)   packed states                -> max_a q[:, a]       (the afterstate score)"""
 
     def __init__(self, w1, b1, w2, b2, w3, b3):
         torch = _cabi.require_cuda()
         lib = _cabi.load()
-        lib.narde_mlp_forward.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        lib.narde_mlp_forward.restype = C.c_int
         self.torch, self.lib = torch, lib
         self.wpack, self.bias = pack_weights(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), w3.cuda(), b3.cuda())
 
@@ -62,18 +66,67 @@ class AfterstateMLP:
         l1, l2 = feature_network[0], feature_network[2]
         return cls(l1.weight.data, l1.bias.data, l2.weight.data, l2.bias.data, move1_head.weight.data, move1_head.bias.data)
 
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def _check_x(self, x):
+        t = self.torch
+        if not (x.is_cuda and x.dtype == t.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[1] == IN):
+            raise _cabi.NardeCudaError("x must be a contiguous CUDA float32 [K,198] tensor")
+
+    def _check_states(self, lo, hi):
+        t = self.torch
+        for a in (lo, hi):
+            if not (a.is_cuda and a.dtype == t.uint8 and a.is_contiguous() and a.dim() == 2 and a.shape[1] == 16):
+                raise _cabi.NardeCudaError("states must be contiguous CUDA uint8 [K,16] planes")
+        if lo.shape[0] != hi.shape[0]:
+            raise _cabi.NardeCudaError("lo/hi planes differ in length")
+
+    def _run(self, fn, args, what):
+        rc = fn(*args, self._stream())
+        if rc != 0:
+            raise _cabi.NardeCudaError("%s failed: %d" % (what, rc))
+
     def forward(self, x, out=None):
         t = self.torch
-        if not (x.is_cuda and x.dtype == t.float32 and x.is_contiguous() and x.shape[1] == IN):
-            raise _cabi.NardeCudaError("x must be a contiguous CUDA float32 [K,198] tensor")
+        self._check_x(x)
         k = x.shape[0]
         if out is None:
             out = t.empty((k, OUT), dtype=t.float32, device=x.device)
-        rc = self.lib.narde_mlp_forward(C.c_void_p(x.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
-                                        C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr()),
-                                        C.c_void_p(t.cuda.current_stream().cuda_stream))
-        if rc != 0:
-            raise _cabi.NardeCudaError("narde_mlp_forward failed: %d" % rc)
+        self._run(self.lib.narde_mlp_forward, (C.c_void_p(x.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
+                                               C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_forward")
+        return out
+
+    def score(self, x, out=None):
+        t = self.torch
+        self._check_x(x)
+        k = x.shape[0]
+        if out is None:
+            out = t.empty(k, dtype=t.float32, device=x.device)
+        self._run(self.lib.narde_mlp_score, (C.c_void_p(x.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
+                                             C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_score")
+        return out
+
+    def forward_states(self, lo, hi, out=None):
+        t = self.torch
+        self._check_states(lo, hi)
+        k = lo.shape[0]
+        if out is None:
+            out = t.empty((k, OUT), dtype=t.float32, device=lo.device)
+        self._run(self.lib.narde_mlp_forward_states,
+                  (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
+                   C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_forward_states")
+        return out
+
+    def score_states(self, lo, hi, out=None, rows=None):
+        t = self.torch
+        self._check_states(lo, hi)
+        k = lo.shape[0] if rows is None else int(rows)
+        if out is None:
+            out = t.empty(lo.shape[0], dtype=t.float32, device=lo.device)
+        self._run(self.lib.narde_mlp_score_states,
+                  (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
+                   C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_score_states")
         return out
 
     __call__ = forward

@@ -127,12 +127,24 @@ int narde_obs24(const void *lo, const void *hi, int64_t n, int32_t *obs24, void 
 int narde_apply_actions(void *lo, void *hi, const uint64_t *acts, int64_t n, int32_t flags,
                         float *reward, uint8_t *done, void *stream);
 
-/* DecomposedDQN.forward(x) with state_size 198 (train_deepq_pytorch.py:184-236) for `rows` afterstate
- * observations: x [rows,198] f32 -> q [rows,576] f32.  bf16 operands, fp32 accumulation on the
- * tcgen05 tensor cores.  wpack / bias: weights re-packed by gym_narde_b200/mlp.py:pack_weights
- * (K-major interleave operand layout, K padded to 256) and the three bias vectors back to back. */
+/* DecomposedDQN.forward(x) with state_size 198 (train_deepq_pytorch.py:184-236: Linear(198,256)-ReLU-
+ * Linear(256,256)-ReLU-Linear(256,576)) for `rows` afterstate observations, bf16 operands and fp32
+ * accumulation on the tcgen05 tensor cores.  wpack / bias: weights re-packed by
+ * gym_narde_b200/mlp.py:pack_weights (K-major interleave operand stages) and the three bias vectors
+ * back to back (1088 floats).
+ *   narde_mlp_forward         x [rows,198] f32 (README.md:44-102 rows) -> q [rows,576] f32
+ *   narde_mlp_score           x [rows,198] f32 -> score [rows] f32 = max_a q[row, a]
+ *   narde_mlp_forward_states  packed states (lo/hi planes as above) -> q; the Box(198) encoding is
+ *                             computed inside the kernel (32 B per row read instead of 792 B)
+ *   narde_mlp_score_states    packed states -> score: the afterstate-scoring call of the actor */
 int narde_mlp_forward(const float *x, int64_t rows, const void *wpack, const float *bias, float *q,
                       void *stream);
+int narde_mlp_score(const float *x, int64_t rows, const void *wpack, const float *bias, float *score,
+                    void *stream);
+int narde_mlp_forward_states(const void *lo, const void *hi, int64_t rows, const void *wpack,
+                             const float *bias, float *q, void *stream);
+int narde_mlp_score_states(const void *lo, const void *hi, int64_t rows, const void *wpack,
+                           const float *bias, float *score, void *stream);
 
 /* *counter += 1 on the device (one tiny launch); see step_dev above. */
 int narde_advance_counter(uint64_t *counter, void *stream);

@@ -52,3 +52,25 @@ def test_mlp_matches_fp32_reference_on_real_observations():
         h2 = torch.relu(fn[2](h1)).to(torch.bfloat16).float()
         ref2 = head(h2)
     assert (mlp2(xb) - ref2).abs().max().item() < 2e-3
+
+
+def test_mlp_state_input_and_score_modes_agree_with_forward():
+    """The in-kernel Box(198) encoding (packed states in) feeds the MMAs the same bf16 operands as the
+    fp32 observation rows, so Q-values are bit-identical; score = row max of those Q-values."""
+    import torch
+    from gym_narde_b200 import VecNardeEnv
+    from gym_narde_b200.mlp import AfterstateMLP
+    fn, head = _reference_net()
+    mlp = AfterstateMLP.from_module(fn, head)
+    env = VecNardeEnv(3000, seed=11)
+    env.reset()
+    for _ in range(70):                      # mid-game and bear-off positions, both colours to move
+        env.step()
+    obs = env.observe().clone()
+    for rows in (3000, 1, 128, 129, 257, 1000):
+        lo, hi, x = env.lo[:rows].contiguous(), env.hi[:rows].contiguous(), obs[:rows].contiguous()
+        q = mlp.forward(x)
+        qs = mlp.forward_states(lo, hi)
+        assert torch.equal(q, qs), rows
+        assert torch.equal(mlp.score(x), q.max(dim=1).values), rows
+        assert torch.equal(mlp.score_states(lo, hi), q.max(dim=1).values), rows

@@ -3,6 +3,7 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn as nn
+from gym_narde_b200 import VecNardeEnv
 from gym_narde_b200.mlp import AfterstateMLP
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 700416
@@ -10,8 +11,14 @@ torch.manual_seed(0)
 fn = nn.Sequential(nn.Linear(198, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU()).cuda()
 head = nn.Linear(256, 576).cuda()
 mlp = AfterstateMLP.from_module(fn, head)
-x = (torch.rand(rows, 198, device="cuda") < 0.1).float()
+env = VecNardeEnv(rows, seed=5, write_actions=False)
+env.reset()
+for _ in range(40):
+    env.step()
+x = env.observe().clone()
+lo, hi = env.lo, env.hi
 q = torch.empty(rows, 576, device="cuda")
+sc = torch.empty(rows, device="cuda")
 flop = rows * 2 * (198 * 256 + 256 * 256 + 256 * 576)
 
 def timeit(f, n=10):
@@ -24,12 +31,17 @@ def timeit(f, n=10):
     torch.cuda.synchronize()
     return min(a.elapsed_time(b) for a, b in ev), sum(a.elapsed_time(b) for a, b in ev) / n
 
-best, mean = timeit(lambda: mlp.forward(x, out=q))
+res = {"rows": rows}
+for name, f in (("forward_x_q", lambda: mlp.forward(x, out=q)), ("score_x", lambda: mlp.score(x, out=sc)),
+                ("forward_states_q", lambda: mlp.forward_states(lo, hi, out=q)),
+                ("score_states", lambda: mlp.score_states(lo, hi, out=sc))):
+    best, mean = timeit(f)
+    res[name] = {"ms": mean, "best_ms": best, "tflops": flop / mean / 1e9, "rows_per_s": rows / mean * 1e3}
 with torch.no_grad():
     tb, tm = timeit(lambda: head(fn(x)))
     fb = nn.Sequential(fn, head).to(torch.bfloat16)
     xb = x.to(torch.bfloat16)
     bb, bm = timeit(lambda: fb(xb))
-print(json.dumps({"rows": rows, "ours_ms": mean, "ours_best_ms": best, "ours_tflops": flop / mean / 1e9,
-                  "rows_per_s": rows / mean * 1e3, "torch_fp32_ms": tm, "torch_fp32_tflops": flop / tm / 1e9,
-                  "torch_bf16_ms": bm, "torch_bf16_tflops": flop / bm / 1e9}))
+res["torch_fp32"] = {"ms": tm, "tflops": flop / tm / 1e9}
+res["torch_bf16"] = {"ms": bm, "tflops": flop / bm / 1e9}
+print(json.dumps(res))
