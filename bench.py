@@ -289,6 +289,11 @@ def run_cuda_arm(args):
     torch.cuda.synchronize()
     ms_small = timed_loop(lambda: small.step(), min(K, 50))
 
+    # ---- config 5 side measurement: afterstate scoring with the tcgen05 MLP, 64K envs (rank 0's GPU) ----
+    cfg5 = None
+    if not args.no_config5 and rank == 0:
+        cfg5 = config5_afterstate_scoring(torch, dev, args, timed_loop)
+
     # ---- reduce over ranks (MAX time), gather episode stats with NCCL ----
     tmax = torch.tensor([total_ms, total_e2e], dtype=torch.float64, device=dev)
     st = env.stats.clone()
@@ -339,6 +344,8 @@ def run_cuda_arm(args):
                                   "ms_per_step": sum(ms_small) / len(ms_small)},
             "episode_stats": {k: int(v) for k, v in zip(_cabi.STAT_NAMES, st_all.sum(0).tolist())},
         }
+        if cfg5 is not None:
+            line["config5_afterstate_scoring"] = cfg5
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             v, n, a, wall = cpu_selfplay(cores, 64, 150)
@@ -348,6 +355,55 @@ def run_cuda_arm(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def config5_afterstate_scoring(torch, dev, args, timed_loop):
+    """BASELINE config 5: DecomposedDQN(198) (train_deepq_pytorch.py:184-236, torch.manual_seed(0) random init) over
+    all legal afterstates of 65536 envs: enumerate -> afterstates -> Box(198) encode + 3-layer MLP + max_a Q
+    on the tcgen05 tensor cores -> greedy choice -> env step, all on the device (AfterstateActor)."""
+    import torch.nn as nn
+    from gym_narde_b200 import VecNardeEnv, AfterstateMLP, AfterstateActor
+    torch.manual_seed(0)
+    fn = nn.Sequential(nn.Linear(198, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU()).to(dev)
+    head = nn.Linear(256, 576).to(dev)
+    mlp = AfterstateMLP.from_module(fn, head)
+    E5 = 65536
+    env = VecNardeEnv(E5, seed=SEED, max_actions=args.cap, device=dev)
+    actor = AfterstateActor(env, mlp)
+    env.reset()
+    for _ in range(60):                      # random self-play burn-in, then greedy turns
+        env.step()
+    for _ in range(5):
+        actor.step()
+    torch.cuda.synchronize()
+    k = max(5, min(args.steps, 30))
+    rows = []
+
+    def greedy_step():
+        actor.step()
+        rows.append(actor.rows_dev.clone())
+
+    ms_actor = timed_loop(greedy_step, k)
+    mean_rows = float(torch.stack(rows).float().mean().item())
+    # the scorer alone on the last step's afterstates (same rows, L2 flushed between launches)
+    ms_mlp = timed_loop(lambda: mlp.score_states(actor.as_lo, actor.as_hi, out=actor.scores, rows_dev=actor.rows_dev), k)
+    last_rows = int(actor.rows_dev.item())
+    flop_row = 2 * (198 * 256 + 256 * 256 + 256 * 576)
+    mlp_ms = sum(ms_mlp) / len(ms_mlp)
+    tfl = last_rows * flop_row / (mlp_ms * 1e-3) / 1e12
+    peak_tf = 1361.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        try:
+            peak_tf = float(json.load(open(pk))["bf16_tflops_sustained"])
+        except Exception:
+            pass
+    return {"envs": E5, "greedy_env_steps_per_s": E5 * k / (sum(ms_actor) * 1e-3), "ms_per_greedy_step": sum(ms_actor) / k,
+            "afterstate_rows_per_step": mean_rows, "scorer_rows": last_rows, "scorer_ms": mlp_ms,
+            "scorer_rows_per_s": last_rows / (mlp_ms * 1e-3), "scorer_tflops": tfl,
+            "scorer_frac_of_bf16_peak": tfl / peak_tf, "bf16_peak_tflops": peak_tf,
+            "flops_per_row": flop_row, "dtype": "bf16 operands, fp32 accumulate (tcgen05)",
+            "note": "k_mlp<states in, row-max out>: Box(198) encoded in-kernel from 32-byte afterstates; weights random init"}
 
 
 def main():
@@ -363,6 +419,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=None)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -3,6 +3,7 @@
 Public surface (mirrors gym_narde/__init__.py + gym_narde/envs):
   gym_narde_b200.envs.NardeEnv / Narde   single-game facade, same names as the reference
   gym_narde_b200.VecNardeEnv             N lock-step games on the GPU
+  gym_narde_b200.AfterstateMLP / AfterstateActor   DecomposedDQN(198) scorer and the greedy batched actor
   gym_narde_b200.make(id)                'narde-v0' (reference rules) / 'Narde-v0' (README rules)
 When gymnasium is importable both ids are also registered with it (max_episode_steps=1000, as
 gym_narde/__init__.py:3-7 does).
@@ -20,6 +21,12 @@ def _lazy(name):
     if name == "Narde":
         from .envs.narde import Narde
         return Narde
+    if name == "AfterstateMLP":
+        from .mlp import AfterstateMLP
+        return AfterstateMLP
+    if name == "AfterstateActor":
+        from .actor import AfterstateActor
+        return AfterstateActor
     raise AttributeError(name)
 
 

@@ -1,0 +1,76 @@
+"""Batched afterstate-greedy actor: the device-resident replacement of
+the per-move loop of DQNAgent.act (train_deepq_pytorch.py:411-600).
+
+Per lock-step turn, entirely on the GPU and without a host synchronisation:
+    roll (Philox) -> get_valid_actions (full legal-turn enumeration) -> afterstate of every legal
+    action (narde_afterstates) -> Box(198) encoding + DecomposedDQN(198) forward + max_a Q on the
+    tcgen05 tensor cores (narde_mlp_score_states) -> greedy choice per env (narde_segment_argmax)
+    -> VecNardeEnv.step(action_idx, dice).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _cabi
+
+
+class AfterstateActor:
+    def __init__(self, env, mlp, mode="max"):
+        """env: VecNardeEnv(rules="full"); mlp: AfterstateMLP; mode: "max" (the mover maximises the score)
+        or "white_value" (the net scores positions for WHITE: WHITE maximises, BLACK minimises)."""
+        if env.rules != "full":
+            raise ValueError("AfterstateActor needs rules='full'")
+        if mode not in ("max", "white_value"):
+            raise ValueError("mode must be 'max' or 'white_value'")
+        t = env.torch
+        self.env, self.mlp, self.mode = env, mlp, 0 if mode == "max" else 1
+        n, cap, dev = env.num_envs, env.max_actions, env.device
+        self.cap = cap
+        self.as_lo = t.zeros((n * cap, 16), dtype=t.uint8, device=dev)   # afterstate planes, ragged rows packed
+        self.as_hi = t.zeros((n * cap, 16), dtype=t.uint8, device=dev)
+        self.scores = t.zeros(n * cap, dtype=t.float32, device=dev)
+        self.offsets = t.zeros(n, dtype=t.int64, device=dev)
+        self.rows_dev = t.zeros(1, dtype=t.int64, device=dev)
+        self.choice = t.zeros(n, dtype=t.int32, device=dev)
+        self.value = t.zeros(n, dtype=t.float32, device=dev)
+        self.dice = t.zeros((n, 2), dtype=t.uint8, device=dev)
+        self.lib = _cabi.load()
+
+    def _stream(self):
+        return C.c_void_p(self.env.torch.cuda.current_stream().cuda_stream)
+
+    def afterstates(self, actions, counts):
+        """Fill as_lo/as_hi with the afterstates of actions[i, :min(counts[i], cap)]; returns offsets [N]."""
+        t, env = self.env.torch, self.env
+        c = counts.clamp(max=self.cap).to(t.int64)
+        incl = t.cumsum(c, 0)
+        t.sub(incl, c, out=self.offsets)
+        self.rows_dev.copy_(incl[-1:])
+        rc = self.lib.narde_afterstates(C.c_void_p(env.lo.data_ptr()), C.c_void_p(env.hi.data_ptr()),
+                                        C.c_void_p(actions.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                        C.c_void_p(self.offsets.data_ptr()), env.num_envs, self.cap,
+                                        C.c_void_p(self.as_lo.data_ptr()), C.c_void_p(self.as_hi.data_ptr()), None,
+                                        self._stream())
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_afterstates failed: %d" % rc)
+        return self.offsets
+
+    def choose(self):
+        """roll -> enumerate -> afterstates -> score -> greedy index.  Returns (choice [N] int32, dice [N,2])."""
+        env = self.env
+        self.dice.copy_(env.roll())
+        actions, counts, _ = env.get_valid_actions(self.dice)
+        self.afterstates(actions, counts)
+        self.mlp.score_states(self.as_lo, self.as_hi, out=self.scores, rows_dev=self.rows_dev)
+        rc = self.lib.narde_segment_argmax(C.c_void_p(self.scores.data_ptr()), C.c_void_p(self.offsets.data_ptr()),
+                                           C.c_void_p(counts.data_ptr()), C.c_void_p(env.hi.data_ptr()), env.num_envs,
+                                           self.cap, self.mode, C.c_void_p(self.choice.data_ptr()),
+                                           C.c_void_p(self.value.data_ptr()), self._stream())
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
+        return self.choice, self.dice
+
+    def step(self):
+        """One greedy lock-step turn for all envs; returns VecNardeEnv.step's tuple."""
+        choice, dice = self.choose()
+        return self.env.step(choice, dice=dice)

@@ -420,6 +420,56 @@ __global__ void __launch_bounds__(kThreads) k_apply_actions(uint4* lo, uint4* hi
   if (done) done[i] = (uint8_t)dn;
 }
 
+// Afterstates of every stored legal action (README get_valid_actions list): row offsets[i] + k holds the
+// state of env i after action k and the end-of-turn bookkeeping (player switched), as narde_apply_actions
+// would leave it.  Thread per env; rows of neighbouring envs are neighbours in memory.
+__global__ void __launch_bounds__(kThreads) k_afterstates(const uint4* lo, const uint4* hi, const uint64_t* actions,
+                                                         const int32_t* counts, const int64_t* offsets, int64_t n, int cap,
+                                                         uint4* as_lo, uint4* as_hi, int32_t* row_env) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const State s = ld_state(lo, hi, i);
+  int c = counts[i];
+  c = c < cap ? c : cap;
+  const int64_t base = offsets[i];
+  for (int k = 0; k < c; k++) {
+    State t = s;
+    float r;
+    int dn;
+    apply_actions_env(t, actions[i * (int64_t)cap + k], 0, &r, &dn);
+    st_state(as_lo, as_hi, base + k, t);
+    if (row_env) row_env[base + k] = (int32_t)i;
+  }
+}
+
+// Greedy choice per env over its segment of afterstate scores: mode 0 = maximise; mode 1 = WHITE
+// maximises, BLACK minimises (a value net that scores positions for WHITE).  Ties -> lowest index.
+__global__ void __launch_bounds__(kThreads) k_segment_argmax(const float* score, const int64_t* offsets, const int32_t* counts,
+                                                            const uint4* hi, int64_t n, int cap, int mode, int32_t* idx_out,
+                                                            float* best_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = counts[i];
+  c = c < cap ? c : cap;
+  const int64_t base = offsets[i];
+  float sign = 1.0f;
+  if (mode == 1) {
+    const uint32_t meta = hi[i].z;
+    if ((int)(int8_t)((meta >> 16) & 0xFF) != 1) sign = -1.0f;
+  }
+  int best_k = 0;
+  float best = 0.0f;
+  for (int k = 0; k < c; k++) {
+    float v = sign * score[base + k];
+    if (k == 0 || v > best) {
+      best = v;
+      best_k = k;
+    }
+  }
+  idx_out[i] = best_k;
+  if (best_out) best_out[i] = c ? sign * best : 0.0f;
+}
+
 __global__ void __launch_bounds__(kThreads) k_roll_dice(int64_t n, int64_t env_base, uint64_t seed, uint64_t step, uint8_t* dice) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -590,6 +640,25 @@ int narde_apply_actions(void* lo, void* hi, const uint64_t* acts, int64_t n, int
   if (n == 0) return 0;
   if (n < 0 || !lo || !hi || !acts || !aligned16(lo) || !aligned16(hi)) return -1;
   k_apply_actions<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, acts, n, flags, reward, done);
+  return launch_status();
+}
+
+int narde_afterstates(const void* lo, const void* hi, const uint64_t* actions, const int32_t* counts, const int64_t* offsets,
+                      int64_t n, int32_t cap, void* as_lo, void* as_hi, int32_t* row_env, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || cap <= 0 || !lo || !hi || !actions || !counts || !offsets || !as_lo || !as_hi) return -1;
+  if (!aligned16(lo) || !aligned16(hi) || !aligned16(as_lo) || !aligned16(as_hi)) return -1;
+  k_afterstates<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, actions, counts, offsets, n,
+                                                                    cap, (uint4*)as_lo, (uint4*)as_hi, row_env);
+  return launch_status();
+}
+
+int narde_segment_argmax(const float* score, const int64_t* offsets, const int32_t* counts, const void* hi, int64_t n,
+                         int32_t cap, int32_t mode, int32_t* idx_out, float* best_out, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || cap <= 0 || !score || !offsets || !counts || !hi || !idx_out || !aligned16(hi)) return -1;
+  k_segment_argmax<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(score, offsets, counts, (const uint4*)hi, n, cap, mode,
+                                                                       idx_out, best_out);
   return launch_status();
 }
 

@@ -170,7 +170,8 @@ struct Params {
   const float* x;        // [rows,198] fp32 (IN_STATES = false)
   const uint4* lo;       // packed states (IN_STATES = true), include/narde_b200.h layout
   const uint4* hi;
-  int64_t rows;
+  int64_t rows;          // number of rows (upper bound when rows_dev is given)
+  const int64_t* rows_dev;  // optional device-resident row count (no host sync between producer and scorer)
   const uint8_t* w;      // packed weight stages
   const float* bias;     // 1088 floats
   float* q;              // [rows,576] fp32 (OUT_MAX = false)
@@ -240,7 +241,12 @@ __device__ __forceinline__ void load_state_tile(uint8_t* a_tile, const uint4* __
 }
 
 template <bool IN_STATES, bool OUT_MAX>
-__global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P) {
+__global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P_in) {
+  Params P = P_in;
+  if (P.rows_dev) {
+    const int64_t rd = *P.rows_dev;
+    P.rows = rd < P.rows ? (rd < 0 ? 0 : rd) : P.rows;
+  }
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -511,7 +517,7 @@ int narde_mlp_forward(const float* x, int64_t rows, const void* wpack, const flo
   if (rows == 0) return 0;
   if (rows < 0 || !x || !wpack || !bias || !q) return -1;
   if (!aligned16(wpack) || !aligned16(q) || (((uintptr_t)x) & 7u) != 0) return -1;
-  Params P = {x, nullptr, nullptr, rows, (const uint8_t*)wpack, bias, q, nullptr};
+  Params P = {x, nullptr, nullptr, rows, nullptr, (const uint8_t*)wpack, bias, q, nullptr};
   return launch_mlp<false, false>(P, stream);
 }
 
@@ -519,7 +525,7 @@ int narde_mlp_score(const float* x, int64_t rows, const void* wpack, const float
   if (rows == 0) return 0;
   if (rows < 0 || !x || !wpack || !bias || !score) return -1;
   if (!aligned16(wpack) || (((uintptr_t)x) & 7u) != 0) return -1;
-  Params P = {x, nullptr, nullptr, rows, (const uint8_t*)wpack, bias, nullptr, score};
+  Params P = {x, nullptr, nullptr, rows, nullptr, (const uint8_t*)wpack, bias, nullptr, score};
   return launch_mlp<false, true>(P, stream);
 }
 
@@ -528,16 +534,16 @@ int narde_mlp_forward_states(const void* lo, const void* hi, int64_t rows, const
   if (rows == 0) return 0;
   if (rows < 0 || !lo || !hi || !wpack || !bias || !q) return -1;
   if (!aligned16(wpack) || !aligned16(q) || !aligned16(lo) || !aligned16(hi)) return -1;
-  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, (const uint8_t*)wpack, bias, q, nullptr};
+  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, nullptr, (const uint8_t*)wpack, bias, q, nullptr};
   return launch_mlp<true, false>(P, stream);
 }
 
-int narde_mlp_score_states(const void* lo, const void* hi, int64_t rows, const void* wpack, const float* bias, float* score,
-                           void* stream) {
+int narde_mlp_score_states(const void* lo, const void* hi, int64_t rows, const int64_t* rows_dev, const void* wpack,
+                           const float* bias, float* score, void* stream) {
   if (rows == 0) return 0;
   if (rows < 0 || !lo || !hi || !wpack || !bias || !score) return -1;
   if (!aligned16(wpack) || !aligned16(lo) || !aligned16(hi)) return -1;
-  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, (const uint8_t*)wpack, bias, nullptr, score};
+  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, rows_dev, (const uint8_t*)wpack, bias, nullptr, score};
   return launch_mlp<true, true>(P, stream);
 }
 

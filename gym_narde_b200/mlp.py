@@ -118,14 +118,16 @@ class AfterstateMLP:
                    C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_forward_states")
         return out
 
-    def score_states(self, lo, hi, out=None, rows=None):
+    def score_states(self, lo, hi, out=None, rows_dev=None):
+        """rows_dev: optional int64 CUDA tensor [1]; only min(rows_dev, len(lo)) rows are scored (no host sync)."""
         t = self.torch
         self._check_states(lo, hi)
-        k = lo.shape[0] if rows is None else int(rows)
+        k = lo.shape[0]
         if out is None:
-            out = t.empty(lo.shape[0], dtype=t.float32, device=lo.device)
+            out = t.empty(k, dtype=t.float32, device=lo.device)
         self._run(self.lib.narde_mlp_score_states,
-                  (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
+                  (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k,
+                   C.c_void_p(rows_dev.data_ptr() if rows_dev is not None else None), C.c_void_p(self.wpack.data_ptr()),
                    C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_score_states")
         return out
 

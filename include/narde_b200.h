@@ -143,8 +143,26 @@ int narde_mlp_score(const float *x, int64_t rows, const void *wpack, const float
                     void *stream);
 int narde_mlp_forward_states(const void *lo, const void *hi, int64_t rows, const void *wpack,
                              const float *bias, float *q, void *stream);
-int narde_mlp_score_states(const void *lo, const void *hi, int64_t rows, const void *wpack,
-                           const float *bias, float *score, void *stream);
+int narde_mlp_score_states(const void *lo, const void *hi, int64_t rows, const int64_t *rows_dev,
+                           const void *wpack, const float *bias, float *score, void *stream);
+/* rows_dev (may be NULL): device-resident row count, min(*rows_dev, rows) rows are scored -- lets the
+ * afterstate generator and the scorer run back to back without a host synchronisation. */
+
+/* The afterstate of every stored legal turn action (the batched form of the enumeration loop of
+ * DQNAgent.act, train_deepq_pytorch.py:430-507): row offsets[i] + k of (as_lo, as_hi) = state of
+ * environment i after actions[i*cap + k] and the end-of-turn bookkeeping of narde_apply_actions, for
+ * k < min(counts[i], cap).  offsets: [n] i64 exclusive prefix sums of min(counts, cap) (caller computes).
+ * row_env (may be NULL): [rows] i32, the environment of each row. */
+int narde_afterstates(const void *lo, const void *hi, const uint64_t *actions, const int32_t *counts,
+                      const int64_t *offsets, int64_t n, int32_t cap, void *as_lo, void *as_hi,
+                      int32_t *row_env, void *stream);
+
+/* Greedy policy over each environment's segment of afterstate scores: idx_out[i] = argmax_k
+ * score[offsets[i] + k] (mode 0), or argmin when BLACK is to move (mode 1: the net scores positions for
+ * WHITE).  best_out (may be NULL): the chosen score.  Ties: lowest index; empty segment: 0. */
+int narde_segment_argmax(const float *score, const int64_t *offsets, const int32_t *counts, const void *hi,
+                         int64_t n, int32_t cap, int32_t mode, int32_t *idx_out, float *best_out,
+                         void *stream);
 
 /* *counter += 1 on the device (one tiny launch); see step_dev above. */
 int narde_advance_counter(uint64_t *counter, void *stream);
