@@ -290,9 +290,11 @@ def run_cuda_arm(args):
     ms_small = timed_loop(lambda: small.step(), min(K, 50))
 
     # ---- config 5 side measurement: afterstate scoring with the tcgen05 MLP, 64K envs (rank 0's GPU) ----
-    cfg5 = None
+    cfg5 = cfg3 = None
     if not args.no_config5 and rank == 0:
         cfg5 = config5_afterstate_scoring(torch, dev, args, timed_loop)
+    if not args.no_config3 and rank == 0:
+        cfg3 = config3_enumeration_microbench(torch, dev, args, timed_loop, measured_peaks()[0])
 
     # ---- reduce over ranks (MAX time), gather episode stats with NCCL ----
     tmax = torch.tensor([total_ms, total_e2e], dtype=torch.float64, device=dev)
@@ -346,6 +348,8 @@ def run_cuda_arm(args):
         }
         if cfg5 is not None:
             line["config5_afterstate_scoring"] = cfg5
+        if cfg3 is not None:
+            line["config3_enumeration_microbench"] = cfg3
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             v, n, a, wall = cpu_selfplay(cores, 64, 150)
@@ -355,6 +359,80 @@ def run_cuda_arm(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def config3_enumeration_microbench(torch, dev, args, timed_loop, peak):
+    """BASELINE config 3: get_valid_actions over 1M synthetic positions, seed 1234, three strata:
+    A 40% self-play states sampled at a uniformly random ply in [0,90]; B 30% stratum-A states with the dice
+    forced to doubles; C 30% bear-off races (15-k mover checkers over points 0..5, 15-k' opponent checkers over
+    the mover-frame points 12..17, first_turn False, uniform dice)."""
+    from gym_narde_b200 import VecNardeEnv, _cabi
+    g = torch.Generator(device=dev).manual_seed(1234)
+    n = 1 << 20
+    nA, nB = int(0.4 * n), int(0.3 * n)
+    nC = n - nA - nB
+    env = VecNardeEnv(nA, seed=1234, max_actions=1, device=dev, write_actions=False)
+    env.reset()
+    target = torch.randint(0, 91, (nA,), device=dev, generator=g)
+    lo_a, hi_a = env.lo.clone(), env.hi.clone()
+    for t in range(1, 91):
+        env.step()
+        m = (target == t)[:, None]
+        lo_a = torch.where(m, env.lo, lo_a)
+        hi_a = torch.where(m, env.hi, hi_a)
+    dice_a = torch.randint(1, 7, (nA, 2), device=dev, generator=g).to(torch.uint8)
+    pick = torch.randint(0, nA, (nB,), device=dev, generator=g)
+    d = torch.randint(1, 7, (nB, 1), device=dev, generator=g).to(torch.uint8)
+    lo_b, hi_b, dice_b = lo_a[pick], hi_a[pick], d.expand(nB, 2).contiguous()
+    # stratum C, absolute frame with WHITE (= mover) to move
+    k_m = torch.randint(0, 15, (nC,), device=dev, generator=g)
+    k_o = torch.randint(0, 15, (nC,), device=dev, generator=g)
+    board = torch.zeros((nC, 24), dtype=torch.int32, device=dev)
+    slots = torch.arange(15, device=dev)[None, :]
+    pm = torch.randint(0, 6, (nC, 15), device=dev, generator=g)
+    po = torch.randint(12, 18, (nC, 15), device=dev, generator=g)
+    board.scatter_add_(1, pm, (slots < (15 - k_m)[:, None]).to(torch.int32))
+    board.scatter_add_(1, po, -(slots < (15 - k_o)[:, None]).to(torch.int32))
+    planes = torch.zeros((nC, 32), dtype=torch.uint8, device=dev)
+    planes[:, :24] = board.to(torch.int8).view(torch.uint8)
+    planes[:, 24] = k_m.to(torch.uint8)
+    planes[:, 25] = k_o.to(torch.uint8)
+    planes[:, 26] = 1                                              # WHITE to move; flags 0 (first_turn False)
+    lo_c, hi_c = planes[:, :16].contiguous(), planes[:, 16:].contiguous()
+    dice_c = torch.randint(1, 7, (nC, 2), device=dev, generator=g).to(torch.uint8)
+    lo = torch.cat([lo_a, lo_b, lo_c]).contiguous()
+    hi = torch.cat([hi_a, hi_b, hi_c]).contiguous()
+    dice = torch.cat([dice_a, dice_b, dice_c]).contiguous()
+    cap = args.cap
+    actions = torch.zeros((n, cap), dtype=torch.int64, device=dev)
+    counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    ovf = torch.zeros(n, dtype=torch.uint8, device=dev)
+    ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    run = lambda: _cabi.enumerate_actions_fast(lo, hi, dice, actions, counts, ovf, ws)
+    for _ in range(3):
+        run()
+    k = max(5, min(args.steps, 20))
+    ms = timed_loop(run, k)
+    mean_ms = sum(ms) / k
+    # cross-check against the independent thread-per-env enumerator on a 10k-position subsample
+    sub = torch.randperm(n, device=dev, generator=g)[:10000]
+    a2 = torch.zeros((10000, cap), dtype=torch.int64, device=dev)
+    c2 = torch.zeros(10000, dtype=torch.int32, device=dev)
+    _cabi.enumerate_actions(lo[sub].contiguous(), hi[sub].contiguous(), dice[sub].contiguous(), a2, c2, None)
+    keep = torch.arange(cap, device=dev)[None, :] < c2.clamp(max=cap)[:, None]
+    same = bool(torch.equal(c2, counts[sub]) and torch.equal(a2[keep], actions[sub][keep]))
+    A = float(counts.float().mean().item())
+    bytes_per = 38 + 8 * float(counts.clamp(max=cap).float().mean().item())
+    strata = {}
+    for name, a, b in (("A_selfplay", 0, nA), ("B_doubles", nA, nA + nB), ("C_bearoff", nA + nB, n)):
+        strata[name] = {"positions": b - a, "mean_legal": float(counts[a:b].float().mean().item()),
+                        "max_legal": int(counts[a:b].max().item())}
+    return {"positions": n, "positions_per_s": n / (mean_ms * 1e-3), "ms": mean_ms, "cap": cap, "mean_legal_actions": A,
+            "max_legal_actions": int(counts.max().item()), "overflow_positions": int(ovf.sum().item()),
+            "deferred_exact_positions": int(ws[0].item()), "strata": strata,
+            "subsample_equals_thread_per_env_enumerator": same,
+            "achieved_GBps": n * bytes_per / (mean_ms * 1e-3) / 1e9, "hbm_frac": n * bytes_per / (mean_ms * 1e-3) / 1e9 / peak,
+            "algorithmic_bytes_per_position": bytes_per}
 
 
 def config5_afterstate_scoring(torch, dev, args, timed_loop):
@@ -420,6 +498,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "narde_half_moves": ([_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp], _int),
     "narde_step_ref": ([_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_enumerate": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp], _int),
+    "narde_enumerate_fast": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_step_full": ([_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp, _i32, _i32, _vp, _vp, _vp], _int),
     "narde_advance_counter": ([_vp, _vp], _int),
@@ -154,6 +155,20 @@ def enumerate_actions(lo, hi, dice, actions, counts, overflow=None):
                                 _ptr(actions, torch.int64, "actions"), _ptr(counts, torch.int32, "counts"),
                                 _ptr(overflow, torch.uint8, "overflow"), _stream())
     _check(rc, "narde_enumerate")
+
+
+def enumerate_actions_fast(lo, hi, dice, actions, counts, overflow=None, workspace=None):
+    import torch
+
+    cap = actions.shape[1] if actions is not None else 0
+    if workspace is not None and workspace.numel() < lo.shape[0] + 1:
+        raise NardeCudaError("workspace must hold n + 1 int32")
+    rc = load().narde_enumerate_fast(_ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"),
+                                     _ptr(dice, torch.uint8, "dice"), lo.shape[0], cap,
+                                     _ptr(actions, torch.int64, "actions"), _ptr(counts, torch.int32, "counts"),
+                                     _ptr(overflow, torch.uint8, "overflow"), _ptr(workspace, torch.int32, "workspace"),
+                                     _stream())
+    _check(rc, "narde_enumerate_fast")
 
 
 def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actions=None, counts=None,

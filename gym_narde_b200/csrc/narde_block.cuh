@@ -684,7 +684,7 @@ struct BlockStep {
       if (A.dice_out) A.dice_out[2 * i] = A.dice_out[2 * i + 1] = 0;
       if (A.chosen) A.chosen[i] = ACT_EMPTY;
       if (A.reward) A.reward[i] = 0.0f;
-      if (A.done) A.done[i] = 1;
+      if (A.done) A.done[i] = (A.flags & F_ENUMERATE_ONLY) ? 0 : 1;
       if (A.truncated) A.truncated[i] = 0;
       return;
     }

@@ -11,6 +11,7 @@ enum : int {
   F_AUTORESET = 2,
   F_HALF_MOVES_ONLY = 4,
   F_ACTION_FRACTION = 32,
+  F_ENUMERATE_ONLY = 64,
   DONE_TERMINATED = 1,
   DONE_TRUNCATED = 2,
 };
@@ -192,6 +193,12 @@ NHD void complete_env(State& s, int64_t i, const StepFullArgs& A, int player, ui
   L.count = (int)count;
   L.overflow = (slice && (int)count > A.cap) ? 1 : 0;
   L.finished = L.white_win = L.black_win = L.mars = L.ep_len = 0;
+  if (A.flags & F_ENUMERATE_ONLY) {  // get_valid_actions: the list and its length only, the state is not touched
+    if (A.counts) A.counts[i] = (int32_t)count;
+    if (A.chosen) A.chosen[i] = count ? act : ACT_EMPTY;
+    if (A.done) A.done[i] = (uint8_t)L.overflow;  // the "done" output carries the overflow flag in this mode
+    return;
+  }
   if (count) apply_action(s, player, act);
   float rew;
   int dn;

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   __syncthreads();
   PHASE_MARK(8);
   // deferred envs belong to k_step_deferred, which may already be running: never store their state here
-  if (valid && !sh.defer[tid]) st_state(lo, hi, i, sh.st[tid]);
+  if (valid && !sh.defer[tid] && !(A.flags & F_ENUMERATE_ONLY)) st_state(lo, hi, i, sh.st[tid]);
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
     int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
       State st = sh.st;
       complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
       sh.st = st;
-      st_state(lo, hi, i, st);
+      if (!(A.flags & F_ENUMERATE_ONLY)) st_state(lo, hi, i, st);
       if (stats) {
         int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
         for (int k = 0; k < 6; k++)
@@ -560,6 +560,20 @@ int narde_enumerate(const void* lo, const void* hi, const uint8_t* dice, int64_t
 int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
                     const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
                     uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
+                    int32_t flags, int32_t max_episode_steps, int32_t* workspace, const uint64_t* step_dev, void* stream);
+
+int narde_enumerate_fast(const void* lo, const void* hi, const uint8_t* dice, int64_t n, int32_t cap, uint64_t* actions,
+                         int32_t* counts, uint8_t* overflow, int32_t* workspace, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || cap < 0 || !lo || !hi || !dice || !counts || (cap > 0 && !actions)) return -1;
+  return narde_step_full(const_cast<void*>(lo), const_cast<void*>(hi), n, 0, 0, 0, dice, nullptr, cap, actions, counts, nullptr,
+                         nullptr, nullptr, nullptr, overflow, nullptr, nullptr, NARDE_ENUMERATE_ONLY, 0, workspace, nullptr,
+                         stream);
+}
+
+int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
+                    const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
+                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
                     int32_t flags, int32_t max_episode_steps, int32_t* workspace, const uint64_t* step_dev, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || cap < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
@@ -585,6 +599,7 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.defer_list = nullptr;
   A.step_dev = step_dev;
   if (flags & NARDE_PER_THREAD_KERNEL) {
+    if (flags & NARDE_ENUMERATE_ONLY) return -1;
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
     return launch_status();
   }

@@ -63,6 +63,7 @@ class VecNardeEnv:
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._chunks[1:]]
         # deferred-turn lists (see narde_b200.h: (n + 1) int32 per call)
         self._workspaces = [torch.zeros((e - b) + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
+        self._enum_ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)   # get_valid_actions' deferred-turn list
         # device-resident copy of step_count: kernel arguments stay frozen, so a step is one graph replay
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.action_in = torch.zeros(n, dtype=torch.int32, device=dev)   # persistent policy input (graph-replayable)
@@ -111,7 +112,7 @@ class VecNardeEnv:
         Returns (actions [N,max_actions] int64 bit patterns, counts [N], overflow [N])."""
         if dice is None:
             dice = self.roll()
-        _cabi.enumerate_actions(self.lo, self.hi, dice, self.actions, self.counts, self.overflow)
+        _cabi.enumerate_actions_fast(self.lo, self.hi, dice, self.actions, self.counts, self.overflow, self._enum_ws)
         return self.actions, self.counts, self.overflow
 
     def step(self, actions=None, dice=None, fraction=False):

@@ -44,6 +44,8 @@ extern "C" {
 #define NARDE_AUTORESET 2        /* reset a finished environment in the same step (obs = first obs of the new game) */
 #define NARDE_PER_THREAD_KERNEL 8 /* narde_step_full: use the thread-per-env kernel (A/B testing; same results) */
 #define NARDE_ACTION_FRACTION 32  /* narde_step_full: action_idx[i] is a u32 fraction f; plays action floor(f * count / 2^32) */
+#define NARDE_ENUMERATE_ONLY 64   /* narde_step_full: write actions / counts (/ chosen) only, leave every state untouched;
+                                    done[i] then receives the overflow flag (count > cap) */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 
 /* done[i] = 1 when the episode terminated (a player bore off 15 checkers); truncated[i] = 1 when
@@ -97,6 +99,13 @@ int narde_step_ref(void *lo, void *hi, const uint8_t *dice, const int32_t *codes
  * first cap are stored).  overflow may be NULL. */
 int narde_enumerate(const void *lo, const void *hi, const uint8_t *dice, int64_t n, int32_t cap,
                     uint64_t *actions, int32_t *counts, uint8_t *overflow, void *stream);
+
+/* Same results as narde_enumerate through the CTA-cooperative kernels of the fused step (work items dealt
+ * evenly over a 128-environment CTA, order-dependent doubles turns handed to the exact kernel when a
+ * workspace of (n + 1) int32 is given): the fast path VecNardeEnv.get_valid_actions uses. */
+int narde_enumerate_fast(const void *lo, const void *hi, const uint8_t *dice, int64_t n, int32_t cap,
+                         uint64_t *actions, int32_t *counts, uint8_t *overflow, int32_t *workspace,
+                         void *stream);
 
 /* One fused full-rules env step for n environments:
  *   dice (dice_in [n,2] u8, or Philox(seed, env_base+i, step) when NULL) -> legal-turn

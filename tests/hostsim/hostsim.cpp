@@ -121,6 +121,17 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
   return 0;
 }
 
+int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice_in,
+                    const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
+                    uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
+                    int32_t flags, int32_t max_episode_steps, int32_t* workspace, void*);
+// narde_enumerate_fast: the fused-step phases in enumerate-only mode (flag 64)
+int hs_enumerate_fast(const void* lo, const void* hi, const uint8_t* dice, int64_t n, int32_t cap, uint64_t* actions,
+                      int32_t* counts, uint8_t* overflow, int32_t* workspace, void*) {
+  return hs_step_full_v2(const_cast<void*>(lo), const_cast<void*>(hi), n, 0, 0, 0, dice, nullptr, cap, actions, counts, nullptr,
+                         nullptr, nullptr, nullptr, overflow, nullptr, nullptr, 64, 0, workspace, nullptr);
+}
+
 }  // extern "C"
 
 // CTA-cooperative step (narde_block.cuh) emulated phase by phase: every phase runs for all tids

@@ -64,14 +64,23 @@ class HostSim:
                              _p(obs), _p(rew), _p(done), None, None)
         return obs, rew, done
 
+    enumerate_fast = False  # True: narde_enumerate_fast (fused-step phases, enumerate-only mode)
+
     def enumerate(self, lo, hi, dice, cap):
         n = lo.shape[0]
         dice = np.ascontiguousarray(dice, np.uint8)
         actions = np.full((n, cap), 0xFFFFFFFFFFFFFFFF, np.uint64)
         counts = np.zeros(n, np.int32)
         overflow = np.zeros(n, np.uint8)
-        self.lib.hs_enumerate(_p(lo), _p(hi), _p(dice), C.c_int64(n), C.c_int32(cap), _p(actions), _p(counts),
-                              _p(overflow), None)
+        if self.enumerate_fast:
+            lo0, hi0 = lo.copy(), hi.copy()
+            ws = np.zeros(n + 1, np.int32)
+            self.lib.hs_enumerate_fast(_p(lo), _p(hi), _p(dice), C.c_int64(n), C.c_int32(cap), _p(actions), _p(counts),
+                                       _p(overflow), _p(ws), None)
+            assert (lo == lo0).all() and (hi == hi0).all()   # states untouched
+        else:
+            self.lib.hs_enumerate(_p(lo), _p(hi), _p(dice), C.c_int64(n), C.c_int32(cap), _p(actions), _p(counts),
+                                  _p(overflow), None)
         return actions, counts, overflow
 
     def obs198(self, lo, hi):
@@ -185,6 +194,8 @@ class CudaBackend:
         self._sync_back(lo, hi, tlo, thi)
         return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
 
+    enumerate_fast = False  # True: narde_enumerate_fast (fused-step kernels, enumerate-only mode)
+
     def enumerate(self, lo, hi, dice, cap):
         t = self.torch
         n = lo.shape[0]
@@ -192,6 +203,11 @@ class CudaBackend:
         actions = t.full((n, cap), -1, dtype=t.int64, device=self.dev)
         counts = t.zeros(n, dtype=t.int32, device=self.dev)
         overflow = t.zeros(n, dtype=t.uint8, device=self.dev)
+        if self.enumerate_fast:
+            ws = t.zeros(n + 1, dtype=t.int32, device=self.dev)
+            self.cabi.enumerate_actions_fast(tlo, thi, self._up(np.asarray(dice, np.uint8)), actions, counts, overflow, ws)
+            assert t.equal(tlo.cpu(), t.from_numpy(lo)) and t.equal(thi.cpu(), t.from_numpy(hi))   # states untouched
+            return actions.cpu().numpy().view(np.uint64), counts.cpu().numpy(), overflow.cpu().numpy()
         self.cabi.enumerate_actions(tlo, thi, self._up(np.asarray(dice, np.uint8)), actions, counts, overflow)
         return actions.cpu().numpy().view(np.uint64), counts.cpu().numpy(), overflow.cpu().numpy()
 

@@ -54,6 +54,21 @@ def test_enumerate_overflow_reports_true_count(hostsim):
     P.check_enumerate_vs_oracle(hostsim, lo, hi, P.random_dice(500, 19, 0.7), cap=8)
 
 
+def test_enumerate_fast_path(hostsim):
+    """narde_enumerate_fast (fused-step phases in enumerate-only mode, exact phases for deferred turns)
+    against the oracle on the same corpora; the states must come back untouched."""
+    hostsim.enumerate_fast = True
+    try:
+        lo, hi = P.pack_corpus(P.selfplay_corpus(25, 5))
+        assert P.check_enumerate_vs_oracle(hostsim, lo, hi, P.random_dice(lo.shape[0], 6, 0.3)) > 0
+        b, off, ft = P.synthetic_boards(3000, 7)
+        lo, hi, _, _ = P.pack_mover_boards(b, off, ft, 8)
+        assert P.check_enumerate_vs_oracle(hostsim, lo, hi, P.random_dice(3000, 9, 0.5)) > 0
+        P.check_enumerate_vs_oracle(hostsim, lo[:500].copy(), hi[:500].copy(), P.random_dice(500, 19, 0.7), cap=8)
+    finally:
+        hostsim.enumerate_fast = False
+
+
 def test_step_ref_lockstep(hostsim):
     assert P.check_step_ref_lockstep(hostsim, 64, 500, 42) > 0
 

@@ -55,6 +55,20 @@ def test_gpu_enumerate_overflow(cuda_backend):
     P.check_enumerate_vs_oracle(cuda_backend, lo, hi, P.random_dice(1000, 112, 0.7), cap=8)
 
 
+def test_gpu_enumerate_fast_path(cuda_backend):
+    """narde_enumerate_fast (what VecNardeEnv.get_valid_actions calls) against the oracle; states untouched."""
+    cuda_backend.enumerate_fast = True
+    try:
+        lo, hi = P.pack_corpus(P.selfplay_corpus(60, 105))
+        assert P.check_enumerate_vs_oracle(cuda_backend, lo, hi, P.random_dice(lo.shape[0], 106, 0.3)) > 0
+        b, off, ft = P.synthetic_boards(12000, 107)
+        lo, hi, _, _ = P.pack_mover_boards(b, off, ft, 108)
+        assert P.check_enumerate_vs_oracle(cuda_backend, lo, hi, P.random_dice(12000, 109, 0.5)) > 0
+        P.check_enumerate_vs_oracle(cuda_backend, lo[:1000].copy(), hi[:1000].copy(), P.random_dice(1000, 112, 0.7), cap=8)
+    finally:
+        cuda_backend.enumerate_fast = False
+
+
 def test_gpu_step_ref_lockstep(cuda_backend):
     assert P.check_step_ref_lockstep(cuda_backend, 200, 500, 42) > 0
 
