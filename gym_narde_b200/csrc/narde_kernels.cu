@@ -20,8 +20,8 @@ using namespace narde;
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kDeferredThreads = 512;  // exact-doubles kernel: one 512-thread CTA per env at a time, ~20 KB shared memory
-constexpr int kDeferredGrid = 148 * 2;
+constexpr int kDeferredThreads = 256;  // exact-doubles kernel: one 256-thread CTA per env at a time, ~18 KB shared memory
+constexpr int kDeferredGrid = 148 * 4;  // 4 CTAs per SM (measured: 512x2 and 128x8 are slower on the self-play mix)
 
 __device__ __forceinline__ State ld_state(const uint4* __restrict__ lo, const uint4* __restrict__ hi, int64_t i) {
   uint4 a = lo[i], b = hi[i];

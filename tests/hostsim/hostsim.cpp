@@ -242,7 +242,7 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     step_full_v2_host<128, true>(lo, hi, n, A, obs198, stats);
   else
     step_full_v2_host<128, false>(lo, hi, n, A, obs198, stats);
-  if (workspace) step_deferred_host<512>(lo, hi, A, obs198, stats);
+  if (workspace) step_deferred_host<256>(lo, hi, A, obs198, stats);
   return 0;
 }
 
