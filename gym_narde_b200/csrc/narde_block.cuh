@@ -264,6 +264,45 @@ struct BlockStep {
       sh.base[l][tid] = r;
     }
   }
+  // The same exclusive scan in ONE phase.  On the device warp l scans lane l with shuffles (BLK = 128: four
+  // warps, four lanes); the host harness runs the plain serial scan.  lanes: bit mask of the lanes needed.
+  static NHD void ph_scan_serial(int tid, Sh& sh, uint32_t lanes) {
+#if defined(__CUDA_ARCH__)
+    static_assert(BLK == 128, "one warp per scan lane");
+    const int l = tid >> 5, lane = tid & 31;
+    if (!((lanes >> l) & 1u)) return;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      v[k] = sh.part[l][lane * PER + k];
+      sum += v[k];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t r = incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      sh.base[l][lane * PER + k] = r;
+      r += v[k];
+    }
+    if (lane == 31) sh.ws[l][32] = incl;
+#else
+    if (tid & 31) return;
+    const int l = tid >> 5;
+    if (l >= 4 || !((lanes >> l) & 1u)) return;
+    uint32_t r = 0;
+    for (int k = 0; k < BLK; k++) {
+      uint32_t t = sh.part[l][k];
+      sh.base[l][k] = r;
+      r += t;
+    }
+    sh.ws[l][32] = r;
+#endif
+  }
   // after the first scan: bases of the ND row items and of the doubles level-1 items
   static NHD void ph_item_bases(int tid, Sh& sh) {
     sh.ibase[tid] = sh.base[0][tid];

@@ -213,22 +213,16 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_load(tid, sh, valid, s, i, A);
   __syncthreads();
   PHASE_MARK(1);
-  BS::ph_scan1(tid, sh);
+  BS::ph_scan_serial(tid, sh, 0x3u);
   __syncthreads();
-  BS::ph_scan2(tid, sh);
-  __syncthreads();
-  BS::ph_scan3(tid, sh);
   BS::ph_item_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(2);
   BS::ph_rows(tid, sh);
   __syncthreads();
   PHASE_MARK(3);
-  BS::ph_scan1(tid, sh);
+  BS::ph_scan_serial(tid, sh, 0x2u);
   __syncthreads();
-  BS::ph_scan2(tid, sh);
-  __syncthreads();
-  BS::ph_scan3(tid, sh);
   BS::ph_l2_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(4);
@@ -244,11 +238,8 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   // Programmatic dependent launch: k_step_deferred may start as soon as every CTA is past this point,
   // i.e. while the action lists and Box(198) rows of the other envs are still being written.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  BS::ph_scan1(tid, sh);
+  BS::ph_scan_serial(tid, sh, 0xFu);
   __syncthreads();
-  BS::ph_scan2(tid, sh);
-  __syncthreads();
-  BS::ph_scan3(tid, sh);
   BS::ph_env_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(6);

@@ -149,18 +149,15 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
     }
     // NOTE: phases fused between two barriers on the GPU are emulated in DESCENDING tid order as
     // well as ascending elsewhere, so that a read-after-write hazard inside a fused pair shows up
-    for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
-    for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_item_bases(t, sh); }
+    for (int t = 0; t < BLK; t++) BS::ph_scan_serial(t, sh, 0x3u);
+    for (int t = BLK - 1; t >= 0; t--) BS::ph_item_bases(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
-    for (int t = 0; t < BLK; t++) { BS::ph_scan3(t, sh); BS::ph_l2_bases(t, sh); }
+    for (int t = 0; t < BLK; t++) BS::ph_scan_serial(t, sh, 0x2u);
+    for (int t = 0; t < BLK; t++) BS::ph_l2_bases(t, sh);
     for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh);
     for (int t = 0; t < BLK; t++) { BS::ph_env_totals(t, sh); if (DEFER) BS::ph_defer_push(t, sh, row0 + t < n, row0 + t, A); }
-    for (int t = 0; t < BLK; t++) BS::ph_scan1(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_scan2(t, sh);
-    for (int t = BLK - 1; t >= 0; t--) { BS::ph_scan3(t, sh); BS::ph_env_bases(t, sh); }
+    for (int t = 0; t < BLK; t++) BS::ph_scan_serial(t, sh, 0xFu);
+    for (int t = BLK - 1; t >= 0; t--) BS::ph_env_bases(t, sh);
     for (int t = 0; t < BLK; t++) BS::ph_emit(t, sh, row0, A);
     for (int t = 0; t < BLK; t++) {
       bool valid = row0 + t < n;
