@@ -317,10 +317,10 @@ def run_cuda_arm(args):
         kernel_ms = total_ms / K                             # rank-0 kernel: one launch per step
         achieved = E * bytes_per_unit / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "step_full_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r01b_step_full_v2.json")   # ncu --set full of the same kernel/workload
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp))["launches"][0].get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
@@ -332,8 +332,8 @@ def run_cuda_arm(args):
                        "mean_legal_actions": A, "max_legal_actions": int(st_all[:, 6].max().item()),
                        "l2": "flushed between timed steps (256 MiB fill, untimed)" if flush is not None else "not flushed",
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
-            "roofline": {"bound": "hbm", "kernel": "k_step_full_v2<128> (+ k_step_deferred<512> for order-dependent doubles turns), %d chunk launches per step, timed as one step" % len(env._chunks), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_step_full_v2<128,true> + its programmatic dependent k_step_deferred<256> (order-dependent doubles turns, overlaps the tail), timed together as one step", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01b_step_full_v2.json (per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 5 * E,
                     "ms_per_step": total_e2e_max / K,
@@ -353,7 +353,8 @@ def run_cuda_arm(args):
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             v, n, a, wall = cpu_selfplay(cores, 64, 150)
-            v, n, a, wall = cpu_selfplay(cores, 64, max(150, int(150 * 12.0 / max(wall, 1e-3))))
+            # size the reported sample to ~12 s of CPU work from the measured rate (pool start-up excluded)
+            v, n, a, wall = cpu_selfplay(cores, 64, max(150, int(12.0 * v / (cores * 64))))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d procs x 64 envs, %d env turns total in %.1f s (oracle/narde_oracle.c o_selfplay)" % (cores, n, wall)}
         print(json.dumps(line))

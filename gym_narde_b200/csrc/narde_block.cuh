@@ -65,10 +65,11 @@ NHD_NOINLINE int walk_short_double(const Pos& P, int d, bool first_turn, int H, 
   return enum_double(P, d, first_turn, !block_rule_irrelevant(P, d, d), sink, &depth);
 }
 
-constexpr int kL1Cap = 1024;  // level-1 doubles items a CTA can hold (128 envs x <= 15 sources, never reached)
+constexpr int kL1PerEnv = 8;  // level-1 doubles items a CTA can hold per env (all-doubles CTAs with > 8 sources per env overflow to the sequential walk; never observed)
 
 template <int BLK>
 struct BlockShared {
+  static constexpr int kL1Cap = kL1PerEnv * BLK;
   State st[BLK];
   // per-env position in the mover frame
   uint32_t own[BLK], opp[BLK], ones[BLK];
@@ -268,32 +269,32 @@ struct BlockStep {
   // warps, four lanes); the host harness runs the plain serial scan.  lanes: bit mask of the lanes needed.
   static NHD void ph_scan_serial(int tid, Sh& sh, uint32_t lanes) {
 #if defined(__CUDA_ARCH__)
-    static_assert(BLK == 128, "one warp per scan lane");
-    const int l = tid >> 5, lane = tid & 31;
-    if (!((lanes >> l) & 1u)) return;
-    uint32_t v[PER], sum = 0;
+    const int lane = tid & 31;
+    for (int l = tid >> 5; l < 4; l += BLK / 32) {  // a warp per scan lane (BLK = 128), fewer warps take several
+      if (!((lanes >> l) & 1u)) continue;
+      uint32_t v[PER], sum = 0;
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-      v[k] = sh.part[l][lane * PER + k];
-      sum += v[k];
-    }
-    uint32_t incl = sum;
+      for (int k = 0; k < PER; k++) {
+        v[k] = sh.part[l][lane * PER + k];
+        sum += v[k];
+      }
+      uint32_t incl = sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    uint32_t r = incl - sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      uint32_t r = incl - sum;
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-      sh.base[l][lane * PER + k] = r;
-      r += v[k];
+      for (int k = 0; k < PER; k++) {
+        sh.base[l][lane * PER + k] = r;
+        r += v[k];
+      }
+      if (lane == 31) sh.ws[l][32] = incl;
     }
-    if (lane == 31) sh.ws[l][32] = incl;
 #else
-    if (tid & 31) return;
-    const int l = tid >> 5;
-    if (l >= 4 || !((lanes >> l) & 1u)) return;
+    if (tid >= 4 || !((lanes >> tid) & 1u)) return;
+    const int l = tid;
     uint32_t r = 0;
     for (int k = 0; k < BLK; k++) {
       uint32_t t = sh.part[l][k];
@@ -311,7 +312,7 @@ struct BlockStep {
       sh.ibase[BLK] = sh.ws[0][32];
       sh.dbase[BLK] = sh.ws[1][32];
       uint32_t n1 = sh.ws[1][32];
-      sh.n_l1 = n1 <= (uint32_t)kL1Cap ? n1 : 0u;  // overflow: doubles envs fall back to the sequential walk
+      sh.n_l1 = n1 <= (uint32_t)Sh::kL1Cap ? n1 : 0u;  // overflow: doubles envs fall back to the sequential walk
     }
   }
 

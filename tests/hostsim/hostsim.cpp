@@ -134,6 +134,9 @@ int hs_enumerate_fast(const void* lo, const void* hi, const uint8_t* dice, int64
 
 }  // extern "C"
 
+static int64_t g_small_batch = 16384;
+extern "C" void hs_set_small_batch(int64_t v) { g_small_batch = v; }
+
 // CTA-cooperative step (narde_block.cuh) emulated phase by phase: every phase runs for all tids
 // of a block before the next one starts, which is what __syncthreads() guarantees on the GPU.
 template <int BLK, bool DEFER>
@@ -235,10 +238,18 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     A.defer_count = workspace;
     A.defer_list = workspace + 1;
   }
-  if (workspace)
+  // same dispatch as narde_step_full: one-warp CTAs of 32 envs for small batches (g_small_batch can be
+  // lowered by the tests so that both tile sizes are exercised on small inputs)
+  if (n <= g_small_batch) {
+    if (workspace)
+      step_full_v2_host<32, true>(lo, hi, n, A, obs198, stats);
+    else
+      step_full_v2_host<32, false>(lo, hi, n, A, obs198, stats);
+  } else if (workspace) {
     step_full_v2_host<128, true>(lo, hi, n, A, obs198, stats);
-  else
+  } else {
     step_full_v2_host<128, false>(lo, hi, n, A, obs198, stats);
+  }
   if (workspace) step_deferred_host<256>(lo, hi, A, obs198, stats);
   return 0;
 }

@@ -119,6 +119,18 @@ def _v1_v2_equal(hostsim, lo, hi, **kw):
     return o1
 
 
+def test_block_kernel_tile_128_equals_per_thread_body(hostsim):
+    """The library uses 32-env one-warp CTAs for batches <= 16384 and 128-env CTAs above; force the 128-env
+    tile on small inputs so that both are checked here (the other tests run the 32-env tile)."""
+    import ctypes as C
+    hostsim.lib.hs_set_small_batch(C.c_int64(0))
+    try:
+        test_block_kernel_equals_per_thread_body(hostsim)
+        P.check_step_full_lockstep(hostsim, 200, 120, 0xBEEF)
+    finally:
+        hostsim.lib.hs_set_small_batch(C.c_int64(16384))
+
+
 def test_block_kernel_equals_per_thread_body(hostsim):
     """The CTA-cooperative phases (narde_block.cuh) and the per-thread body (narde_env.cuh) must agree
     bit for bit: synthetic block-rule-heavy boards, ragged batch sizes, given dice / given indices."""
