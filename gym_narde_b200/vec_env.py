@@ -131,16 +131,24 @@ class VecNardeEnv:
         if self.rules == "full":
             flags = (_cabi.REWARD_MOVER12 if self.reward_mode == "mover12" else 0) | (
                 _cabi.AUTORESET if self.autoreset else 0) | (_cabi.ACTION_FRACTION if fraction and actions is not None else 0)
-            # graphs are replayed only for frozen argument sets: the random-policy step and the step
-            # driven by the persistent input buffer `self.action_in`; anything else is launched directly
-            graphable = self.use_graph and dice is None and (actions is None or actions is self.action_in)
-            if graphable:
-                key = "random" if actions is None else ("action_in", bool(fraction))
-                g = self._graphs.get(key)
-                if g is None:
-                    g = self._capture(actions, dice, flags)
-                    self._graphs[key] = g
-                g.replay()
+            # A captured graph freezes the kernel arguments, so graphs are cached per action-input buffer
+            # (identified by its device pointer; the tensor is kept alive by the cache) and replayed when the
+            # same persistent buffer is passed again.  Up to 8 buffers are cached; anything else (fresh
+            # tensors, explicit dice) is launched directly.
+            key = None
+            if self.use_graph and dice is None:
+                if actions is None:
+                    key = "random"
+                elif actions.is_contiguous() and actions.dtype == t.int32 and actions.numel() == self.num_envs:
+                    key = (actions.data_ptr(), bool(fraction))
+                    if key not in self._graphs and len(self._graphs) >= 8:
+                        key = None
+            if key is not None:
+                ent = self._graphs.get(key)
+                if ent is None:
+                    ent = (self._capture(actions, dice, flags), actions)
+                    self._graphs[key] = ent
+                ent[0].replay()
             else:
                 self._step_dev.fill_(self.step_count)
                 self._launch_full(actions, dice, flags)
