@@ -464,6 +464,51 @@ __global__ void __launch_bounds__(kThreads) k_segment_argmax(const float* score,
   if (best_out) best_out[i] = c ? sign * best : 0.0f;
 }
 
+// Trainer-compatible action codes (train_deepq_pytorch.py:432-437,495-507,752-761): for every stored legal
+// turn action the reference's (move1_code, move2_code) pair, code = from*24 + to with to = 0 for a bear-off
+// and move2_code = 0 when the turn has one half-move.  Only the first two half-moves are representable in
+// the reference's pair space; codes[.., 2] = number of half-moves of the turn (3 or 4 for doubles).
+__global__ void __launch_bounds__(kThreads) k_action_codes(const uint64_t* actions, const int32_t* counts, int64_t n, int cap,
+                                                          int32_t* codes) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n * (int64_t)cap) return;
+  const int64_t i = g / cap;
+  const int k = (int)(g - i * cap);
+  int32_t c1 = 0, c2 = 0, nh = 0;
+  if (k < counts[i]) {
+    const uint64_t a = actions[g];
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      const uint32_t hm = (uint32_t)(a >> (16 * h)) & 0xFFFFu;
+      if (hm == 0xFFFFu) break;
+      const int from = (int)(hm & 0xFF), to = (int)(hm >> 8);
+      const int code = from * 24 + (to == 255 ? 0 : to);
+      if (h == 0) c1 = code;
+      if (h == 1) c2 = code;
+      nh++;
+    }
+  }
+  codes[3 * g] = c1;
+  codes[3 * g + 1] = c2;
+  codes[3 * g + 2] = nh;
+}
+
+// Trajectory record of one env turn, 48 bytes:
+//   [0,16) lo lane | [16,32) hi lane (state AFTER the turn = state before the next one) | u64 action played
+//   | f32 reward | u8 die 1, u8 die 2, u8 done (1 terminated, 2 truncated), u8 reserved
+__global__ void __launch_bounds__(kThreads) k_trajectory_append(const uint4* lo, const uint4* hi, const uint8_t* dice,
+                                                               const uint64_t* chosen, const float* reward, const uint8_t* done,
+                                                               const uint8_t* truncated, int64_t n, uint4* records) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t a = chosen ? chosen[i] : ~0ull;
+  const uint32_t d = dice ? (uint32_t)reinterpret_cast<const uint16_t*>(dice)[i] : 0u;
+  const uint32_t dn = (done && done[i] ? 1u : 0u) | (truncated && truncated[i] ? 2u : 0u);
+  records[3 * i] = lo[i];
+  records[3 * i + 1] = hi[i];
+  records[3 * i + 2] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), reward ? __float_as_uint(reward[i]) : 0u, d | (dn << 16));
+}
+
 __global__ void __launch_bounds__(kThreads) k_roll_dice(int64_t n, int64_t env_base, uint64_t seed, uint64_t step, uint8_t* dice) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -679,6 +724,23 @@ int narde_segment_argmax(const float* score, const int64_t* offsets, const int32
   if (n < 0 || cap <= 0 || !score || !offsets || !counts || !hi || !idx_out || !aligned16(hi)) return -1;
   k_segment_argmax<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(score, offsets, counts, (const uint4*)hi, n, cap, mode,
                                                                        idx_out, best_out);
+  return launch_status();
+}
+
+int narde_action_codes(const uint64_t* actions, const int32_t* counts, int64_t n, int32_t cap, int32_t* codes, void* stream) {
+  if (n == 0 || cap == 0) return 0;
+  if (n < 0 || cap < 0 || !actions || !counts || !codes) return -1;
+  k_action_codes<<<grid_for(n * (int64_t)cap), kThreads, 0, (cudaStream_t)stream>>>(actions, counts, n, cap, codes);
+  return launch_status();
+}
+
+int narde_trajectory_append(const void* lo, const void* hi, const uint8_t* dice, const uint64_t* chosen, const float* reward,
+                            const uint8_t* done, const uint8_t* truncated, int64_t n, void* records, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !lo || !hi || !records || !aligned16(lo) || !aligned16(hi) || !aligned16(records)) return -1;
+  if (dice && (((uintptr_t)dice) & 1u) != 0) return -1;
+  k_trajectory_append<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, dice, chosen, reward,
+                                                                          done, truncated, n, (uint4*)records);
   return launch_status();
 }
 

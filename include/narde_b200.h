@@ -173,6 +173,23 @@ int narde_segment_argmax(const float *score, const int64_t *offsets, const int32
                          int64_t n, int32_t cap, int32_t mode, int32_t *idx_out, float *best_out,
                          void *stream);
 
+/* Trainer-compatible action codes for every stored legal turn action: the reference's (move1_code,
+ * move2_code) pairs (train_deepq_pytorch.py:432-437,495-507; action_to_idx :752-761): code = from*24 + to,
+ * to = 0 for a bear-off, move2_code = 0 when the turn has a single half-move.  codes: [n,cap,3] i32 =
+ * (move1_code, move2_code, number of half-moves of the turn: doubles turns may have 3 or 4, of which the
+ * reference's pair space can only name the first two).  Slots k >= counts[i] are written as zeros. */
+int narde_action_codes(const uint64_t *actions, const int32_t *counts, int64_t n, int32_t cap,
+                       int32_t *codes, void *stream);
+
+/* Append one 48-byte trajectory record per environment (state after the turn, action played, reward,
+ * dice, done bits) to records [n] (16-byte aligned): the device-resident replay / trajectory ring
+ * (the reference only checkpoints model weights, train_deepq_pytorch.py:1136-1145).  Layout:
+ * lo lane | hi lane | u64 action | f32 reward | u8 die1 | u8 die2 | u8 done (1 terminated, 2 truncated) | u8 0.
+ * dice, chosen, reward, done, truncated may be NULL. */
+int narde_trajectory_append(const void *lo, const void *hi, const uint8_t *dice, const uint64_t *chosen,
+                            const float *reward, const uint8_t *done, const uint8_t *truncated, int64_t n,
+                            void *records, void *stream);
+
 /* *counter += 1 on the device (one tiny launch); see step_dev above. */
 int narde_advance_counter(uint64_t *counter, void *stream);
 

@@ -28,6 +28,30 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert lib.narde_reset(None, None, 4, 0, 0, 0, None) == -1
     assert lib.narde_enumerate(None, None, None, 4, 8, None, None, None, None) == -1
     assert lib.narde_reset(None, None, -1, 0, 0, 0, None) == -1
+    # empty batches are a no-op for every entry point (n == 0 / rows == 0 returns before any CUDA call)
+    assert lib.narde_reset(None, None, 0, 0, 0, 0, None) == 0
+    assert lib.narde_enumerate(None, None, None, 0, 8, None, None, None, None) == 0
+    assert lib.narde_enumerate_fast(None, None, None, 0, 8, None, None, None, None, None) == 0
+    assert lib.narde_step_full(None, None, 0, 0, 0, 0, None, None, 8, None, None, None, None, None, None, None, None,
+                               None, 0, 0, None, None, None) == 0
+    assert lib.narde_mlp_forward(None, 0, None, None, None, None) == 0
+    assert lib.narde_afterstates(None, None, None, None, None, 0, 8, None, None, None, None) == 0
+    # null / misaligned buffers and negative sizes are rejected with -1, nothing is launched
+    assert lib.narde_step_full(None, None, 4, 0, 0, 0, None, None, 8, None, None, None, None, None, None, None, None,
+                               None, 0, 0, None, None, None) == -1
+    assert lib.narde_enumerate_fast(None, None, None, 4, 8, None, None, None, None, None) == -1
+    assert lib.narde_mlp_forward(None, 4, None, None, None, None) == -1
+    assert lib.narde_mlp_score(None, 4, None, None, None, None) == -1
+    assert lib.narde_mlp_forward_states(None, None, 4, None, None, None, None) == -1
+    assert lib.narde_mlp_score_states(None, None, 4, None, None, None, None, None) == -1
+    assert lib.narde_afterstates(None, None, None, None, None, 4, 8, None, None, None, None) == -1
+    assert lib.narde_segment_argmax(None, None, None, None, 4, 8, 0, None, None, None) == -1
+    assert lib.narde_mlp_forward(None, -3, None, None, None, None) == -1
+    import ctypes as C
+    buf = C.create_string_buffer(256)
+    base = C.addressof(buf)
+    mis = C.c_void_p(base + 8 if base % 16 == 0 else base)          # 8-byte aligned, not 16
+    assert lib.narde_reset(mis, mis, 2, 0, 0, 0, None) == -1
 
 
 def test_no_cpu_fallback():

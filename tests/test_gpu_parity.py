@@ -204,3 +204,15 @@ def test_gpu_block_kernel_equals_per_thread_kernel(cuda_backend):
     lo, hi = P.pack_corpus(P.selfplay_corpus(60, 41))
     for step in range(1, 6):
         _v1_v2_equal(cuda_backend, lo, hi, seed=77, step=step, cap=32, flags=2)
+
+
+def test_gpu_edge_sizes_and_ragged_batches(cuda_backend):
+    """Ragged batch sizes around both CTA tiles (32 / 128 envs) and the small-batch switch (16384):
+    the fused step must agree with the thread-per-env kernel bit for bit; cap = 0 (count only) and cap = 1."""
+    from test_core_hostsim import _v1_v2_equal
+    b, off, ft = P.synthetic_boards(16500, 77)
+    lo, hi, _, _ = P.pack_mover_boards(b, off, ft, 78)
+    for n in (1, 31, 32, 33, 127, 129, 16383, 16384, 16385):
+        _v1_v2_equal(cuda_backend, lo[:n].copy(), hi[:n].copy(), seed=n, step=5, cap=24, flags=2)
+    _v1_v2_equal(cuda_backend, lo[:700].copy(), hi[:700].copy(), seed=3, step=2, cap=0, flags=0, want_actions=False)
+    _v1_v2_equal(cuda_backend, lo[:700].copy(), hi[:700].copy(), seed=3, step=2, cap=1, flags=1)
