@@ -354,6 +354,25 @@ def run_cuda_arm(args):
     if not args.no_config3 and rank == 0:
         cfg3 = config3_enumeration_microbench(torch, dev, args, timed_loop, measured_peaks()[0])
 
+    # ---- policy-weight broadcast (config 4: NCCL broadcast of the packed DecomposedDQN(198) weights) ----
+    bcast_ms = None
+    if world > 1:
+        from gym_narde_b200 import dist as ndist
+        wp = torch.zeros(557056 // 2 + 16, dtype=torch.int16, device=dev)   # packed operand stages (~0.56 MB bf16)
+        bs = torch.zeros(1088, dtype=torch.float32, device=dev)
+        if rank == 0:
+            wp.fill_(7)
+            bs.fill_(0.5)
+        ndist.broadcast_policy([wp, bs], src=0)                               # warm-up / communicator setup
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ndist.broadcast_policy([wp, bs], src=0)
+        b.record()
+        torch.cuda.synchronize()
+        assert int(wp[0].item()) == 7 and float(bs[0].item()) == 0.5
+        bcast_ms = a.elapsed_time(b)
+
     # ---- reduce over ranks (MAX time), gather episode stats with NCCL ----
     tmax = torch.tensor([total_ms, total_e2e, ms_pipe], dtype=torch.float64, device=dev)
     st = env.stats.clone()
@@ -409,6 +428,8 @@ def run_cuda_arm(args):
                                   "ms_per_step": sum(ms_small) / len(ms_small)},
             "episode_stats": {k: int(v) for k, v in zip(_cabi.STAT_NAMES, st_all.sum(0).tolist())},
         }
+        if bcast_ms is not None:
+            line["policy_broadcast_ms"] = bcast_ms
         if cfg5 is not None:
             line["config5_afterstate_scoring"] = cfg5
         if cfg3 is not None:

@@ -1,6 +1,7 @@
 """Multi-GPU plumbing: environments are independent, so the path shards by global env id with no
 data-path collective.  torch.distributed (NCCL on GPUs, gloo in the CPU tests) is
-used only to all-gather the int64[8] episode statistics and to max-reduce timings."""
+used only to all-gather the int64[8] episode statistics, to max-reduce timings and to broadcast policy
+weights (the packed DecomposedDQN(198) operand stages, ~1.1 MB) from the learner's rank -- never inside the step."""
 from __future__ import annotations
 
 
@@ -34,6 +35,17 @@ def max_over_ranks(values, group=None):
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(values, op=dist.ReduceOp.MAX, group=group)
     return values
+
+
+def broadcast_policy(tensors, src=0, group=None):
+    """Broadcast the policy weights (e.g. AfterstateMLP.wpack and .bias) from rank `src` in place; returns the
+    same tensors.  NCCL over NVLink on GPUs (one ncclBroadcast per tensor), a no-op without a process group."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+    return tensors
 
 
 def merge_stats(all_stats):

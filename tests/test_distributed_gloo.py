@@ -36,6 +36,10 @@ def _worker(rank, world, port, total, steps, seed, out_dir):
         s = o["stats"]
         stats[[0, 1, 2, 3, 4, 5, 7]] += s[[0, 1, 2, 3, 4, 5, 7]]
         stats[6] = max(stats[6], s[6])
+    # policy-weight broadcast from rank 0 (NCCL on GPUs): every rank ends with rank 0's tensors
+    w = [torch.full((1000,), float(rank + 1)), torch.arange(16, dtype=torch.int16) * (rank + 1)]
+    D.broadcast_policy(w, src=0)
+    assert (w[0] == 1.0).all() and (w[1] == torch.arange(16, dtype=torch.int16)).all()
     allst = D.gather_stats(torch.from_numpy(stats))
     tmax = D.max_over_ranks(torch.tensor([float(rank + 1)], dtype=torch.float64))
     planes = [torch.zeros((D.shard_range(total, r, world)[1], 32), dtype=torch.uint8) for r in range(world)]
