@@ -42,9 +42,13 @@ def broadcast_policy(tensors, src=0, group=None):
     same tensors.  NCCL over NVLink on GPUs (one ncclBroadcast per tensor), a no-op without a process group."""
     import torch.distributed as dist
 
+    import torch
+
     if dist.is_available() and dist.is_initialized():
         for t in tensors:
-            dist.broadcast(t, src=src, group=group)
+            # bytes on the wire: the packed weights are int16 bit patterns of bf16, which neither NCCL nor gloo
+            # has a reduction type for (a broadcast needs none)
+            dist.broadcast(t.view(torch.uint8) if t.is_contiguous() else t, src=src, group=group)
     return tensors
 
 
