@@ -537,13 +537,13 @@ def config5_afterstate_scoring(torch, dev, args, timed_loop):
     for _ in range(60):                      # random self-play burn-in, then greedy turns
         env.step()
     for _ in range(5):
-        actor.step()
+        actor.step_graph()
     torch.cuda.synchronize()
     k = max(5, min(args.steps, 30))
     rows = []
 
     def greedy_step():
-        actor.step()
+        actor.step_graph()                   # one CUDA-graph replay per greedy turn
         rows.append(actor.rows_dev.clone())
 
     ms_actor = timed_loop(greedy_step, k)

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libnarde_b200.so")
 REWARD_MOVER12 = 1
 AUTORESET = 2
 ACTION_FRACTION = 32
+ENUMERATE_ONLY = 64
 HALF_MOVES_ONLY = 4
 MAX_HALF_MOVES = 96
 NUM_STATS = 8

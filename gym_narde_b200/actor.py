@@ -35,6 +35,8 @@ class AfterstateActor:
         self.value = t.zeros(n, dtype=t.float32, device=dev)
         self.dice = t.zeros((n, 2), dtype=t.uint8, device=dev)
         self.lib = _cabi.load()
+        self._graph = None
+        self._enum_ws = t.zeros(n + 1, dtype=t.int32, device=dev)
 
     def _stream(self):
         return C.c_void_p(self.env.torch.cuda.current_stream().cuda_stream)
@@ -74,3 +76,57 @@ class AfterstateActor:
         """One greedy lock-step turn for all envs; returns VecNardeEnv.step's tuple."""
         choice, dice = self.choose()
         return self.env.step(choice, dice=dice)
+
+    # -- the same turn as ONE CUDA-graph replay ---------------------------------------------------
+    def _enqueue_turn(self):
+        """All launches of a greedy turn with the step number read from the env's device counter, so that the
+        captured graph can be replayed: enumerate (Philox dice of the turn) -> afterstates -> score -> argmax ->
+        fused step with the chosen indices (which re-derives the same dice from the same counter)."""
+        env, t = self.env, self.env.torch
+        flags = (_cabi.REWARD_MOVER12 if env.reward_mode == "mover12" else 0) | (_cabi.AUTORESET if env.autoreset else 0)
+        _cabi.advance_counter(env._step_dev)
+        _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, actions=env.actions, counts=env.counts,
+                        dice_out=self.dice, done=env.overflow, flags=_cabi.ENUMERATE_ONLY, workspace=self._enum_ws,
+                        step_dev=env._step_dev)
+        self.afterstates(env.actions, env.counts)
+        self.mlp.score_states(self.as_lo, self.as_hi, out=self.scores, rows_dev=self.rows_dev)
+        rc = self.lib.narde_segment_argmax(C.c_void_p(self.scores.data_ptr()), C.c_void_p(self.offsets.data_ptr()),
+                                           C.c_void_p(env.counts.data_ptr()), C.c_void_p(env.hi.data_ptr()), env.num_envs,
+                                           self.cap, self.mode, C.c_void_p(self.choice.data_ptr()),
+                                           C.c_void_p(self.value.data_ptr()), self._stream())
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
+        _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, action_idx=self.choice,
+                        actions=env.actions if env.write_actions else None, counts=env.counts, dice_out=env.dice,
+                        chosen=env.chosen, obs198=env.obs, reward=env.reward, done=env.done, stats=env.stats,
+                        flags=flags, max_episode_steps=env.max_episode_steps, truncated=env.trunc,
+                        workspace=env._workspaces[0], step_dev=env._step_dev)
+
+    def step_graph(self):
+        """step() as one CUDA-graph replay (captured on first use; needs the env built with chunks=1)."""
+        env, t = self.env, self.env.torch
+        if len(env._chunks) != 1:
+            raise ValueError("step_graph needs an unchunked env")
+        env.step_count += 1
+        if self._graph is None:
+            self._enqueue_turn_warmup()
+            env._step_dev.fill_(env.step_count - 1)
+            t.cuda.synchronize(env.device)
+            g = t.cuda.CUDAGraph()
+            with t.cuda.graph(g):
+                self._enqueue_turn()
+            self._graph = g
+        self._graph.replay()
+        return env.obs, env.reward, env.terminated, env.truncated, env.info
+
+    def _enqueue_turn_warmup(self):
+        """First-use work that must not happen during capture (function attributes, lazy allocations): run the
+        read-only part of a turn once, outside the graph."""
+        env = self.env
+        saved = env._step_dev.clone()
+        _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, actions=env.actions, counts=env.counts,
+                        dice_out=self.dice, done=env.overflow, flags=_cabi.ENUMERATE_ONLY, workspace=self._enum_ws,
+                        step_dev=env._step_dev)
+        self.afterstates(env.actions, env.counts)
+        self.mlp.score_states(self.as_lo, self.as_hi, out=self.scores, rows_dev=self.rows_dev)
+        env._step_dev.copy_(saved)

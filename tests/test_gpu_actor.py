@@ -77,3 +77,26 @@ def test_actor_choice_is_segment_argmax_and_step_plays_it():
             chosen_act = env.actions[torch.arange(n, device="cuda"), choice.long()].clone()
             env.step(choice, dice=dice)
             assert torch.equal(env.chosen[live], chosen_act[live])
+
+
+def test_actor_graph_replay_equals_eager_turns():
+    """AfterstateActor.step_graph (one CUDA-graph replay per greedy turn, step number read from the device
+    counter) plays exactly the turns of the eager step()."""
+    import torch
+    from gym_narde_b200 import VecNardeEnv, AfterstateMLP, AfterstateActor
+    fn, head = _net()
+    mlp = AfterstateMLP.from_module(fn, head)
+    n, cap = 4096, 64
+    envs = [VecNardeEnv(n, seed=13, max_actions=cap) for _ in range(2)]
+    actors = [AfterstateActor(e, mlp) for e in envs]
+    for e in envs:
+        e.reset()
+        for _ in range(30):
+            e.step()
+    for t in range(50):
+        actors[0].step()
+        actors[1].step_graph()
+        assert torch.equal(envs[0].lo, envs[1].lo) and torch.equal(envs[0].hi, envs[1].hi), t
+        assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[0].reward, envs[1].reward)
+        assert torch.equal(envs[0].chosen, envs[1].chosen)
+    assert envs[0].episode_stats() == envs[1].episode_stats()
