@@ -359,6 +359,20 @@ struct BlockStep {
     *m1_out = m1;
     *m2_out = m2;
   }
+  // the m1 half of nd_row alone (which pairs can be played with p's higher-die move first): all the emit
+  // phase needs to order a pair's two half-moves
+  static NHD uint32_t nd_m1(const Sh& sh, int e, int p) {
+    const uint32_t bp = 1u << p;
+    if (!(sh.Ca[e] & bp)) return 0u;
+    const int b = sh.b[e], ta = p - sh.a[e];
+    if (sh.blk[e]) {
+      Pos P1 = pos_of(sh, e);
+      P1.move(p, ta);
+      return block_filter(P1, cand_mask(P1.own, P1.opp, b, p != 23), b);
+    }
+    uint32_t own1 = (sh.own[e] & ~(sh.ones[e] & bp)) | (ta >= 0 ? (1u << ta) : 0u);
+    return cand_mask(own1, sh.opp[e], b, p != 23);
+  }
   // pairs of row p that duplicate a pair of a higher row (see enum_nondouble)
   static NHD uint32_t nd_dups(const Sh& sh, int e, int p) {
     int a = sh.a[e], b = sh.b[e];
@@ -582,7 +596,13 @@ struct BlockStep {
     it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
     uint32_t sum = 0;
     while (it.next(sh.rowmask, &e, &p)) {
-      uint32_t c = (uint32_t)popc32(sh.pres[e * 24 + p] & ~nd_dups(sh, e, p));
+      // De-duplicate IN PLACE so that the emit phase reads the final mask.  This is race-free although other
+      // threads test bits of this row in nd_dups at the same time: only bits ABOVE the row index are ever
+      // removed from a row (bit p+b, bits q in (p, b)), and only bits BELOW the row index are ever tested
+      // (row x bit x-a, row q bit p < q), so a tested bit has the same value before and after.
+      uint32_t nd = sh.pres[e * 24 + p] & ~nd_dups(sh, e, p);
+      sh.pres[e * 24 + p] = nd;
+      uint32_t c = (uint32_t)popc32(nd);
       if (c) sm_add(&sh.etotal[e], c);
       sum += c;
     }
@@ -636,7 +656,7 @@ struct BlockStep {
     it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
     uint32_t G = sh.base[0][tid];
     while (it.next(sh.rowmask, &e, &p)) {
-      uint32_t nd = sh.pres[e * 24 + p] & ~nd_dups(sh, e, p);
+      uint32_t nd = sh.pres[e * 24 + p];  // already de-duplicated by ph_count
       uint32_t cnt = (uint32_t)popc32(nd);
       uint32_t off = G - sh.ebase[e];
       G += cnt;
@@ -645,8 +665,7 @@ struct BlockStep {
       uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
       bool want = idx >= off && idx < off + cnt;
       if (!want && (!slice || (int)off >= A.cap)) continue;
-      uint32_t m1, m2;
-      nd_row(sh, e, p, &m1, &m2);
+      const uint32_t m1 = nd_m1(sh, e, p);  // pairs playable "p with the higher die first"
       int a = sh.a[e], b = sh.b[e], ta = p - a;
       uint32_t k = off;
       const uint32_t hp = (uint32_t)p | ((ta < 0 ? 255u : (uint32_t)ta) << 8);  // half-move of the higher die
