@@ -128,6 +128,15 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -290,24 +299,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P_in) {
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   if (warp == 0) {
-    // ===== weight producer =====
-    if (lane == 0) {
-      uint32_t it = 0;
+    // ===== weight producer ===== (whole warp in uniform control flow, one elected lane issues the copies)
+    {
+      uint32_t s = 0, ph = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll 1
         for (int j = 0; j < 5; j++) {
           const Job jb = c_jobs[j];
+          const uint32_t full_bytes = (uint32_t)(jb.nb * kKC * 2);
+#pragma unroll 1
           for (int slot = 0; slot < 2; slot++) {
             if (pair * 2 + slot >= n_tiles) continue;
             const uint8_t* src = P.w + jb.w_off;
+#pragma unroll 1
             for (int k0 = 0; k0 < jb.k; k0 += kKC) {
-              const int klen = jb.k - k0 < kKC ? jb.k - k0 : kKC;
-              const uint32_t bytes = (uint32_t)(jb.nb * klen * 2);
-              const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+              const uint32_t bytes = jb.k - k0 < kKC ? (uint32_t)(jb.nb * (jb.k - k0) * 2) : full_bytes;
               mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-              mbar_expect_tx(bar_full + 8 * s, bytes);
-              bulk_g2s(bsm + s * kStageBytes, src, bytes, bar_full + 8 * s);
+              if (elect_one()) {
+                mbar_expect_tx(bar_full + 8 * s, bytes);
+                bulk_g2s(bsm + s * kStageBytes, src, bytes, bar_full + 8 * s);
+              }
+              __syncwarp();
               src += bytes;
-              it++;
+              if (++s == (uint32_t)kStages) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
           }
         }
@@ -315,33 +332,55 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P_in) {
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t it = 0, ready_phase[2] = {0, 0};
+    // The whole warp runs the loop (uniform control flow keeps counters and descriptors in uniform registers);
+    // one elected lane issues the tcgen05 instructions.  Descriptors are built once per job / stage and only
+    // their 14-bit address field is advanced per K step: the issue loop must cost less than the 128 tensor
+    // cycles of an M=128, N=256, K=16 MMA, otherwise the tensor core starves (it did: 34 % busy).
+    {
+      uint32_t s = 0, ph = 0, ready_phase0 = 0, ready_phase1 = 0;
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);           // SBO = 128 B, descriptor version 1
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+#pragma unroll 1
         for (int j = 0; j < 5; j++) {
           const Job jb = c_jobs[j];
           const uint32_t idesc = make_idesc(kRows, jb.nb);
+          const uint32_t b_lbo = ((uint32_t)(jb.nb * 16) >> 4) << 16;   // LBO field of the B descriptor
+          const uint32_t b_step = (uint32_t)(2 * jb.nb);                // 16 K = two 8-wide chunks of nb*16 B (>> 4)
+          const int n_stage = (jb.k + kKC - 1) / kKC;
+#pragma unroll 1
           for (int slot = 0; slot < 2; slot++) {
             if (pair * 2 + slot >= n_tiles) continue;
-            mbar_wait(bar_ready + 8 * slot, ready_phase[slot]);
-            ready_phase[slot] ^= 1u;
+            if (slot == 0) {
+              mbar_wait(bar_ready, ready_phase0);
+              ready_phase0 ^= 1u;
+            } else {
+              mbar_wait(bar_ready + 8, ready_phase1);
+              ready_phase1 ^= 1u;
+            }
             tc_fence_after();
-            const uint32_t a_saddr = sbase + kSmemA + slot * kABytes;
             const uint32_t tmem_d = tmem + (uint32_t)(slot * 256);
-            for (int k0 = 0; k0 < jb.k; k0 += kKC) {
-              const int klen = jb.k - k0 < kKC ? jb.k - k0 : kKC;
-              const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+            // A: LBO = kRows*16 = 2048 B; 16 K advance the address by 2 * 2048 B = 256 (>> 4)
+            uint32_t a_lo = (((sbase + kSmemA + (uint32_t)slot * kABytes) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+#pragma unroll 1
+            for (int st = 0; st < n_stage; st++) {
               mbar_wait(bar_full + 8 * s, ph);
               tc_fence_after();
-              for (int kk = 0; kk < klen; kk += 16) {
-                uint64_t ad = make_desc(a_saddr + (uint32_t)((k0 + kk) >> 3) * (kRows * 16), kRows * 16, 128);
-                uint64_t bd = make_desc(bsm + s * kStageBytes + (uint32_t)(kk >> 3) * (jb.nb * 16), jb.nb * 16, 128);
-                umma(tmem_d, ad, bd, idesc, (k0 | kk) ? 1u : 0u);
+              const uint32_t b_lo = (((bsm + s * kStageBytes) >> 4) & 0x3FFFu) | b_lbo;
+              const bool full_stage = (st + 1) * kKC <= jb.k;            // the last stage of layer 1 holds 16 K
+              if (elect_one()) {
+                umma(tmem_d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, st ? 1u : 0u);
+                if (full_stage)
+                  umma(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 256u), ((uint64_t)desc_hi << 32) | (b_lo + b_step), idesc, 1u);
+                umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
+                if (st + 1 == n_stage) umma_commit(slot == 0 ? bar_acc : bar_acc + 8);   // accumulator complete
               }
-              umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
-              it++;
+              __syncwarp();
+              a_lo += 512u;
+              if (++s == (uint32_t)kStages) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
-            umma_commit(bar_acc + 8 * slot);   // accumulator of this job complete
           }
         }
       }
