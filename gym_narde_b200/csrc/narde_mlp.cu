@@ -361,22 +361,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P_in) {
             const uint32_t tmem_d = tmem + (uint32_t)(slot * 256);
             // A: LBO = kRows*16 = 2048 B; 16 K advance the address by 2 * 2048 B = 256 (>> 4)
             uint32_t a_lo = (((sbase + kSmemA + (uint32_t)slot * kABytes) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+            // score mode (5-deep ring): two weight stages (4 MMAs) per trip amortise the per-trip overhead of the
+            // single issuing lane; the q-output mode has a 3-deep ring and keeps one stage per trip
+            constexpr int kTrip = OUT_MAX ? 2 : 1;
 #pragma unroll 1
-            for (int st = 0; st < n_stage; st++) {
+            for (int st = 0; st < n_stage; st += kTrip) {
+              const bool two = kTrip == 2 && st + 1 < n_stage;
+              uint32_t s2 = s + 1, ph2 = ph;
+              if (s2 == (uint32_t)kStages) {
+                s2 = 0;
+                ph2 ^= 1u;
+              }
               mbar_wait(bar_full + 8 * s, ph);
+              if (two) mbar_wait(bar_full + 8 * s2, ph2);
               tc_fence_after();
               const uint32_t b_lo = (((bsm + s * kStageBytes) >> 4) & 0x3FFFu) | b_lbo;
-              const bool full_stage = (st + 1) * kKC <= jb.k;            // the last stage of layer 1 holds 16 K
+              const uint32_t b_lo2 = (((bsm + s2 * kStageBytes) >> 4) & 0x3FFFu) | b_lbo;
+              const bool full1 = (st + 1) * kKC <= jb.k;                 // the last stage of layer 1 holds 16 K
+              const bool full2 = (st + 2) * kKC <= jb.k;
               if (elect_one()) {
                 umma(tmem_d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, st ? 1u : 0u);
-                if (full_stage)
+                if (full1)
                   umma(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 256u), ((uint64_t)desc_hi << 32) | (b_lo + b_step), idesc, 1u);
                 umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
-                if (st + 1 == n_stage) umma_commit(slot == 0 ? bar_acc : bar_acc + 8);   // accumulator complete
+                if (two) {
+                  umma(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 512u), ((uint64_t)desc_hi << 32) | b_lo2, idesc, 1u);
+                  if (full2)
+                    umma(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 768u), ((uint64_t)desc_hi << 32) | (b_lo2 + b_step), idesc, 1u);
+                  umma_commit(bar_empty + 8 * s2);
+                }
+                if (st + kTrip >= n_stage) umma_commit(slot == 0 ? bar_acc : bar_acc + 8);   // accumulator complete
               }
               __syncwarp();
-              a_lo += 512u;
-              if (++s == (uint32_t)kStages) {
+              a_lo += kTrip == 2 ? 1024u : 512u;
+              if (two) {
+                s = s2 + 1;
+                ph = ph2;
+              } else {
+                s = s2;
+                ph = ph2;
+                continue;
+              }
+              if (s == (uint32_t)kStages) {
                 s = 0;
                 ph ^= 1u;
               }
