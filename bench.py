@@ -436,9 +436,10 @@ def run_cuda_arm(args):
             line["config3_enumeration_microbench"] = cfg3
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            v, n, a, wall = cpu_selfplay(cores, 64, 150)
-            # size the reported sample to ~12 s of CPU work from the measured rate (pool start-up excluded)
-            v, n, a, wall = cpu_selfplay(cores, 64, max(150, int(12.0 * v / (cores * 64))))
+            cpu_selfplay(cores, 64, 150)                        # pool / library warm-up
+            v, n, a, wall = cpu_selfplay(cores, 64, 2000)       # rate probe (~1-2 s)
+            # size the reported sample to ~12 s of CPU work from the probed rate
+            v, n, a, wall = cpu_selfplay(cores, 64, max(2000, min(200000, int(12.0 * v / (cores * 64)))))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d procs x 64 envs, %d env turns total in %.1f s (oracle/narde_oracle.c o_selfplay)" % (cores, n, wall)}
         print(json.dumps(line))
