@@ -194,6 +194,48 @@ class VecNardeEnv:
             self._launch_full(actions, dice, flags)
         return g
 
+    # -- host-facing step: host buffers in, host buffers out, one graph replay ---------------------------
+    def host_io(self):
+        """Pinned host buffers of step_host(): write `actions` (int32 [N]; indices, or u32 fractions with
+        fraction=True), read `reward` (float32 [N]), `done` (uint8 [N]: bit 0 terminated, bit 1 truncated)."""
+        t = self.torch
+        if getattr(self, "_hio", None) is None:
+            n = self.num_envs
+            self._hio = {"actions": t.zeros(n, dtype=t.int32).pin_memory(),
+                         "reward": t.zeros(n, dtype=t.float32).pin_memory(),
+                         "done": t.zeros(n, dtype=t.uint8).pin_memory()}
+            self._hio_done_dev = t.zeros(n, dtype=t.uint8, device=self.device)
+            self._hio_graphs = {}
+        return self._hio
+
+    def step_host(self, fraction=False):
+        """One lock-step turn driven from the host (rules="full"): H2D copy of host_io()["actions"], the fused
+        step, D2H copies of reward and done bits into host_io() -- captured together as ONE CUDA graph (copy
+        nodes on pinned memory), so the copies start without stream round trips.  Asynchronous: synchronise the
+        stream (or an event) before reading the host buffers.  Box(198) stays in `self.obs` on the device."""
+        t = self.torch
+        if self.rules != "full":
+            raise ValueError("step_host needs rules='full'")
+        io = self.host_io()
+        self.step_count += 1
+        flags = (_cabi.REWARD_MOVER12 if self.reward_mode == "mover12" else 0) | (
+            _cabi.AUTORESET if self.autoreset else 0) | (_cabi.ACTION_FRACTION if fraction else 0)
+        g = self._hio_graphs.get(bool(fraction))
+        if g is None:
+            self._step_dev.fill_(self.step_count - 1)
+            t.cuda.synchronize(self.device)
+            g = t.cuda.CUDAGraph()
+            with t.cuda.graph(g):
+                self.action_in.copy_(io["actions"], non_blocking=True)
+                _cabi.advance_counter(self._step_dev)
+                self._launch_full(self.action_in, None, flags)
+                t.bitwise_or(self.done, self.trunc << 1, out=self._hio_done_dev)
+                io["reward"].copy_(self.reward, non_blocking=True)
+                io["done"].copy_(self._hio_done_dev, non_blocking=True)
+            self._hio_graphs[bool(fraction)] = g
+        g.replay()
+        return io
+
     def episode_stats(self):
         """Device-side counters as a dict (one D2H copy)."""
         v = self.stats.cpu().tolist()
@@ -210,6 +252,8 @@ class VecNardeEnv:
         self.seed, self.step_count, self.env_base = sd["seed"], sd["step_count"], sd["env_base"]
         self._step_dev.fill_(self.step_count)
         self._graphs.clear()  # the seed is a frozen kernel argument
+        if getattr(self, "_hio", None) is not None:
+            self._hio_graphs.clear()
 
     def close(self):
         pass
