@@ -74,3 +74,29 @@ def test_mlp_state_input_and_score_modes_agree_with_forward():
         assert torch.equal(q, qs), rows
         assert torch.equal(mlp.score(x), q.max(dim=1).values), rows
         assert torch.equal(mlp.score_states(lo, hi), q.max(dim=1).values), rows
+
+
+def test_mlp_cluster_pair_variant_is_bit_identical():
+    """The opt-in cluster-pair kernel (two CTAs share each weight stage through TMA multicast, stages released by
+    tcgen05.commit multicast to both CTAs) computes the same bits as the default kernel, for ragged row counts
+    (odd tile counts leave one CTA of a pair with empty rounds)."""
+    import torch
+    from gym_narde_b200 import VecNardeEnv, _cabi
+    from gym_narde_b200.mlp import AfterstateMLP
+    fn, head = _reference_net()
+    mlp = AfterstateMLP.from_module(fn, head)
+    env = VecNardeEnv(40000, seed=2)
+    env.reset()
+    for _ in range(50):
+        env.step()
+    lib = _cabi.load()
+    for rows in (40000, 129, 1, 38017):
+        lo, hi = env.lo[:rows].contiguous(), env.hi[:rows].contiguous()
+        a_q, a_s = mlp.forward_states(lo, hi), mlp.score_states(lo, hi)
+        lib.narde_debug_mlp_pair(1)
+        try:
+            b_q, b_s = mlp.forward_states(lo, hi), mlp.score_states(lo, hi)
+            torch.cuda.synchronize()
+        finally:
+            lib.narde_debug_mlp_pair(0)
+        assert torch.equal(a_q, b_q) and torch.equal(a_s, b_s), rows
