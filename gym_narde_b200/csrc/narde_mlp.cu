@@ -608,6 +608,332 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P_in) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+// =====================================================================================================
+// 2-SM variant of the scorer (packed states in, row-max out): clusters of two CTAs, tcgen05 cta_group::2.
+// One tcgen05.mma issued by the leader CTA multiplies BOTH CTAs' 128-row tiles (M = 256) with a B operand of
+// which each CTA holds half (N/2 rows of every weight stage, fetched by its own producer): per FLOP it needs
+// half the MMA instructions -- the measured limiter of k_mlp is the issue path of the issuing lane -- and half
+// the weight bytes per SM.  Hand-offs across the pair: the peer's "stage landed" is relayed to the leader by a
+// remote mbarrier arrive, the peer's epilogue threads arrive remotely on the leader's slot_ready barrier, and
+// the leader's tcgen05.commit multicasts "stage free" / "accumulator complete" to both CTAs.
+// Weights are packed per stage as [half 0 | half 1] (gym_narde_b200/mlp.py:pack_weights(two_sm=True)).
+// =====================================================================================================
+constexpr int kStages2 = 10;                    // 8 KB half-stages
+constexpr int kHalfStageBytes = 128 * kKC * 2;  // 8 KB: 128 (N/2) x 32 (K) bf16
+constexpr int kSmem2Bar = kSmemLut + 16 * 8;    // 64 barriers
+constexpr int kSmem2Xch = kSmem2Bar + 64 * 8;
+constexpr int kSmem2B = kSmem2Xch + 1024;
+constexpr int kSmem2Bytes = kSmem2B + kStages2 * kHalfStageBytes;
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_saddr) {
+  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): the data the signal
+  // announces stays in the arriving CTA's own shared memory / tensor memory; a cluster-scope release costs
+  // hundreds of cycles in the critical path of every job
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
+}
+// no release fence: the relay publishes nothing of its own (a cluster-scope release per weight stage throttled
+// the whole pipeline to ~700 cycles per stage)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_saddr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_mlp2sm(Params P_in) {
+  Params P = P_in;
+  if (P.rows_dev) {
+    const int64_t rd = *P.rows_dev;
+    P.rows = rd < P.rows ? (rd < 0 ? 0 : rd) : P.rows;
+  }
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bsm = sbase + kSmem2B;
+  const uint32_t bar_full = sbase + kSmem2Bar;                 // [kStages2] own half landed
+  const uint32_t bar_full2 = bar_full + 8 * kStages2;          // [kStages2] (leader) the peer's half landed
+  const uint32_t bar_empty = bar_full2 + 8 * kStages2;         // [kStages2] both SMs' MMAs have read the stage
+  const uint32_t bar_acc = bar_empty + 8 * kStages2;           // [2]
+  const uint32_t bar_ready = bar_acc + 16;                     // [2] (leader) both CTAs' slot ready: one arrival per CTA
+  float* s_bias = reinterpret_cast<float*>(smem + kSmemBias);
+  uint64_t* s_lut = reinterpret_cast<uint64_t*>(smem + kSmemLut);
+  const uint32_t crank = cluster_ctarank();
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages2; s++) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full2 + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(bar_acc + 8 * s, 1);
+      mbar_init(bar_ready + 8 * s, 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {  // both CTAs of the pair allocate all 512 TMEM columns together
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  for (int k = tid; k < kBiasFloats; k += kThreads) s_bias[k] = P.bias[k];
+  if (tid < 16) {
+    const int n = tid;
+    uint32_t a = pack_bf16(n >= 1 ? 1.0f : 0.0f, n >= 2 ? 1.0f : 0.0f);
+    uint32_t b = pack_bf16(n >= 3 ? 1.0f : 0.0f, n > 3 ? (float)(n - 3) * 0.5f : 0.0f);
+    s_lut[n] = (uint64_t)a | ((uint64_t)b << 32);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  cluster_sync_all();
+
+  const int64_t n_tiles = (P.rows + kRows - 1) / kRows;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const int64_t n_rounds = (n_pairs + gridDim.x - 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ===== weight producer: this CTA's half of every stage =====
+    uint32_t s = 0, ph = 0;
+    for (int64_t round = 0; round < n_rounds; round++) {
+#pragma unroll 1
+      for (int j = 0; j < 5; j++) {
+        const Job jb = c_jobs[j];
+#pragma unroll 1
+        for (int slot = 0; slot < 2; slot++) {
+          const uint8_t* src = P.w + jb.w_off;
+#pragma unroll 1
+          for (int k0 = 0; k0 < jb.k; k0 += kKC) {
+            const int klen = jb.k - k0 < kKC ? jb.k - k0 : kKC;
+            const uint32_t half = (uint32_t)((jb.nb >> 1) * klen * 2);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(bar_full + 8 * s, half);
+              bulk_g2s(bsm + s * kHalfStageBytes, src + crank * half, half, bar_full + 8 * s);
+            }
+            __syncwarp();
+            src += 2 * half;
+            if (++s == (uint32_t)kStages2) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && crank == 1) {
+    // ===== peer relay: "my half of stage s has landed" -> the leader's full2[s] =====
+    uint32_t s = 0, ph = 0;
+    for (int64_t round = 0; round < n_rounds; round++) {
+#pragma unroll 1
+      for (int j = 0; j < 5; j++) {
+        const int n_stage = (c_jobs[j].k + kKC - 1) / kKC;
+#pragma unroll 1
+        for (int st = 0; st < 2 * n_stage; st++) {
+          mbar_wait(bar_full + 8 * s, ph);
+          if (elect_one()) mbar_arrive_remote_relaxed(map_to_cta(bar_full2 + 8 * s, 0));
+          __syncwarp();
+          if (++s == (uint32_t)kStages2) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if ((warp == 1 || warp == kMmaWarp1) && crank == 0) {
+    // ===== MMA issuers of the leader CTA: one per slot, M = 256 over both CTAs =====
+    const int my_slot = warp == 1 ? 0 : 1;
+    uint32_t s = 0, ph = 0, ready_phase = 0;
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t tmem_d = tmem + (uint32_t)(my_slot * 256);
+    const uint32_t a_base = (((sbase + kSmemA + (uint32_t)my_slot * kABytes) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);
+    const uint32_t my_ready = bar_ready + 8 * my_slot, my_acc = bar_acc + 8 * my_slot;
+    for (int64_t round = 0; round < n_rounds; round++) {
+#pragma unroll 1
+      for (int j = 0; j < 5; j++) {
+        const Job jb = c_jobs[j];
+        const uint32_t idesc = make_idesc(256, jb.nb);
+        const uint32_t nh = (uint32_t)(jb.nb >> 1);                   // B rows held by each CTA
+        const uint32_t b_lbo = ((nh * 16u) >> 4) << 16;
+        const uint32_t b_step = 2u * nh;                              // 16 K = two 8-wide chunks of nh*16 B (>> 4)
+        const int n_stage = (jb.k + kKC - 1) / kKC;
+        if (my_slot == 1) {                                           // walk the other slot's stages in order
+          for (int st = 0; st < n_stage; st++) {
+            mbar_wait(bar_full + 8 * s, ph);
+            if (++s == (uint32_t)kStages2) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+        mbar_wait(my_ready, ready_phase);
+        ready_phase ^= 1u;
+        tc_fence_after();
+        uint32_t a_lo = a_base;
+#pragma unroll 1
+        for (int st = 0; st < n_stage; st += 2) {
+          const bool two = st + 1 < n_stage;
+          uint32_t s2 = s + 1, ph2 = ph;
+          if (s2 == (uint32_t)kStages2) {
+            s2 = 0;
+            ph2 ^= 1u;
+          }
+          mbar_wait(bar_full + 8 * s, ph);
+          mbar_wait(bar_full2 + 8 * s, ph);
+          if (two) {
+            mbar_wait(bar_full + 8 * s2, ph2);
+            mbar_wait(bar_full2 + 8 * s2, ph2);
+          }
+          tc_fence_after();
+          const uint32_t b_lo = (((bsm + s * kHalfStageBytes) >> 4) & 0x3FFFu) | b_lbo;
+          const uint32_t b_lo2 = (((bsm + s2 * kHalfStageBytes) >> 4) & 0x3FFFu) | b_lbo;
+          const bool full1 = (st + 1) * kKC <= jb.k;
+          const bool full2 = (st + 2) * kKC <= jb.k;
+          if (elect_one()) {
+            umma2(tmem_d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, st ? 1u : 0u);
+            if (full1)
+              umma2(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 256u), ((uint64_t)desc_hi << 32) | (b_lo + b_step), idesc, 1u);
+            umma2_commit_multicast(bar_empty + 8 * s, (uint16_t)3);
+            if (two) {
+              umma2(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 512u), ((uint64_t)desc_hi << 32) | b_lo2, idesc, 1u);
+              if (full2)
+                umma2(tmem_d, ((uint64_t)desc_hi << 32) | (a_lo + 768u), ((uint64_t)desc_hi << 32) | (b_lo2 + b_step), idesc, 1u);
+              umma2_commit_multicast(bar_empty + 8 * s2, (uint16_t)3);
+            }
+            if (st + 2 >= n_stage) umma2_commit_multicast(my_acc, (uint16_t)3);
+          }
+          __syncwarp();
+          a_lo += 1024u;
+          if (two) {
+            s = s2 + 1;
+            ph = ph2;
+            if (s == (uint32_t)kStages2) {
+              s = 0;
+              ph ^= 1u;
+            }
+          } else {
+            s = s2;
+            ph = ph2;
+          }
+        }
+        if (my_slot == 0) {
+          for (int st = 0; st < n_stage; st++) {
+            mbar_wait(bar_full + 8 * s, ph);
+            if (++s == (uint32_t)kStages2) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < kMmaWarp1) {
+    // ===== epilogue groups (same as k_mlp<states, max>) =====
+    const int e = warp - 2;
+    const int slot = e >> 3;
+    const int quarter = warp & 3;
+    const int half = (e & 7) >> 2;
+    const int gtid = (e & 7) * 32 + lane;
+    const int r = quarter * 32 + lane;
+    uint8_t* a_tile = smem + kSmemA + slot * kABytes;
+    const uint32_t tmem_row = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 256);
+    const uint32_t ready_remote = map_to_cta(bar_ready + 8 * slot, 0);   // the leader's barrier (own when crank == 0)
+    uint32_t acc_phase = 0;
+    for (int64_t round = 0; round < n_rounds; round++) {
+      const int64_t tile = (round * gridDim.x + blockIdx.x) * 2 + slot;
+      const int64_t row0 = tile * kRows;
+      load_state_tile(a_tile, P.lo, P.hi, row0, P.rows, gtid, s_lut);
+      fence_async_smem();
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");   // the slot's 8 warps, then ONE remote arrive
+      if (gtid == 0) mbar_arrive_remote(ready_remote);
+      float best = -3.0e38f;
+#pragma unroll 1
+      for (int j = 0; j < 5; j++) {
+        const Job jb = c_jobs[j];
+        mbar_wait(bar_acc + 8 * slot, acc_phase);
+        acc_phase ^= 1u;
+        tc_fence_after();
+        const int ncol = jb.nb >> 1;
+        const int cbase = half * ncol;
+        const int nch = ncol >> 5;
+#pragma unroll 1
+        for (int c = 0; c < nch; c++) {
+          uint32_t va[32];
+          tmem_ld32(tmem_row + (uint32_t)(cbase + c * 32), va);
+          tmem_wait_ld();
+          const int col = cbase + c * 32;
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + jb.b_off + col);
+          if (j < 2) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
+              uint4 pk;
+              pk.x = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 0]) + ba.x, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 1]) + ba.y, 0.0f));
+              pk.y = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 2]) + ba.z, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 3]) + ba.w, 0.0f));
+              pk.z = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 4]) + bb.x, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 5]) + bb.y, 0.0f));
+              pk.w = pack_bf16(fmaxf(__uint_as_float(va[g * 8 + 6]) + bb.z, 0.0f), fmaxf(__uint_as_float(va[g * 8 + 7]) + bb.w, 0.0f));
+              *reinterpret_cast<uint4*>(a_tile + tile_off(kRows, r, col + g * 8)) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+              const float4 bq = b4[g];
+              best = fmaxf(best, fmaxf(fmaxf(__uint_as_float(va[g * 4 + 0]) + bq.x, __uint_as_float(va[g * 4 + 1]) + bq.y),
+                                       fmaxf(__uint_as_float(va[g * 4 + 2]) + bq.z, __uint_as_float(va[g * 4 + 3]) + bq.w)));
+            }
+          }
+        }
+        if (j < 2) fence_async_smem();
+        if (j == 4) {
+          float* xch = reinterpret_cast<float*>(smem + kSmem2Xch) + slot * 128;
+          if (half == 1) xch[r] = best;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
+          if (half == 0 && row0 + r < P.rows) P.score[row0 + r] = fmaxf(best, xch[r]);
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");   // xch is reused by the next tile
+        }
+        if (j < 4) {
+          tc_fence_before();
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + slot) : "memory");
+          if (gtid == 0) mbar_arrive_remote(ready_remote);
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 bool g_mlp_attr_set[8] = {false, false, false, false, false, false, false, false};
 // The cluster-pair variant halves the L2 weight traffic but measured no faster (0.178 vs 0.176 ms for 350 k rows:
 // the kernel is bound by the MMA issue path, not by the weight stream), so it is opt-in: NARDE_MLP_PAIR=1 in the
@@ -659,6 +985,38 @@ bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 }  // namespace
 
 extern "C" {
+
+// Debug / A-B entry (not part of the public ABI): the cta_group::2 scorer.  wpack2: weights packed with
+// pack_weights(two_sm=True).
+int narde_debug_mlp_score_states_2sm(const void* lo, const void* hi, int64_t rows, const int64_t* rows_dev, const void* wpack2,
+                                     const float* bias, float* score, void* stream) {
+  if (rows == 0) return 0;
+  if (rows < 0 || !lo || !hi || !wpack2 || !bias || !score) return -1;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2Bytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, rows_dev, (const uint8_t*)wpack2, bias, nullptr, score};
+  int64_t tiles = (rows + kRows - 1) / kRows, pairs = (tiles + 1) / 2;
+  int grid = (int)(pairs < 148 ? pairs : 148);
+  grid = (grid + 1) & ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem2Bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_mlp2sm, P);
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
+}
 
 // Debug / A-B switch (not part of the public ABI): 1 = cluster-pair variant with multicast weight stages.
 int narde_debug_mlp_pair(int on) {

@@ -16,31 +16,35 @@ from . import _cabi
 IN, HID, OUT, K1, KC = 198, 256, 576, 208, 32
 
 
-def _pack_block(w_blk):
+def _pack_block(w_blk, two_sm=False):
     """w_blk: [nb, K] float32 (K a multiple of 16) -> bf16 stages of 32 K (the last may be 16) in the K-major
-    interleave layout: offset(n, k) = (k//8)*(nb*16) + (n//8)*128 + (n%8)*16 + (k%8)*2 within a stage."""
+    interleave layout: offset(n, k) = (k//8)*(nb*16) + (n//8)*128 + (n%8)*16 + (k%8)*2 within a stage.
+    two_sm: every stage is stored as [rows 0..nb/2) | rows nb/2..nb)], each half in that layout on its own
+    (the B operand halves of a cta_group::2 MMA, one per CTA of the pair)."""
     import torch
 
     nb, k = w_blk.shape
     stages = []
     for k0 in range(0, k, KC):
         klen = min(KC, k - k0)
-        s = w_blk[:, k0:k0 + klen].to(torch.bfloat16)                   # [nb, klen]
-        s = s.reshape(nb // 8, 8, klen // 8, 8).permute(2, 0, 1, 3)      # [kchunk, rowgroup, row, k]
-        stages.append(s.contiguous().view(torch.int16).reshape(-1))
+        for rows in ((slice(0, nb // 2), slice(nb // 2, nb)) if two_sm else (slice(0, nb),)):
+            s = w_blk[rows, k0:k0 + klen].to(torch.bfloat16)             # [n, klen]
+            n = s.shape[0]
+            s = s.reshape(n // 8, 8, klen // 8, 8).permute(2, 0, 1, 3)   # [kchunk, rowgroup, row, k]
+            stages.append(s.contiguous().view(torch.int16).reshape(-1))
     return torch.cat(stages)
 
 
-def pack_weights(w1, b1, w2, b2, w3, b3):
+def pack_weights(w1, b1, w2, b2, w3, b3, two_sm=False):
     """torch Linear weights ([out, in]) and biases -> (wpack int16 tensor, bias float32 [1088])."""
     import torch
 
     assert tuple(w1.shape) == (HID, IN) and tuple(w2.shape) == (HID, HID) and tuple(w3.shape) == (OUT, HID)
     w1p = torch.zeros((HID, K1), dtype=torch.float32, device=w1.device)
     w1p[:, :IN] = w1.float()
-    parts = [_pack_block(w1p), _pack_block(w2.float())]
+    parts = [_pack_block(w1p, two_sm), _pack_block(w2.float(), two_sm)]
     for n0 in range(0, OUT, 256):
-        parts.append(_pack_block(w3.float()[n0:min(n0 + 256, OUT)]))
+        parts.append(_pack_block(w3.float()[n0:min(n0 + 256, OUT)], two_sm))
     wpack = torch.cat(parts).contiguous()
     bias = torch.cat([b1.float(), b2.float(), b3.float()]).contiguous()
     return wpack, bias
@@ -59,6 +63,7 @@ class AfterstateMLP:
         lib = _cabi.load()
         self.torch, self.lib = torch, lib
         self.wpack, self.bias = pack_weights(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), w3.cuda(), b3.cuda())
+        self.wpack2, _ = pack_weights(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), w3.cuda(), b3.cuda(), two_sm=True)
 
     @classmethod
     def from_module(cls, feature_network, move1_head):
@@ -129,6 +134,21 @@ class AfterstateMLP:
                   (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k,
                    C.c_void_p(rows_dev.data_ptr() if rows_dev is not None else None), C.c_void_p(self.wpack.data_ptr()),
                    C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_score_states")
+        return out
+
+    def score_states_2sm(self, lo, hi, out=None, rows_dev=None):
+        """score_states through the cta_group::2 kernel (clusters of two CTAs, M = 256 per tcgen05.mma)."""
+        t = self.torch
+        self._check_states(lo, hi)
+        k = lo.shape[0]
+        if out is None:
+            out = t.empty(k, dtype=t.float32, device=lo.device)
+        fn = self.lib.narde_debug_mlp_score_states_2sm
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+        self._run(fn, (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k,
+                       C.c_void_p(rows_dev.data_ptr() if rows_dev is not None else None), C.c_void_p(self.wpack2.data_ptr()),
+                       C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_debug_mlp_score_states_2sm")
         return out
 
     __call__ = forward

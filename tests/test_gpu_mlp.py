@@ -100,3 +100,24 @@ def test_mlp_cluster_pair_variant_is_bit_identical():
         finally:
             lib.narde_debug_mlp_pair(0)
         assert torch.equal(a_q, b_q) and torch.equal(a_s, b_s), rows
+
+
+def test_mlp_cta_group2_scorer_is_bit_identical():
+    """k_mlp2sm: clusters of two CTAs, tcgen05.mma cta_group::2 (M = 256 over both CTAs' tiles, each CTA holds half
+    of the B operand), peer hand-offs through remote mbarrier arrives and commit multicast.  Same bits as the
+    default scorer, including ragged row counts that leave a CTA of the pair without rows."""
+    import torch
+    from gym_narde_b200 import VecNardeEnv
+    from gym_narde_b200.mlp import AfterstateMLP
+    fn, head = _reference_net()
+    mlp = AfterstateMLP.from_module(fn, head)
+    env = VecNardeEnv(50000, seed=8)
+    env.reset()
+    for _ in range(60):
+        env.step()
+    for rows in (50000, 1, 128, 129, 257, 40001):
+        lo, hi = env.lo[:rows].contiguous(), env.hi[:rows].contiguous()
+        a = mlp.score_states(lo, hi)
+        b = mlp.score_states_2sm(lo, hi)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), rows
