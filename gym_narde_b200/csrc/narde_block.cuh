@@ -65,7 +65,7 @@ NHD_NOINLINE int walk_short_double(const Pos& P, int d, bool first_turn, int H, 
   return enum_double(P, d, first_turn, !block_rule_irrelevant(P, d, d), sink, &depth);
 }
 
-constexpr int kL1PerEnv = 8;  // level-1 doubles items a CTA can hold per env (all-doubles CTAs with > 8 sources per env overflow to the sequential walk; never observed)
+constexpr int kL1PerEnv = 5;  // level-1 doubles items a CTA can hold per env (all-doubles CTAs with > 8 sources per env overflow to the sequential walk; never observed)
 
 template <int BLK>
 struct BlockShared {
@@ -88,6 +88,7 @@ struct BlockShared {
   uint32_t d2mask[kL1Cap];
   uint32_t d2base[kL1Cap + 1];
   uint8_t l1env[kL1Cap], l1src[kL1Cap];
+  uint16_t itab[BLK * 24];               // ND work items in canonical order: env << 5 | source point
   uint32_t n_l1;
   // scan scratch (4 lanes)
   uint32_t part[4][BLK], base[4][BLK], ws[4][36];
@@ -308,6 +309,14 @@ struct BlockStep {
   static NHD void ph_item_bases(int tid, Sh& sh) {
     sh.ibase[tid] = sh.base[0][tid];
     sh.dbase[tid] = sh.base[1][tid];
+    // item table of the pair rows: every later phase deals out [j0, j1) and reads (env, point) from here
+    // instead of searching the per-env bases and walking bit masks (17 % of the warp samples before)
+    uint32_t j = sh.base[0][tid];
+    for (uint32_t m = sh.rowmask[tid]; m;) {
+      int p = fls32(m);
+      m &= ~(1u << p);
+      sh.itab[j++] = (uint16_t)((tid << 5) | p);
+    }
     if (tid == 0) {
       sh.ibase[BLK] = sh.ws[0][32];
       sh.dbase[BLK] = sh.ws[1][32];
@@ -551,8 +560,10 @@ struct BlockStep {
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
     ItemIter<uint32_t> it;
-    it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
-    while (it.next(sh.rowmask, &e, &p)) {
+    for (int jj = j0; jj < j1; jj++) {
+      const uint32_t v = sh.itab[jj];
+      e = (int)(v >> 5);
+      p = (int)(v & 31u);
       uint32_t m1, m2;
       nd_row(sh, e, p, &m1, &m2);
       sh.pres[e * 24 + p] = m1 | m2;
@@ -593,9 +604,11 @@ struct BlockStep {
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
     ItemIter<uint32_t> it;
-    it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
     uint32_t sum = 0;
-    while (it.next(sh.rowmask, &e, &p)) {
+    for (int jj = j0; jj < j1; jj++) {
+      const uint32_t v = sh.itab[jj];
+      e = (int)(v >> 5);
+      p = (int)(v & 31u);
       // De-duplicate IN PLACE so that the emit phase reads the final mask.  This is race-free although other
       // threads test bits of this row in nd_dups at the same time: only bits ABOVE the row index are ever
       // removed from a row (bit p+b, bits q in (p, b)), and only bits BELOW the row index are ever tested
@@ -653,9 +666,11 @@ struct BlockStep {
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
     ItemIter<uint32_t> it;
-    it.init(sh.rowmask, sh.ibase, BLK, j0, j1);
     uint32_t G = sh.base[0][tid];
-    while (it.next(sh.rowmask, &e, &p)) {
+    for (int jj = j0; jj < j1; jj++) {
+      const uint32_t v = sh.itab[jj];
+      e = (int)(v >> 5);
+      p = (int)(v & 31u);
       uint32_t nd = sh.pres[e * 24 + p];  // already de-duplicated by ph_count
       uint32_t cnt = (uint32_t)popc32(nd);
       uint32_t off = G - sh.ebase[e];
