@@ -317,6 +317,17 @@ struct BlockStep {
       m &= ~(1u << p);
       sh.itab[j++] = (uint16_t)((tid << 5) | p);
     }
+    // doubles level-1 items (env, first source): same idea, straight into the l1env / l1src tables
+    uint32_t jd = sh.base[1][tid];
+    if (sh.ws[1][32] <= (uint32_t)Sh::kL1Cap) {
+      for (uint32_t m = sh.dmask[tid]; m;) {
+        int p = fls32(m);
+        m &= ~(1u << p);
+        sh.l1env[jd] = (uint8_t)tid;
+        sh.l1src[jd] = (uint8_t)p;
+        jd++;
+      }
+    }
     if (tid == 0) {
       sh.ibase[BLK] = sh.ws[0][32];
       sh.dbase[BLK] = sh.ws[1][32];
@@ -559,7 +570,6 @@ struct BlockStep {
     constexpr bool deferral = DEFER;
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    ItemIter<uint32_t> it;
     for (int jj = j0; jj < j1; jj++) {
       const uint32_t v = sh.itab[jj];
       e = (int)(v >> 5);
@@ -569,32 +579,68 @@ struct BlockStep {
       sh.pres[e * 24 + p] = m1 | m2;
     }
     chunk((int)sh.n_l1, tid, &j0, &j1);
-    it.init(sh.dmask, sh.dbase, BLK, j0, j1);
     uint32_t sum = 0;
-    int j = j0;
-    while (it.next(sh.dmask, &e, &p)) {
+    for (int j = j0; j < j1; j++) {
+      e = sh.l1env[j];
+      p = sh.l1src[j];
       int d = sh.a[e];
       Pos P1 = pos_of(sh, e);
       P1.move(p, p - d);
       uint32_t m2 = cand_mask(P1.own, P1.opp, d, (p == 23) < head_budget(sh, e)) & ((2u << p) - 1u);
       sh.d2mask[j] = m2;
-      sh.l1env[j] = (uint8_t)e;
-      sh.l1src[j] = (uint8_t)p;
       if (!sh.blk[e] || deferral) sm_max(&sh.maxd[e], m2 ? 2u : 1u);
       if (sh.blk[e] && deferral && violates_block(P1.own, P1.opp)) sm_max(&sh.defer[e], 1u);
       sum += (uint32_t)popc32(m2);
-      j++;
     }
     sh.part[1][tid] = sum;
   }
+  // level-2 doubles items share the item table with the pair rows when both fit (they practically always do;
+  // otherwise the phases fall back to the searching iterator)
+  static NHD bool l2_in_table(const Sh& sh, uint32_t n_l2) {
+    return sh.n_l1 > 0 && sh.n_l1 < 1024u && sh.ibase[BLK] + n_l2 <= (uint32_t)(BLK * 24);
+  }
+  struct L2Iter {  // items (level-1 item j, second source p) of [j0, j1): from the table, else by searching
+    bool tab;
+    int jj, j1;
+    uint32_t t0;
+    ItemIter<uint32_t> it;
+    NHD void init(const Sh& sh, int j0, int j1_) {
+      const int n1 = (int)sh.n_l1;
+      tab = l2_in_table(sh, sh.d2base[n1]);
+      jj = j0;
+      j1 = j1_;
+      t0 = sh.ibase[BLK];
+      if (!tab) it.init(sh.d2mask, sh.d2base, n1, j0, j1_);
+    }
+    NHD bool next(const Sh& sh, int* j, int* p) {
+      if (!tab) return it.next(sh.d2mask, j, p);
+      if (jj >= j1) return false;
+      const uint32_t v = sh.itab[t0 + (uint32_t)jj++];
+      *j = (int)(v >> 5);
+      *p = (int)(v & 31u);
+      return true;
+    }
+  };
   // after the scan of level-2 counts: per level-1 item bases
   static NHD void ph_l2_bases(int tid, Sh& sh) {
     int j0, j1;
     chunk((int)sh.n_l1, tid, &j0, &j1);
     uint32_t r = sh.base[1][tid];
+    // level-2 items (level-1 item, second source) go into the free tail of the item table when they fit
+    const uint32_t t0 = sh.ibase[BLK];
+    const bool tab = l2_in_table(sh, sh.ws[1][32]);
     for (int j = j0; j < j1; j++) {
       sh.d2base[j] = r;
-      r += (uint32_t)popc32(sh.d2mask[j]);
+      uint32_t m = sh.d2mask[j];
+      if (tab) {
+        uint32_t k = t0 + r;
+        for (uint32_t mm = m; mm;) {
+          int p = fls32(mm);
+          mm &= ~(1u << p);
+          sh.itab[k++] = (uint16_t)((j << 5) | p);
+        }
+      }
+      r += (uint32_t)popc32(m);
     }
     if (tid == 0) sh.d2base[sh.n_l1] = sh.ws[1][32];
   }
@@ -603,7 +649,6 @@ struct BlockStep {
     constexpr bool deferral = DEFER;
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    ItemIter<uint32_t> it;
     uint32_t sum = 0;
     for (int jj = j0; jj < j1; jj++) {
       const uint32_t v = sh.itab[jj];
@@ -624,9 +669,10 @@ struct BlockStep {
     sum = 0;
     if (n1 > 0) {
       chunk((int)sh.d2base[n1], tid, &j0, &j1);
-      it.init(sh.d2mask, sh.d2base, n1, j0, j1);
+      L2Iter it2;
+      it2.init(sh, j0, j1);
       int j;
-      while (it.next(sh.d2mask, &j, &p)) {
+      while (it2.next(sh, &j, &p)) {
         e = sh.l1env[j];
         int s1 = sh.l1src[j];
         uint32_t c;
@@ -665,7 +711,6 @@ struct BlockStep {
   static NHD void ph_emit(int tid, Sh& sh, int64_t row0, const StepFullArgs& A) {
     int j0, j1, e, p;
     chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    ItemIter<uint32_t> it;
     uint32_t G = sh.base[0][tid];
     for (int jj = j0; jj < j1; jj++) {
       const uint32_t v = sh.itab[jj];
@@ -700,10 +745,11 @@ struct BlockStep {
     int n1 = (int)sh.n_l1;
     if (n1 > 0) {
       chunk((int)sh.d2base[n1], tid, &j0, &j1);
-      it.init(sh.d2mask, sh.d2base, n1, j0, j1);
+      L2Iter it2;
+      it2.init(sh, j0, j1);
       G = sh.base[1][tid];
       int j;
-      while (it.next(sh.d2mask, &j, &p)) {
+      while (it2.next(sh, &j, &p)) {
         e = sh.l1env[j];
         int s1 = sh.l1src[j];
         uint32_t total = sh.etotal[e];
