@@ -347,6 +347,19 @@ def run_cuda_arm(args):
     torch.cuda.synchronize()
     ms_small = timed_loop(lambda: small.step(), min(K, 50))
 
+    # ---- Tier R side measurement: the reference CODE's exact NardeEnv.step (narde_env.py:27-103) batched ----
+    ref_env = VecNardeEnv(E, seed=SEED, rules="reference", device=dev)
+    ref_env.reset()
+    codes = torch.randint(0, 576, (E, 2), dtype=torch.int32, device=dev)
+    for _ in range(30):
+        ref_env.step(codes)
+    torch.cuda.synchronize()
+    ms_ref = timed_loop(lambda: ref_env.step(codes), min(K, 50))
+    tier_r = {"value": E * len(ms_ref) / (sum(ms_ref) * 1e-3), "unit": "reference-exact env steps/s (rank 0)", "envs": E,
+              "ms_per_step": sum(ms_ref) / len(ms_ref),
+              "note": "k_roll_dice + k_step_ref: NardeEnv.step semantics of the reference code (2 dice, <= 2 half-moves, its "
+                      "quirks), int32[24] observation, uniformly random action codes as examples/play_random_agent.py samples them"}
+
     # ---- config 5 side measurement: afterstate scoring with the tcgen05 MLP, 64K envs (rank 0's GPU) ----
     cfg5 = cfg3 = None
     if not args.no_config5 and rank == 0:
@@ -428,6 +441,7 @@ def run_cuda_arm(args):
                                   "ms_per_step": sum(ms_small) / len(ms_small)},
             "episode_stats": {k: int(v) for k, v in zip(_cabi.STAT_NAMES, st_all.sum(0).tolist())},
         }
+        line["tier_r_reference_rules_step"] = tier_r
         if bcast_ms is not None:
             line["policy_broadcast_ms"] = bcast_ms
         if cfg5 is not None:
