@@ -639,17 +639,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_saddr) {
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_saddr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAITC_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONEC_%=;\n\t"
-      "bra WAITC_%=;\n\t"
-      "DONEC_%=:\n\t}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
 __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
