@@ -54,17 +54,26 @@ __device__ __forceinline__ void write_obs198_cta(const State* sm, const float4* 
                                                  float* __restrict__ obs, const uint32_t* skip = nullptr) {
   float* base = obs + row0 * 198;
   const int items = rows * 24;
+  // rows are 792 B: in a 16-byte aligned row the WHITE block (4 floats per point from offset 0) is made of
+  // aligned 16-byte lanes and the BLACK block (from offset 392 B) of 8-byte ones; in the next row it is the
+  // other way round -- one 16-byte and two 8-byte stores per (env, point) instead of four 8-byte stores
+  const bool even_aligned = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0);
   for (int g = threadIdx.x; g < items; g += blockDim.x) {
     int e = g / 24, pt = g - e * 24;
     if (skip && skip[e]) continue;  // row written by the deferred kernel
     int v = sm[e].point(pt);
     float4 fw = lut[v > 0 ? v : 0], fb = lut[v < 0 ? -v : 0];
-    float2* pw = reinterpret_cast<float2*>(base + e * 198 + 4 * pt);
-    float2* pb = reinterpret_cast<float2*>(base + e * 198 + 98 + 4 * pt);
-    pw[0] = make_float2(fw.x, fw.y);
-    pw[1] = make_float2(fw.z, fw.w);
-    pb[0] = make_float2(fb.x, fb.y);
-    pb[1] = make_float2(fb.z, fb.w);
+    float* rw = base + e * 198 + 4 * pt;
+    float* rb = rw + 98;
+    if (((e & 1) == 0) == even_aligned) {
+      *reinterpret_cast<float4*>(rw) = fw;
+      reinterpret_cast<float2*>(rb)[0] = make_float2(fb.x, fb.y);
+      reinterpret_cast<float2*>(rb)[1] = make_float2(fb.z, fb.w);
+    } else {
+      reinterpret_cast<float2*>(rw)[0] = make_float2(fw.x, fw.y);
+      reinterpret_cast<float2*>(rw)[1] = make_float2(fw.z, fw.w);
+      *reinterpret_cast<float4*>(rb) = fb;
+    }
   }
   for (int g = threadIdx.x; g < rows * 3; g += blockDim.x) {
     int e = g / 3, k = g - e * 3;
