@@ -1,7 +1,7 @@
 """GPU soak (not part of the pytest suites: minutes of single-core Python): the fused step against the oracle,
 lock-step, over ~2 M env turns on both CTA tiles of the kernel, with auto-reset and the Philox stream."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import parity as P

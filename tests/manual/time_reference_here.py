@@ -4,7 +4,7 @@ reference's own speed.  The reference cannot travel to the GPU box; the result i
 (profiles/reference_python_timing_container.json).  Test infrastructure: imports oracle/.
 """
 import json, os, platform, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 from oracle import ref_loader, oracle as O
