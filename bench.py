@@ -254,11 +254,19 @@ def run_cuda_arm(args):
     h_rew = torch.zeros(E, dtype=torch.float32).pin_memory()
     h_done = torch.zeros(E, dtype=torch.uint8).pin_memory()
 
-    def e2e_step():
+    def e2e_step_copies():
         d_idx.copy_(h_idx, non_blocking=True)               # H2D: this step's inputs (action choices)
         obs, rew, term, trunc, info = env.step(d_idx, fraction=True)   # public API call (graph replay)
         h_rew.copy_(rew, non_blocking=True)                  # D2H: this step's results
         h_done.copy_(env.done, non_blocking=True)
+
+    io = env.host_io()                                       # pinned host buffers of the host-facing step
+    io["actions"].copy_(h_idx)
+
+    def e2e_step():
+        # public API call with HOST buffers, zero-copy: the fused step reads this step's action choices from
+        # pinned host memory and writes reward / done / truncated into pinned host memory (PCIe inside the kernel)
+        env.step_host(fraction=True)
 
     for _ in range(W):
         e2e_step()
@@ -266,70 +274,40 @@ def run_cuda_arm(args):
     ms_e2e = timed_loop(e2e_step, K)
     barrier()
     total_e2e = sum(ms_e2e)
+    for _ in range(W):
+        e2e_step_copies()
+    ms_e2e_copies = timed_loop(e2e_step_copies, K)
+    barrier()
 
-    # ---- end-to-end, pipelined: the same per-step copies, double-buffered on copy streams so that the H2D of
-    # step t+1 and the D2H of step t-1 overlap the kernels of step t (an open-loop / prefetching host).  Timed
-    # as ONE device interval over all K steps; no L2 flush is possible inside it, but a step writes ~180 MB
-    # (Box(198) 104 MB + action lists 67 MB + ...), more than the 126 MB L2. ----
-    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    d_idx2 = [torch.zeros(E, dtype=torch.int32, device=dev) for _ in range(2)]
-    d_rew2 = [torch.zeros(E, dtype=torch.float32, device=dev) for _ in range(2)]
-    d_done2 = [torch.zeros(E, dtype=torch.uint8, device=dev) for _ in range(2)]
-    h_rew2 = [torch.zeros(E, dtype=torch.float32).pin_memory() for _ in range(2)]
-    h_done2 = [torch.zeros(E, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    # ---- end-to-end, pipelined: VecNardeEnv.host_pipeline -- windows of 8 turns as ONE CUDA graph whose per-turn
+    # H2D (action choices) / D2H (reward, done bits) copies run on copy streams, double-buffered on the device, so
+    # the copies of neighbouring turns overlap the kernels.  Every turn still copies its own inputs in and its own
+    # results out; timed as one device interval over K turns; no L2 flush is possible inside it, but a turn writes
+    # ~120 MB of outputs (Box(198) 104 MB + action lists + ...) on top of the previous turn's, more than the L2. ----
+    depth = 8
+    pipe = env.host_pipeline(depth=depth, fraction=True)
+    pipe.actions.copy_(h_idx[None, :].expand(depth, E))
+    n_rep = max(1, (K + depth - 1) // depth)
 
-    def e2e_pipelined(n_steps):
-        main = torch.cuda.current_stream(dev)
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_c = [torch.cuda.Event() for _ in range(2)]
-        ev_out = [torch.cuda.Event() for _ in range(2)]
+    def e2e_pipelined(reps):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record(main)
-        s_in.wait_stream(main)
-        s_out.wait_stream(main)
-        def prefetch(t):                                           # H2D of step t's inputs on the copy-in stream
-            b = t & 1
-            torch.cuda.set_stream(s_in)
-            if t >= 2:
-                s_in.wait_event(ev_c[b])                           # step t-2 has consumed d_idx2[b]
-            d_idx2[b].copy_(h_idx, non_blocking=True)
-            ev_in[b].record(s_in)
-            torch.cuda.set_stream(main)
-
-        prefetch(0)
-        for t in range(n_steps):
-            b = t & 1
-            if t + 1 < n_steps:
-                prefetch(t + 1)                                    # overlaps the kernels of step t
-            main.wait_event(ev_in[b])
-            if t >= 2:
-                main.wait_event(ev_out[b])                         # results of step t-2 have left d_rew2[b]
-            obs, rew, term, trunc, info = env.step(d_idx2[b], fraction=True)   # public API call (graph replay)
-            d_rew2[b].copy_(rew, non_blocking=True)                # device staging (outputs are reused next step)
-            d_done2[b].copy_(env.done, non_blocking=True)
-            ev_c[b].record(main)
-            torch.cuda.set_stream(s_out)
-            s_out.wait_event(ev_c[b])
-            h_rew2[b].copy_(d_rew2[b], non_blocking=True)          # D2H: this step's results
-            h_done2[b].copy_(d_done2[b], non_blocking=True)
-            ev_out[b].record(s_out)
-            torch.cuda.set_stream(main)
-        main.wait_stream(s_out)
-        main.wait_stream(s_in)
-        t1.record(main)
+        t0.record()
+        for _ in range(reps):
+            pipe.run()
+        t1.record()
         torch.cuda.synchronize()
         return t0.elapsed_time(t1)
 
-    e2e_pipelined(max(W, 4))
+    e2e_pipelined(2)
     barrier()
-    ms_pipe = e2e_pipelined(K)
+    ms_pipe = e2e_pipelined(n_rep) * K / (n_rep * depth)      # scaled to K turns (n_rep * depth >= K turns were timed)
     barrier()
 
     # ---- end-to-end with the whole Box(198) batch copied to the host as well (a host-side policy) ----
     h_obs = torch.empty((E, 198), dtype=torch.float32).pin_memory()
 
     def e2e_obs_step():
-        e2e_step()
+        e2e_step_copies()
         h_obs.copy_(env.obs, non_blocking=True)
 
     k_obs = max(3, min(K, 20))
@@ -425,14 +403,17 @@ def run_cuda_arm(args):
             "roofline": {"bound": "hbm", "kernel": "k_step_full_v2<128,true> + its programmatic dependent k_step_deferred<256> (order-dependent doubles turns, overlaps the tail), timed together as one step", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01d_step_full_v2.json (per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 5 * E,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 6 * E,
                     "ms_per_step": total_e2e_max / K,
-                    "note": "VecNardeEnv.step(action_idx, fraction=True): pinned int32 action choices (u32 fractions of the legal list) H2D, reward f32 + done u8 D2H every step; Box(198) stays in HBM for the device-resident policy (VecNardeEnv.step_host wraps the same sequence in one CUDA graph; measured slower: 0.224 vs 0.197 ms)"},
+                    "note": "VecNardeEnv.step_host(fraction=True), zero-copy: every step the fused kernel reads that step's int32 action choices (u32 fractions of the legal list) from pinned host memory and writes reward f32 + done u8 + truncated u8 into pinned host memory (mapped page-locked buffers, PCIe traffic inside the kernel); Box(198) stays in HBM for the device-resident policy"},
+            "e2e_explicit_copies": {"value": world * E * K / (sum(ms_e2e_copies) * 1e-3), "unit": UNIT, "ms_per_step": sum(ms_e2e_copies) / K,
+                                    "note": "the same turn with cudaMemcpyAsync H2D / D2H around VecNardeEnv.step (rank 0's time)"},
             "e2e_pipelined": {"value": units / (ms_pipe_max * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe_max / K,
                               "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 5 * E,
-                              "note": "same copies and the same VecNardeEnv.step call every step, double-buffered on copy streams "
-                                      "(H2D of step t+1 / D2H of step t-1 overlap the kernels of step t); one device interval over all "
-                                      "K steps, no L2 flush (a step writes ~180 MB > 126 MB L2)"},
+                              "note": "VecNardeEnv.host_pipeline(depth=8, fraction=True): 8 turns per CUDA-graph replay, every turn with its "
+                                      "own H2D of pinned action choices and D2H of reward + done bits on copy streams (double-buffered on "
+                                      "the device; copies of neighbouring turns overlap the kernels); one device interval, no L2 flush "
+                                      "(a turn's outputs exceed the L2)"},
             "e2e_obs_to_host": {"value": world * E * k_obs / (sum(ms_e2e_obs) * 1e-3), "unit": UNIT, "steps": k_obs,
                                 "d2h_bytes_per_step": 5 * E + 792 * E, "ms_per_step": sum(ms_e2e_obs) / k_obs,
                                 "note": "same as e2e plus the full Box(198) float32 batch copied D2H every step (PCIe-bound; rank 0's time)"},

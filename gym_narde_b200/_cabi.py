@@ -102,8 +102,10 @@ def _ptr(t, dtype=None, name="tensor"):
         return None
     import torch
 
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
-        raise NardeCudaError("%s must be a CUDA tensor (no CPU fallback)" % name)
+    # device memory, or page-locked host memory (mapped into the device address space by CUDA's unified
+    # addressing: the kernels read / write it directly over PCIe -- the zero-copy I/O of VecNardeEnv.step_host)
+    if not isinstance(t, torch.Tensor) or not (t.is_cuda or t.is_pinned()):
+        raise NardeCudaError("%s must be a CUDA tensor or a pinned host tensor (no CPU fallback)" % name)
     if not t.is_contiguous():
         raise NardeCudaError("%s must be contiguous" % name)
     if dtype is not None and t.dtype != dtype:

@@ -159,6 +159,10 @@ struct BlockStep {
 
   // ---- phase 1: load, dice, decode, classify, item masks --------------------------------
   static NHD void ph_load(int tid, Sh& sh, bool valid, const State& s_in, int64_t i, const StepFullArgs& A) {
+    // the policy's choice may live in pinned HOST memory (zero-copy step_host): issue that load first and consume
+    // it last, so that the microseconds of PCIe latency overlap everything else this phase does
+    uint32_t policy_word = 0;
+    if (valid && A.action_idx) policy_word = (uint32_t)A.action_idx[i];
     for (int l = 0; l < 4; l++) sh.part[l][tid] = 0;
     sh.rowmask[tid] = 0;
     sh.dmask[tid] = 0;
@@ -184,7 +188,6 @@ struct BlockStep {
       d1 = die_from_word(rnd.x);
       d2 = die_from_word(rnd.y);
     }
-    sh.rnd[tid] = A.action_idx ? (uint32_t)A.action_idx[i] : rnd.z;  // the policy's choice, or the uniform word
     sh.d1[tid] = (uint8_t)d1;
     sh.d2[tid] = (uint8_t)d2;
     int player = s_in.turn();
@@ -235,6 +238,7 @@ struct BlockStep {
       sh.dmask[tid] = m;
       sh.part[1][tid] = (uint32_t)popc32(m);
     }
+    sh.rnd[tid] = A.action_idx ? policy_word : rnd.z;  // the policy's choice, or the uniform word of the turn
   }
 
   // ---- block exclusive scan of part[l] -> base[l], totals in ws[l][32] (3 phases) ---------

@@ -197,22 +197,25 @@ class VecNardeEnv:
     # -- host-facing step: host buffers in, host buffers out, one graph replay ---------------------------
     def host_io(self):
         """Pinned host buffers of step_host(): write `actions` (int32 [N]; indices, or u32 fractions with
-        fraction=True), read `reward` (float32 [N]), `done` (uint8 [N]: bit 0 terminated, bit 1 truncated)."""
+        fraction=True), read `reward` (float32 [N]), `done` and `truncated` (uint8 [N])."""
         t = self.torch
         if getattr(self, "_hio", None) is None:
             n = self.num_envs
             self._hio = {"actions": t.zeros(n, dtype=t.int32).pin_memory(),
                          "reward": t.zeros(n, dtype=t.float32).pin_memory(),
-                         "done": t.zeros(n, dtype=t.uint8).pin_memory()}
-            self._hio_done_dev = t.zeros(n, dtype=t.uint8, device=self.device)
+                         "done": t.zeros(n, dtype=t.uint8).pin_memory(),
+                         "truncated": t.zeros(n, dtype=t.uint8).pin_memory()}
             self._hio_graphs = {}
         return self._hio
 
     def step_host(self, fraction=False):
-        """One lock-step turn driven from the host (rules="full"): H2D copy of host_io()["actions"], the fused
-        step, D2H copies of reward and done bits into host_io() -- captured together as ONE CUDA graph (copy
-        nodes on pinned memory), so the copies start without stream round trips.  Asynchronous: synchronise the
-        stream (or an event) before reading the host buffers.  Box(198) stays in `self.obs` on the device."""
+        """One lock-step turn driven from the host (rules="full") with ZERO-COPY I/O: the fused step reads the
+        policy's choices straight from the pinned host buffer host_io()["actions"] and writes reward / done /
+        truncated straight into the pinned host buffers (page-locked memory is mapped into the device address
+        space; 4 B in and 6 B out per env cross PCIe inside the kernel, overlapped with its own compute), so there
+        are no separate copy operations and no stream round trips.  One CUDA-graph replay per turn.  Asynchronous:
+        synchronise the stream (or an event) before reading the host buffers; write the next actions only after
+        that.  Box(198) stays in `self.obs` on the device; self.reward / self.done are NOT updated by this call."""
         t = self.torch
         if self.rules != "full":
             raise ValueError("step_host needs rules='full'")
@@ -226,15 +229,23 @@ class VecNardeEnv:
             t.cuda.synchronize(self.device)
             g = t.cuda.CUDAGraph()
             with t.cuda.graph(g):
-                self.action_in.copy_(io["actions"], non_blocking=True)
                 _cabi.advance_counter(self._step_dev)
-                self._launch_full(self.action_in, None, flags)
-                t.bitwise_or(self.done, self.trunc << 1, out=self._hio_done_dev)
-                io["reward"].copy_(self.reward, non_blocking=True)
-                io["done"].copy_(self._hio_done_dev, non_blocking=True)
+                b, e = self._chunks[0]
+                _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, 0, action_idx=io["actions"],
+                                actions=self.actions if self.write_actions else None, counts=self.counts,
+                                dice_out=self.dice, chosen=self.chosen, obs198=self.obs, reward=io["reward"],
+                                done=io["done"], stats=self.stats, flags=flags,
+                                max_episode_steps=self.max_episode_steps, truncated=io["truncated"],
+                                workspace=self._workspaces[0], step_dev=self._step_dev)
             self._hio_graphs[bool(fraction)] = g
         g.replay()
         return io
+
+    def host_pipeline(self, depth=8, fraction=False):
+        """A window of `depth` lock-step turns driven from pinned host buffers as ONE CUDA graph with the copies
+        on their own streams: the H2D copy of turn t+1's actions and the D2H copy of turn t-1's results overlap
+        the kernels of turn t (see HostPipeline)."""
+        return HostPipeline(self, depth, fraction)
 
     def episode_stats(self):
         """Device-side counters as a dict (one D2H copy)."""
@@ -257,3 +268,74 @@ class VecNardeEnv:
 
     def close(self):
         pass
+
+
+class HostPipeline:
+    """`depth` consecutive turns of a VecNardeEnv(rules="full") with host-side inputs and outputs.
+
+    actions [depth, N] int32 (pinned): the policy's choices for the next `depth` turns (indices, or u32 fractions
+    of the legal list with fraction=True); reward [depth, N] float32 and done [depth, N] uint8 (bit 0 terminated,
+    bit 1 truncated) (pinned) receive every turn's results.  run() replays one captured graph: per turn an H2D
+    copy on a copy-in stream, the fused step on the compute stream, and the D2H copies on a copy-out stream,
+    double-buffered on the device, so copies and kernels of neighbouring turns overlap.  Asynchronous:
+    synchronise before reading the host buffers.  Box(198) of the last turn stays in env.obs."""
+
+    def __init__(self, env, depth=8, fraction=False):
+        t = env.torch
+        if env.rules != "full" or len(env._chunks) != 1:
+            raise ValueError("HostPipeline needs an unchunked rules='full' env")
+        self.env, self.depth, self.fraction = env, int(depth), bool(fraction)
+        n, dev = env.num_envs, env.device
+        self.actions = t.zeros((depth, n), dtype=t.int32).pin_memory()
+        self.reward = t.zeros((depth, n), dtype=t.float32).pin_memory()
+        self.done = t.zeros((depth, n), dtype=t.uint8).pin_memory()
+        self._d_act = [t.zeros(n, dtype=t.int32, device=dev) for _ in range(2)]
+        self._d_rew = [t.zeros(n, dtype=t.float32, device=dev) for _ in range(2)]
+        self._d_done = [t.zeros(n, dtype=t.uint8, device=dev) for _ in range(2)]
+        self._s_in, self._s_out = t.cuda.Stream(device=dev), t.cuda.Stream(device=dev)
+        self._graph = None
+
+    def _capture(self):
+        env, t, D = self.env, self.env.torch, self.depth
+        flags = (_cabi.REWARD_MOVER12 if env.reward_mode == "mover12" else 0) | (
+            _cabi.AUTORESET if env.autoreset else 0) | (_cabi.ACTION_FRACTION if self.fraction else 0)
+        env._step_dev.fill_(env.step_count)
+        t.cuda.synchronize(env.device)
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g):
+            main = t.cuda.current_stream(env.device)
+            ev_in = [t.cuda.Event() for _ in range(D)]
+            ev_c = [t.cuda.Event() for _ in range(D)]
+            ev_out = [t.cuda.Event() for _ in range(D)]
+            self._s_in.wait_stream(main)
+            self._s_out.wait_stream(main)
+            for k in range(D):
+                b = k & 1
+                with t.cuda.stream(self._s_in):
+                    if k >= 2:
+                        self._s_in.wait_event(ev_c[k - 2])          # turn k-2 has consumed this device buffer
+                    self._d_act[b].copy_(self.actions[k], non_blocking=True)
+                    ev_in[k].record(self._s_in)
+                main.wait_event(ev_in[k])
+                if k >= 2:
+                    main.wait_event(ev_out[k - 2])                  # turn k-2's results have left the staging buffers
+                _cabi.advance_counter(env._step_dev)
+                env._launch_full(self._d_act[b], None, flags)
+                self._d_rew[b].copy_(env.reward, non_blocking=True)
+                t.bitwise_or(env.done, env.trunc << 1, out=self._d_done[b])
+                ev_c[k].record(main)
+                with t.cuda.stream(self._s_out):
+                    self._s_out.wait_event(ev_c[k])
+                    self.reward[k].copy_(self._d_rew[b], non_blocking=True)
+                    self.done[k].copy_(self._d_done[b], non_blocking=True)
+                    ev_out[k].record(self._s_out)
+            main.wait_stream(self._s_in)
+            main.wait_stream(self._s_out)
+        return g
+
+    def run(self):
+        """Play the next `depth` turns (one graph replay)."""
+        if self._graph is None:
+            self._graph = self._capture()
+        self._graph.replay()
+        self.env.step_count += self.depth
