@@ -17,6 +17,7 @@ REWARD_MOVER12 = 1
 AUTORESET = 2
 ACTION_FRACTION = 32
 ENUMERATE_ONLY = 64
+PACK_RESULT = 128
 HALF_MOVES_ONLY = 4
 MAX_HALF_MOVES = 96
 NUM_STATS = 8

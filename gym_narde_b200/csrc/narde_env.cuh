@@ -12,6 +12,7 @@ enum : int {
   F_HALF_MOVES_ONLY = 4,
   F_ACTION_FRACTION = 32,
   F_ENUMERATE_ONLY = 64,
+  F_PACK_RESULT = 128,
   DONE_TERMINATED = 1,
   DONE_TRUNCATED = 2,
 };
@@ -223,6 +224,10 @@ NHD void complete_env(State& s, int64_t i, const StepFullArgs& A, int player, ui
     A.dice_out[2 * i + 1] = (uint8_t)d2;
   }
   if (A.chosen) A.chosen[i] = count ? act : ACT_EMPTY;
+  if (A.flags & F_PACK_RESULT) {  // one byte per env: bit 0 terminated, bit 1 truncated, bits 2-3 the reward (0, 1, 2)
+    if (A.done) A.done[i] = (uint8_t)(bits | ((int)rew << 2));
+    return;
+  }
   if (A.reward) A.reward[i] = rew;
   if (A.done) A.done[i] = (bits & DONE_TERMINATED) ? 1 : 0;
   if (A.truncated) A.truncated[i] = (bits & DONE_TRUNCATED) ? 1 : 0;

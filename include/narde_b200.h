@@ -46,6 +46,9 @@ extern "C" {
 #define NARDE_ACTION_FRACTION 32  /* narde_step_full: action_idx[i] is a u32 fraction f; plays action floor(f * count / 2^32) */
 #define NARDE_ENUMERATE_ONLY 64   /* narde_step_full: write actions / counts (/ chosen) only, leave every state untouched;
                                     done[i] then receives the overflow flag (count > cap) */
+#define NARDE_PACK_RESULT 128     /* narde_step_full (CTA-cooperative kernels): done[i] receives one packed byte per env -- bit 0
+                                    terminated, bit 1 truncated, bits 2-3 the reward (0, 1 or 2); reward[] and truncated[] are
+                                    not written.  One byte instead of six per env for a host-resident consumer. */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 
 /* done[i] = 1 when the episode terminated (a player bore off 15 checkers); truncated[i] = 1 when
