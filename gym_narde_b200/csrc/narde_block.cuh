@@ -75,7 +75,8 @@ struct BlockShared {
   uint32_t own[BLK], opp[BLK], ones[BLK];
   uint32_t nlo0[BLK], nlo1[BLK], nhi[BLK];
   uint32_t Ca[BLK], S[BLK], qhome[BLK];  // non-doubles: candidates of die a, die b; "q makes all home"
-  uint32_t rnd[BLK];
+  alignas(16) uint32_t rnd[BLK];         // the policy word of the turn (bulk-copied from the caller's buffer, or Philox)
+  alignas(8) unsigned long long rnd_bar; // mbarrier of that bulk copy
   uint64_t chosen[BLK];
   uint8_t a[BLK], b[BLK], kind[BLK], first[BLK], d1[BLK], d2[BLK], blk[BLK];
   uint32_t maxd[BLK];                    // doubles: deepest playable level seen
@@ -158,11 +159,13 @@ struct BlockStep {
   }
 
   // ---- phase 1: load, dice, decode, classify, item masks --------------------------------
-  static NHD void ph_load(int tid, Sh& sh, bool valid, const State& s_in, int64_t i, const StepFullArgs& A) {
+  // bulk_words: the CTA's action words are arriving in sh.rnd through a bulk asynchronous copy (see the kernel)
+  static NHD void ph_load(int tid, Sh& sh, bool valid, const State& s_in, int64_t i, const StepFullArgs& A,
+                          bool bulk_words = false) {
     // the policy's choice may live in pinned HOST memory (zero-copy step_host): issue that load first and consume
     // it last, so that the microseconds of PCIe latency overlap everything else this phase does
     uint32_t policy_word = 0;
-    if (valid && A.action_idx) policy_word = (uint32_t)A.action_idx[i];
+    if (valid && A.action_idx && !bulk_words) policy_word = (uint32_t)A.action_idx[i];
     for (int l = 0; l < 4; l++) sh.part[l][tid] = 0;
     sh.rowmask[tid] = 0;
     sh.dmask[tid] = 0;
@@ -238,7 +241,7 @@ struct BlockStep {
       sh.dmask[tid] = m;
       sh.part[1][tid] = (uint32_t)popc32(m);
     }
-    sh.rnd[tid] = A.action_idx ? policy_word : rnd.z;  // the policy's choice, or the uniform word of the turn
+    if (!bulk_words) sh.rnd[tid] = A.action_idx ? policy_word : rnd.z;  // the policy's choice, or the turn's uniform word
   }
 
   // ---- block exclusive scan of part[l] -> base[l], totals in ws[l][32] (3 phases) ---------

@@ -221,8 +221,25 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   const bool valid = i < n;
   State s;
   PHASE_MARK(0);
+  // The caller's action words of this CTA (BLK x 4 B, contiguous) come in as ONE bulk asynchronous copy into
+  // shared memory.  When the buffer is pinned host memory (zero-copy step_host) that is one PCIe read of 512 B
+  // per CTA instead of a 32-byte read per warp sector: the host step was bound by the NUMBER of small reads.
+  const int cta_rows = (int)((n - row0) < (int64_t)BLK ? (n - row0) : (int64_t)BLK);
+  const bool bulk_words = A.action_idx != nullptr && (cta_rows & 3) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(A.action_idx + row0) & 15u) == 0);
+  if (bulk_words && tid == 0) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sh.rnd_bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sh.rnd);
+    const uint32_t bytes = (uint32_t)cta_rows * 4u;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(A.action_idx + row0), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
   if (valid) s = ld_state(lo, hi, i);
-  BS::ph_load(tid, sh, valid, s, i, A);
+  BS::ph_load(tid, sh, valid, s, i, A, bulk_words);
   __syncthreads();
   PHASE_MARK(1);
   BS::ph_scan_serial(tid, sh, 0x3u);
@@ -255,6 +272,17 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_env_bases(tid, sh);
   __syncthreads();
   PHASE_MARK(6);
+  if (bulk_words) {  // the action words have landed (long ago): the wait makes the async-proxy writes visible
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&sh.rnd_bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra DONEW_%=;\n\t"
+        "bra WAITW_%=;\n\t"
+        "DONEW_%=:\n\t}" ::"r"(bar)
+        : "memory");
+  }
   BS::ph_emit(tid, sh, row0, A);
   __syncthreads();
   PHASE_MARK(7);

@@ -209,16 +209,18 @@ class VecNardeEnv:
             self._hio_graphs = {}
         return self._hio
 
-    def step_host(self, fraction=False, packed=False):
-        """One lock-step turn driven from the host (rules="full") with ZERO-COPY I/O: the fused step reads the
-        policy's choices straight from the pinned host buffer host_io()["actions"] and writes reward / done /
-        truncated straight into the pinned host buffers (page-locked memory is mapped into the device address
-        space; 4 B in and 6 B out per env cross PCIe inside the kernel, overlapped with its own compute), so there
-        are no separate copy operations and no stream round trips.  One CUDA-graph replay per turn.  Asynchronous:
+    def step_host(self, fraction=False, packed=False, actions=None):
+        """One lock-step turn driven from the host (rules="full"): one DMA brings the policy's choices from the
+        pinned host buffer host_io()["actions"] into HBM, and the fused step writes reward / done / truncated
+        STRAIGHT into the pinned host buffers (zero-copy: page-locked memory is mapped into the device address
+        space; 6 B per env leave as posted PCIe writes from inside the kernel, no device-to-host copies, no
+        stream round trips after the kernel).  One CUDA-graph replay per turn.  Asynchronous:
         synchronise the stream (or an event) before reading the host buffers; write the next actions only after
         that.  Box(198) stays in `self.obs` on the device; self.reward / self.done are NOT updated by this call.
         packed=True: one byte per env in host_io()["result"] instead (bit 0 terminated, bit 1 truncated, bits 2-3
-        the reward 0/1/2) -- a sixth of the PCIe write traffic."""
+        the reward 0/1/2) -- a sixth of the PCIe write traffic.
+        actions: another pinned int32 [N] host tensor to read this turn's choices from (e.g. a row of a ring the
+        policy fills ahead); one graph is cached per buffer (up to 32)."""
         t = self.torch
         if self.rules != "full":
             raise ValueError("step_host needs rules='full'")
@@ -227,23 +229,32 @@ class VecNardeEnv:
         flags = (_cabi.REWARD_MOVER12 if self.reward_mode == "mover12" else 0) | (
             _cabi.AUTORESET if self.autoreset else 0) | (_cabi.ACTION_FRACTION if fraction else 0) | (
             _cabi.PACK_RESULT if packed else 0)
-        g = self._hio_graphs.get((bool(fraction), bool(packed)))
+        src = io["actions"] if actions is None else actions
+        if not (src.is_pinned() and src.dtype == t.int32 and src.is_contiguous() and src.numel() == self.num_envs):
+            raise _cabi.NardeCudaError("step_host actions must be a pinned contiguous int32 [N] host tensor")
+        key = (src.data_ptr(), bool(fraction), bool(packed))
+        ent = self._hio_graphs.get(key)
+        g = ent[0] if ent is not None else None
+        if g is None and len(self._hio_graphs) >= 32:
+            raise _cabi.NardeCudaError("step_host: more than 32 distinct host action buffers")
         if g is None:
             self._step_dev.fill_(self.step_count - 1)
             t.cuda.synchronize(self.device)
             g = t.cuda.CUDAGraph()
             with t.cuda.graph(g):
-                # (measured alternatives: a bulk H2D copy node for the actions + zero-copy results 0.167 ms/step,
-                # copy nodes both ways 0.224, cudaMemcpyAsync around the step 0.201; all zero-copy 0.150)
+                # inputs: one DMA of the action choices into HBM (reads of host memory from inside the kernel stall its
+                # CTAs on PCIe round trips: 0.169 ms/step); outputs: written by the kernel straight into host memory
+                # (posted PCIe writes, +3 us per step)
+                self.action_in.copy_(src, non_blocking=True)
                 _cabi.advance_counter(self._step_dev)
-                _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, 0, action_idx=io["actions"],
+                _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, 0, action_idx=self.action_in,
                                 actions=self.actions if self.write_actions else None, counts=self.counts,
                                 dice_out=self.dice, chosen=self.chosen, obs198=self.obs,
                                 reward=None if packed else io["reward"], done=io["result"] if packed else io["done"],
                                 stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
                                 truncated=None if packed else io["truncated"],
                                 workspace=self._workspaces[0], step_dev=self._step_dev)
-            self._hio_graphs[(bool(fraction), bool(packed))] = g
+            self._hio_graphs[key] = (g, src)
         g.replay()
         return io
 
