@@ -415,11 +415,11 @@ def run_cuda_arm(args):
             "e2e_explicit_copies": {"value": world * E * K / (sum(ms_e2e_copies) * 1e-3), "unit": UNIT, "ms_per_step": sum(ms_e2e_copies) / K,
                                     "note": "the same turn with cudaMemcpyAsync H2D / D2H around VecNardeEnv.step (rank 0's time)"},
             "e2e_pipelined": {"value": units / (ms_pipe_max * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe_max / K,
-                              "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 5 * E,
+                              "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 6 * E,
                               "note": "VecNardeEnv.host_pipeline(depth=8, fraction=True): 8 turns per CUDA-graph replay, every turn with its "
-                                      "own H2D of pinned action choices and D2H of reward + done bits on copy streams (double-buffered on "
-                                      "the device; copies of neighbouring turns overlap the kernels); one device interval, no L2 flush "
-                                      "(a turn's outputs exceed the L2)"},
+                                      "own DMA of pinned action choices on a copy-in stream (double-buffered on the device) and its results "
+                                      "written by the kernel straight into pinned host rows; one device interval, no L2 flush (a turn's "
+                                      "outputs exceed the L2)"},
             "e2e_obs_to_host": {"value": world * E * k_obs / (sum(ms_e2e_obs) * 1e-3), "unit": UNIT, "steps": k_obs,
                                 "d2h_bytes_per_step": 5 * E + 792 * E, "ms_per_step": sum(ms_e2e_obs) / k_obs,
                                 "note": "same as e2e plus the full Box(198) float32 batch copied D2H every step (PCIe-bound; rank 0's time)"},

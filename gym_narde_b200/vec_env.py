@@ -291,11 +291,11 @@ class HostPipeline:
     """`depth` consecutive turns of a VecNardeEnv(rules="full") with host-side inputs and outputs.
 
     actions [depth, N] int32 (pinned): the policy's choices for the next `depth` turns (indices, or u32 fractions
-    of the legal list with fraction=True); reward [depth, N] float32 and done [depth, N] uint8 (bit 0 terminated,
-    bit 1 truncated) (pinned) receive every turn's results.  run() replays one captured graph: per turn an H2D
-    copy on a copy-in stream, the fused step on the compute stream, and the D2H copies on a copy-out stream,
-    double-buffered on the device, so copies and kernels of neighbouring turns overlap.  Asynchronous:
-    synchronise before reading the host buffers.  Box(198) of the last turn stays in env.obs."""
+    of the legal list with fraction=True); reward [depth, N] float32, done and truncated [depth, N] uint8 (pinned)
+    receive every turn's results.  run() replays one captured graph: per turn a DMA of that turn's actions on a
+    copy-in stream (double-buffered on the device, so it overlaps the previous turn's kernels) and the fused step,
+    which writes its results straight into the pinned host rows (zero-copy, no device-to-host copies).
+    Asynchronous: synchronise before reading the host buffers.  Box(198) of the last turn stays in env.obs."""
 
     def __init__(self, env, depth=8, fraction=False):
         t = env.torch
@@ -306,10 +306,9 @@ class HostPipeline:
         self.actions = t.zeros((depth, n), dtype=t.int32).pin_memory()
         self.reward = t.zeros((depth, n), dtype=t.float32).pin_memory()
         self.done = t.zeros((depth, n), dtype=t.uint8).pin_memory()
+        self.truncated = t.zeros((depth, n), dtype=t.uint8).pin_memory()
         self._d_act = [t.zeros(n, dtype=t.int32, device=dev) for _ in range(2)]
-        self._d_rew = [t.zeros(n, dtype=t.float32, device=dev) for _ in range(2)]
-        self._d_done = [t.zeros(n, dtype=t.uint8, device=dev) for _ in range(2)]
-        self._s_in, self._s_out = t.cuda.Stream(device=dev), t.cuda.Stream(device=dev)
+        self._s_in = t.cuda.Stream(device=dev)
         self._graph = None
 
     def _capture(self):
@@ -323,9 +322,7 @@ class HostPipeline:
             main = t.cuda.current_stream(env.device)
             ev_in = [t.cuda.Event() for _ in range(D)]
             ev_c = [t.cuda.Event() for _ in range(D)]
-            ev_out = [t.cuda.Event() for _ in range(D)]
             self._s_in.wait_stream(main)
-            self._s_out.wait_stream(main)
             for k in range(D):
                 b = k & 1
                 with t.cuda.stream(self._s_in):
@@ -334,20 +331,15 @@ class HostPipeline:
                     self._d_act[b].copy_(self.actions[k], non_blocking=True)
                     ev_in[k].record(self._s_in)
                 main.wait_event(ev_in[k])
-                if k >= 2:
-                    main.wait_event(ev_out[k - 2])                  # turn k-2's results have left the staging buffers
                 _cabi.advance_counter(env._step_dev)
-                env._launch_full(self._d_act[b], None, flags)
-                self._d_rew[b].copy_(env.reward, non_blocking=True)
-                t.bitwise_or(env.done, env.trunc << 1, out=self._d_done[b])
+                _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, action_idx=self._d_act[b],
+                                actions=env.actions if env.write_actions else None, counts=env.counts,
+                                dice_out=env.dice, chosen=env.chosen, obs198=env.obs, reward=self.reward[k],
+                                done=self.done[k], stats=env.stats, flags=flags,
+                                max_episode_steps=env.max_episode_steps, truncated=self.truncated[k],
+                                workspace=env._workspaces[0], step_dev=env._step_dev)
                 ev_c[k].record(main)
-                with t.cuda.stream(self._s_out):
-                    self._s_out.wait_event(ev_c[k])
-                    self.reward[k].copy_(self._d_rew[b], non_blocking=True)
-                    self.done[k].copy_(self._d_done[b], non_blocking=True)
-                    ev_out[k].record(self._s_out)
             main.wait_stream(self._s_in)
-            main.wait_stream(self._s_out)
         return g
 
     def run(self):
