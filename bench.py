@@ -269,8 +269,8 @@ def run_cuda_arm(args):
     io = env.host_io()                                       # pinned host result buffers of the host-facing step
 
     def e2e_step():
-        # public API call with HOST buffers: DMA of this step's action choices from pinned host memory, fused step,
-        # reward / done / truncated written by the kernel straight into pinned host memory
+        # public API call with HOST buffers, zero-copy: the fused step fetches this step's action choices from pinned
+        # host memory (one bulk copy per CTA) and writes reward / done / truncated into pinned host memory
         e2e_t[0] += 1
         env.step_host(fraction=True, actions=h_pool[e2e_t[0] % POOL])
 
@@ -411,7 +411,7 @@ def run_cuda_arm(args):
                          "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 6 * E,
                     "ms_per_step": total_e2e_max / K,
-                    "note": "VecNardeEnv.step_host(fraction=True, actions=pool row): one CUDA-graph replay per step = DMA of that step's int32 action choices (fresh u32 fractions of the legal list, pinned pool) into HBM + fused step whose reward f32 / done u8 / truncated u8 are written by the kernel straight into pinned host memory (zero-copy results); Box(198) stays in HBM for the device-resident policy"},
+                    "note": "VecNardeEnv.step_host(fraction=True, actions=pool row), zero-copy, one CUDA-graph replay per step: every CTA of the fused step bulk-copies its envs' int32 action choices (fresh u32 fractions of the legal list, pinned pool) from host memory into shared memory, and reward f32 / done u8 / truncated u8 are written by the kernel straight into pinned host memory; Box(198) stays in HBM for the device-resident policy"},
             "e2e_explicit_copies": {"value": world * E * K / (sum(ms_e2e_copies) * 1e-3), "unit": UNIT, "ms_per_step": sum(ms_e2e_copies) / K,
                                     "note": "the same turn with cudaMemcpyAsync H2D / D2H around VecNardeEnv.step (rank 0's time)"},
             "e2e_pipelined": {"value": units / (ms_pipe_max * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe_max / K,

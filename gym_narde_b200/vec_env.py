@@ -209,12 +209,14 @@ class VecNardeEnv:
             self._hio_graphs = {}
         return self._hio
 
-    def step_host(self, fraction=False, packed=False, actions=None):
-        """One lock-step turn driven from the host (rules="full"): one DMA brings the policy's choices from the
-        pinned host buffer host_io()["actions"] into HBM, and the fused step writes reward / done / truncated
-        STRAIGHT into the pinned host buffers (zero-copy: page-locked memory is mapped into the device address
-        space; 6 B per env leave as posted PCIe writes from inside the kernel, no device-to-host copies, no
-        stream round trips after the kernel).  One CUDA-graph replay per turn.  Asynchronous:
+    def step_host(self, fraction=False, packed=False, actions=None, dma_in=False):
+        """One lock-step turn driven from the host (rules="full") with ZERO-COPY I/O: every CTA of the fused step
+        fetches its envs' action words from the pinned host buffer with one bulk asynchronous copy (512 B over
+        PCIe into shared memory, overlapped with the state load and the dice), and reward / done / truncated are
+        written STRAIGHT into the pinned host buffers (page-locked memory is mapped into the device address space;
+        posted PCIe writes from inside the kernel).  No copy operations, no stream round trips: 0.120 ms/step at
+        131 072 envs against 0.110 for the device-resident step and 0.141 with a DMA in front (dma_in=True).
+        One CUDA-graph replay per turn.  Asynchronous:
         synchronise the stream (or an event) before reading the host buffers; write the next actions only after
         that.  Box(198) stays in `self.obs` on the device; self.reward / self.done are NOT updated by this call.
         packed=True: one byte per env in host_io()["result"] instead (bit 0 terminated, bit 1 truncated, bits 2-3
@@ -232,7 +234,7 @@ class VecNardeEnv:
         src = io["actions"] if actions is None else actions
         if not (src.is_pinned() and src.dtype == t.int32 and src.is_contiguous() and src.numel() == self.num_envs):
             raise _cabi.NardeCudaError("step_host actions must be a pinned contiguous int32 [N] host tensor")
-        key = (src.data_ptr(), bool(fraction), bool(packed))
+        key = (src.data_ptr(), bool(fraction), bool(packed), bool(dma_in))
         ent = self._hio_graphs.get(key)
         g = ent[0] if ent is not None else None
         if g is None and len(self._hio_graphs) >= 32:
@@ -242,12 +244,12 @@ class VecNardeEnv:
             t.cuda.synchronize(self.device)
             g = t.cuda.CUDAGraph()
             with t.cuda.graph(g):
-                # inputs: one DMA of the action choices into HBM (reads of host memory from inside the kernel stall its
-                # CTAs on PCIe round trips: 0.169 ms/step); outputs: written by the kernel straight into host memory
-                # (posted PCIe writes, +3 us per step)
-                self.action_in.copy_(src, non_blocking=True)
+                if dma_in:
+                    self.action_in.copy_(src, non_blocking=True)
                 _cabi.advance_counter(self._step_dev)
-                _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, 0, action_idx=self.action_in,
+                # dma_in=False: the kernel fetches its CTA's action words from the host buffer itself (one bulk
+                # asynchronous copy of 512 B per CTA into shared memory)
+                _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, 0, action_idx=self.action_in if dma_in else src,
                                 actions=self.actions if self.write_actions else None, counts=self.counts,
                                 dice_out=self.dice, chosen=self.chosen, obs198=self.obs,
                                 reward=None if packed else io["reward"], done=io["result"] if packed else io["done"],
