@@ -339,3 +339,45 @@ def check_obs198(backend, lo, hi):
     for i in range(lo.shape[0]):
         ref = O.obs198(u["board"][i], int(u["off_w"][i]), int(u["off_b"][i]), int(u["turn"][i]))
         assert (ref == got[i]).all(), i
+
+
+def check_turn_tree_vs_oracle(ops, lo, hi, dice):
+    """The turn manager's tree of partial turns (gym_narde_b200/narde_game_manager.py:TurnTree, built from batched
+    half-move / apply calls through `ops`) against the oracle's full-turn enumeration: the legal end-of-turn
+    positions are the same SET, every canonical sequence of the oracle can be played half-move by half-move,
+    and every half-move offered at the root starts some legal turn."""
+    from gym_narde_b200.narde_game_manager import TurnTree
+
+    u = S.unpack_states(lo, hi)
+    total = 0
+    for i in range(lo.shape[0]):
+        pl = int(u["turn"][i])
+        b = u["board"][i] if pl == 1 else S.rotate_board(u["board"][i])
+        ft = bool(u["first_w"][i] if pl == 1 else u["first_b"][i])
+        moff = int(u["off_w"][i] if pl == 1 else u["off_b"][i])
+        d1, d2 = int(dice[i, 0]), int(dice[i, 1])
+        ref, nref = O.turn_enumerate(b, moff, d1, d2, ft, cap=8192)
+        tree = TurnTree(lo[i].tobytes(), hi[i].tobytes(), (d1, d2), ft, ops=ops)
+        ends = set()
+        for nd in tree.ends:
+            v = S.unpack_states(np.frombuffer(nd.lo, np.uint8), np.frombuffer(nd.hi, np.uint8))
+            eb = v["board"][0] if pl == 1 else S.rotate_board(v["board"][0])
+            ends.add((tuple(int(x) for x in eb), int(v["off_w"][0] if pl == 1 else v["off_b"][0])))
+        if nref == 0:
+            assert tree.max_depth == 0 and tree.moves_from([tree.root]) == [], (i, dice[i], b.tolist())
+            continue
+        want = {(tuple(int(x) for x in r["after"]), int(r["after_off"])) for r in ref}
+        assert ends == want, (i, dice[i], b.tolist(), len(ends), len(want))
+        firsts = set()
+        for r in ref:                                   # each canonical sequence is playable step by step
+            nds = [tree.root]
+            for f, t in r["moves"]:
+                mv = (int(f), "off" if t in (-1, 255, "off") else int(t))
+                assert mv in tree.moves_from(nds), (i, dice[i], b.tolist(), r["moves"], mv)
+                nds = tree.children(nds, *mv)
+            assert any(nd in tree.ends for nd in nds) and tree.moves_from(nds) == []
+            firsts.add((int(r["moves"][0][0]), "off" if r["moves"][0][1] in (-1, 255, "off") else int(r["moves"][0][1])))
+        assert firsts <= set(tree.moves_from([tree.root]))
+        assert tree.launches <= 2 * (4 if d1 == d2 else 2)
+        total += nref
+    return total
