@@ -42,6 +42,8 @@ _SIGNATURES = {
     "narde_mlp_score": ([_vp, _i64, _vp, _vp, _vp, _vp], _int),
     "narde_mlp_forward_states": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp], _int),
     "narde_mlp_score_states": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], _int),
+    "narde_mlp_forward_move2": ([_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _int),
+    "narde_mlp_forward_move2_states": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_action_codes": ([_vp, _vp, _i64, _i32, _vp, _vp], _int),
     "narde_trajectory_append": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp], _int),
     "narde_afterstates": ([_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp], _int),

@@ -206,6 +206,8 @@ struct Params {
   const float* bias;     // 1088 floats
   float* q;              // [rows,576] fp32 (OUT_MAX = false)
   float* score;          // [rows] fp32 max_a Q (OUT_MAX = true)
+  const int32_t* move1;  // optional [rows]: move2_head mode, the selected first-move code of each row
+  const float* w2b_t;    // [576,576] fp32: row m = column 256 + m of move2_head.weight (the one-hot half, transposed)
 };
 
 // ---- operand tile of one slot from fp32 rows: coalesced float2 loads (4 rows = 16 loads in flight per
@@ -586,7 +588,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp(Params P_in) {
               float4 o = *reinterpret_cast<const float4*>(stage + rr * kStageStride + c4);
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
               const int64_t gr = row0 + quarter * 32 + rr;
-              if (gr < P.rows) *reinterpret_cast<float4*>(P.q + gr * kOut + jb.col0 + col) = o;
+              if (gr < P.rows) {
+                if (P.move1) {
+                  // move2_head(cat(features, onehot(move1))) = W[:, :256] features + W[:, 256 + move1] + b: the
+                  // one-hot half of the layer is a gathered row of its transposed weight block (L2-resident)
+                  int m1 = __ldg(P.move1 + gr);
+                  m1 = m1 < 0 ? 0 : (m1 >= kOut ? kOut - 1 : m1);
+                  const float4 w = __ldg(reinterpret_cast<const float4*>(P.w2b_t + (int64_t)m1 * kOut + jb.col0 + col));
+                  o.x += w.x; o.y += w.y; o.z += w.z; o.w += w.w;
+                }
+                *reinterpret_cast<float4*>(P.q + gr * kOut + jb.col0 + col) = o;
+              }
             }
             __syncwarp();
           }
@@ -1022,6 +1034,27 @@ int narde_mlp_forward(const float* x, int64_t rows, const void* wpack, const flo
   if (!aligned16(wpack) || !aligned16(q) || (((uintptr_t)x) & 7u) != 0) return -1;
   Params P = {x, nullptr, nullptr, rows, nullptr, (const uint8_t*)wpack, bias, q, nullptr};
   return launch_mlp<false, false>(P, stream);
+}
+
+// DecomposedDQN.forward(x, selected_move1) (train_deepq_pytorch.py:203-233): Q-values of the SECOND move.
+// wpack / bias: the feature network + the first 256 input columns of move2_head (same packing as above);
+// w2b_t: [576,576] fp32, row m = move2_head.weight[:, 256 + m]; move1: [rows] i32 codes in [0,576) (clamped).
+int narde_mlp_forward_move2(const float* x, int64_t rows, const int32_t* move1, const void* wpack, const float* bias,
+                            const float* w2b_t, float* q2, void* stream) {
+  if (rows == 0) return 0;
+  if (rows < 0 || !x || !move1 || !wpack || !bias || !w2b_t || !q2) return -1;
+  if (!aligned16(wpack) || !aligned16(w2b_t) || !aligned16(q2) || (((uintptr_t)x) & 7u) != 0) return -1;
+  Params P = {x, nullptr, nullptr, rows, nullptr, (const uint8_t*)wpack, bias, q2, nullptr, move1, w2b_t};
+  return launch_mlp<false, false>(P, stream);
+}
+
+int narde_mlp_forward_move2_states(const void* lo, const void* hi, int64_t rows, const int32_t* move1, const void* wpack,
+                                   const float* bias, const float* w2b_t, float* q2, void* stream) {
+  if (rows == 0) return 0;
+  if (rows < 0 || !lo || !hi || !move1 || !wpack || !bias || !w2b_t || !q2) return -1;
+  if (!aligned16(wpack) || !aligned16(w2b_t) || !aligned16(q2) || !aligned16(lo) || !aligned16(hi)) return -1;
+  Params P = {nullptr, (const uint4*)lo, (const uint4*)hi, rows, nullptr, (const uint8_t*)wpack, bias, q2, nullptr, move1, w2b_t};
+  return launch_mlp<true, false>(P, stream);
 }
 
 int narde_mlp_score(const float* x, int64_t rows, const void* wpack, const float* bias, float* score, void* stream) {

@@ -1,7 +1,9 @@
 """Afterstate-scoring MLP (BASELINE config 5): host side of narde_mlp_forward.
 
-Architecture = the reference's DecomposedDQN.forward(x) with state_size 198
-(train_deepq_pytorch.py:184-236): Linear(198,256)-ReLU-Linear(256,256)-ReLU-Linear(256,576).
+Architecture = the reference's DecomposedDQN with state_size 198 (train_deepq_pytorch.py:184-236):
+forward(x) = Linear(198,256)-ReLU-Linear(256,256)-ReLU-Linear(256,576) (move1_head), and
+forward(x, selected_move1) = move2_head(cat(features, onehot(move1))), Linear(832,576), whose one-hot half is a
+column gather added in the same kernel's epilogue.
 The CUDA kernel (csrc/narde_mlp.cu) runs bf16 operands / fp32 accumulation on tcgen05 tensor cores;
 weights are re-packed once on the host into the shared-memory operand layout it streams.
 """
@@ -56,20 +58,47 @@ class AfterstateMLP:
     forward(x)            x float32 [K,198]            -> q float32 [K,576]   (move1 Q-values)
     score(x)              x float32 [K,198]            -> max_a q[:, a]  float32 [K]
     forward_states(lo,hi) packed states [K,16] uint8 x2 -> q   (Box(198) encoded inside the kernel)
-    score_states(lo,hi)   packed states                -> max_a q[:, a]       (the afterstate score)"""
+    score_states(lo,hi)   packed states                -> max_a q[:, a]       (the afterstate score)
+    forward(x, selected_move1) / forward_states(lo, hi, selected_move1)  -> move2 Q-values [K,576] (needs the
+                          move2_head weights: from_module(..., move2_head) or set_move2_head(w, b))"""
 
-    def __init__(self, w1, b1, w2, b2, w3, b3):
+    def __init__(self, w1, b1, w2, b2, w3, b3, w_move2=None, b_move2=None):
         torch = _cabi.require_cuda()
         lib = _cabi.load()
         self.torch, self.lib = torch, lib
-        self.wpack, self.bias = pack_weights(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), w3.cuda(), b3.cuda())
-        self.wpack2, _ = pack_weights(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), w3.cuda(), b3.cuda(), two_sm=True)
+        self._trunk = (w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+        self.wpack, self.bias = pack_weights(*self._trunk, w3.cuda(), b3.cuda())
+        self.wpack2, _ = pack_weights(*self._trunk, w3.cuda(), b3.cuda(), two_sm=True)
+        self.wpack_m2 = self.bias_m2 = self.w2b_t = None
+        if w_move2 is not None:
+            self.set_move2_head(w_move2, b_move2)
+
+    def set_move2_head(self, w, b):
+        """move2_head = Linear(256 + 576, 576) (train_deepq_pytorch.py:200-201): its first 256 input columns become
+        the third GEMM of the chain, the other 576 (one per first-move code) a transposed fp32 gather table."""
+        if tuple(w.shape) != (OUT, HID + OUT) or tuple(b.shape) != (OUT,):
+            raise ValueError("move2_head must be Linear(%d, %d)" % (HID + OUT, OUT))
+        w = w.cuda().float()
+        self.wpack_m2, self.bias_m2 = pack_weights(*self._trunk, w[:, :HID].contiguous(), b.cuda())
+        self.w2b_t = w[:, HID:].t().contiguous()
 
     @classmethod
-    def from_module(cls, feature_network, move1_head):
-        """feature_network = nn.Sequential(Linear, ReLU, Linear, ReLU), move1_head = Linear (reference names)."""
+    def from_module(cls, feature_network, move1_head, move2_head=None):
+        """feature_network = nn.Sequential(Linear, ReLU, Linear, ReLU), move1_head / move2_head = Linear (the
+        reference's attribute names)."""
         l1, l2 = feature_network[0], feature_network[2]
-        return cls(l1.weight.data, l1.bias.data, l2.weight.data, l2.bias.data, move1_head.weight.data, move1_head.bias.data)
+        m2 = (move2_head.weight.data, move2_head.bias.data) if move2_head is not None else (None, None)
+        return cls(l1.weight.data, l1.bias.data, l2.weight.data, l2.bias.data, move1_head.weight.data, move1_head.bias.data,
+                   *m2)
+
+    def _move1(self, selected_move1, k):
+        t = self.torch
+        if self.wpack_m2 is None:
+            raise _cabi.NardeCudaError("move2_head weights were not given (set_move2_head)")
+        m = selected_move1
+        if not (m.is_cuda and m.dim() == 1 and m.shape[0] == k):
+            raise _cabi.NardeCudaError("selected_move1 must be a CUDA tensor [K] of first-move codes")
+        return m.to(t.int32).contiguous()
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -92,12 +121,21 @@ class AfterstateMLP:
         if rc != 0:
             raise _cabi.NardeCudaError("%s failed: %d" % (what, rc))
 
-    def forward(self, x, out=None):
+    def forward(self, x, selected_move1=None, out=None):
+        """DecomposedDQN.forward (train_deepq_pytorch.py:203-233): move1 Q-values, or, given selected_move1
+        (int tensor [K], codes in [0,576)), the move2 Q-values."""
         t = self.torch
         self._check_x(x)
         k = x.shape[0]
         if out is None:
             out = t.empty((k, OUT), dtype=t.float32, device=x.device)
+        if selected_move1 is not None:
+            m = self._move1(selected_move1, k)
+            self._run(self.lib.narde_mlp_forward_move2,
+                      (C.c_void_p(x.data_ptr()), k, C.c_void_p(m.data_ptr()), C.c_void_p(self.wpack_m2.data_ptr()),
+                       C.c_void_p(self.bias_m2.data_ptr()), C.c_void_p(self.w2b_t.data_ptr()), C.c_void_p(out.data_ptr())),
+                      "narde_mlp_forward_move2")
+            return out
         self._run(self.lib.narde_mlp_forward, (C.c_void_p(x.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
                                                C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_forward")
         return out
@@ -112,12 +150,19 @@ class AfterstateMLP:
                                              C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_score")
         return out
 
-    def forward_states(self, lo, hi, out=None):
+    def forward_states(self, lo, hi, selected_move1=None, out=None):
         t = self.torch
         self._check_states(lo, hi)
         k = lo.shape[0]
         if out is None:
             out = t.empty((k, OUT), dtype=t.float32, device=lo.device)
+        if selected_move1 is not None:
+            m = self._move1(selected_move1, k)
+            self._run(self.lib.narde_mlp_forward_move2_states,
+                      (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k, C.c_void_p(m.data_ptr()),
+                       C.c_void_p(self.wpack_m2.data_ptr()), C.c_void_p(self.bias_m2.data_ptr()),
+                       C.c_void_p(self.w2b_t.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_forward_move2_states")
+            return out
         self._run(self.lib.narde_mlp_forward_states,
                   (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k, C.c_void_p(self.wpack.data_ptr()),
                    C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_forward_states")

@@ -160,6 +160,17 @@ int narde_mlp_score_states(const void *lo, const void *hi, int64_t rows, const i
 /* rows_dev (may be NULL): device-resident row count, min(*rows_dev, rows) rows are scored -- lets the
  * afterstate generator and the scorer run back to back without a host synchronisation. */
 
+/* DecomposedDQN.forward(x, selected_move1) (train_deepq_pytorch.py:203-233): the Q-values of the SECOND move,
+ * move2_head(cat(features, onehot(move1))).  The one-hot half of that layer is a column gather, so the kernel is
+ * the same three-layer GEMM chain with wpack / bias built from the feature network and the first 256 input columns
+ * of move2_head (same packing), plus w2b_t [576,576] f32 with row m = move2_head.weight[:, 256 + m], added to the
+ * output row of every sample with move1 == m.  move1: [rows] i32 codes in [0,576) (clamped to that range). */
+int narde_mlp_forward_move2(const float *x, int64_t rows, const int32_t *move1, const void *wpack,
+                            const float *bias, const float *w2b_t, float *q2, void *stream);
+int narde_mlp_forward_move2_states(const void *lo, const void *hi, int64_t rows, const int32_t *move1,
+                                   const void *wpack, const float *bias, const float *w2b_t, float *q2,
+                                   void *stream);
+
 /* The afterstate of every stored legal turn action (the batched form of the enumeration loop of
  * DQNAgent.act, train_deepq_pytorch.py:430-507): row offsets[i] + k of (as_lo, as_hi) = state of
  * environment i after actions[i*cap + k] and the end-of-turn bookkeeping of narde_apply_actions, for

@@ -121,3 +121,46 @@ def test_mlp_cta_group2_scorer_is_bit_identical():
         b = mlp.score_states_2sm(lo, hi)
         torch.cuda.synchronize()
         assert torch.equal(a, b), rows
+
+
+def test_mlp_move2_head_matches_fp32_reference():
+    """DecomposedDQN.forward(x, selected_move1) (train_deepq_pytorch.py:203-233): the move2 Q-values, with the one-hot
+    half of move2_head applied as a gathered weight column in the kernel's epilogue.  Same tolerance as forward(x);
+    the fp32 observation rows and the packed states give bit-identical results."""
+    import torch
+    import torch.nn as nn
+    from gym_narde_b200 import VecNardeEnv
+    from gym_narde_b200.mlp import AfterstateMLP
+    fn, head = _reference_net()
+    move2_head = nn.Linear(256 + 576, 576).cuda()      # drawn after move1_head from the same generator, as in the reference
+    mlp = AfterstateMLP.from_module(fn, head, move2_head)
+    env = VecNardeEnv(3000, seed=5)
+    env.reset()
+    for _ in range(50):
+        env.step()
+    obs = env.observe().clone()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for rows in (3000, 1, 127, 129, 1000):
+        x = obs[:rows].contiguous()
+        m1 = torch.randint(0, 576, (rows,), device="cuda", generator=g)
+        q2 = mlp.forward(x, m1)
+        with torch.no_grad():
+            feats = fn(x)
+            onehot = torch.zeros(rows, 576, device="cuda").scatter_(1, m1.unsqueeze(1), 1)
+            ref = move2_head(torch.cat((feats, onehot), dim=1))
+        err = (q2 - ref).abs().max().item()
+        assert err < ABS_TOL, (rows, err)
+        assert torch.equal(q2, mlp.forward_states(env.lo[:rows].contiguous(), env.hi[:rows].contiguous(), m1)), rows
+        # the move1 path is untouched by the extra mode
+        with torch.no_grad():
+            assert (mlp.forward(x) - head(feats)).abs().max().item() < ABS_TOL
+    # edge codes 0 and 575, int32 and int64 index tensors
+    x = obs[:256].contiguous()
+    for code in (0, 575):
+        m1 = torch.full((256,), code, device="cuda", dtype=torch.int32)
+        with torch.no_grad():
+            ref = fn(x) @ move2_head.weight[:, :256].t() + move2_head.weight[:, 256 + code] + move2_head.bias
+        assert (mlp.forward(x, m1) - ref).abs().max().item() < ABS_TOL
+    mlp_no = AfterstateMLP.from_module(fn, head)
+    with pytest.raises(Exception):
+        mlp_no.forward(x, m1)
