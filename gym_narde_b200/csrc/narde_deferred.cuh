@@ -25,7 +25,6 @@ namespace narde {
 // 549 words instead of 24^4 / 32, and a CTA needs ~16 KB of shared memory.
 constexpr int kDefCap = 2600;                     // multisets per expandable level (<= C(26,3))
 constexpr int kDefBmWords = (17550 + 31) / 32;    // 549
-constexpr int kDefEmit = 256;                     // ranks materialised per emit pass
 
 NHD uint32_t sm_fetch_add(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -75,8 +74,6 @@ struct DeferredSharedT {
   uint64_t chosen;
   uint32_t part[BLK], base[BLK], part2[33];
   uint32_t bm[kDefBmWords];
-  uint32_t ecode[kDefEmit], ebest[kDefEmit];   // emit pass: multisets whose descending order is illegal
-  uint32_t efail[kDefEmit], n_fail;
   uint16_t a[kDefCap], b[kDefCap];             // level lists (levels 1..3: codes of <= 15 bits)
 };
 
@@ -183,7 +180,6 @@ struct DeferredStep {
     sh.count = 0;
     sh.idx = 0;
     sh.chosen = ACT_EMPTY;
-    sh.n_fail = 0;
   }
   // ---- clear the bitmap of `level` -----------------------------------------------------------
   static NHD void ph_clear(int tid, Sh& sh, int level) {
@@ -332,8 +328,7 @@ struct DeferredStep {
   }
   // ---- materialise the first `cap` actions of the canonical list and the chosen one -------------
   // Representative ordering = the lexicographically first legal ordering of the (descending) sources,
-  // higher sources tried first.  All <= 4! orderings of a multiset are tested in parallel, one
-  // (rank, permutation) item per thread, and the smallest legal permutation index wins.
+  // higher sources tried first: highest-source-first itself in the common case, else a depth-first search.
   static NHD uint32_t emit_total(const Sh& sh, const StepFullArgs& A) {  // ranks to materialise (+1: the chosen one)
     uint32_t n = sh.count;
     uint32_t lim = A.actions ? (n < (uint32_t)A.cap ? n : (uint32_t)A.cap) : 0u;
@@ -366,69 +361,27 @@ struct DeferredStep {
     if (k < lim) slice[k] = act;
     if (emit_rank(sh, A, k) == sh.idx) sh.chosen = act;
   }
-  // pass over emit slots [k0, k0 + kDefEmit): rank -> multiset; descending order legal (the common
-  // case) -> written at once, else queued for the parallel ordering search
-  static NHD void ph_emit_select(int tid, Sh& sh, int64_t i, const StepFullArgs& A, uint32_t k0) {
-    uint32_t total = emit_total(sh, A);
+  // the lexicographically first legal ordering of a multiset that cannot be played highest-source-first
+  // (depth-first over the <= 4! orderings, higher sources tried first; a few nodes in practice)
+  static NHD_NOINLINE void first_legal_order(const Sh& sh, const int* src, int j, int* order) {
+    if (!dbl_order_search(base_pos(sh), src, j, sh.d, sh.H, order))
+      for (int t = 0; t < j; t++) order[t] = src[t];  // unreachable: the multiset was reached by a legal sequence
+  }
+  // one thread per emitted rank: rank -> multiset -> representative ordering -> store
+  static NHD void ph_emit(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
+    const uint32_t total = emit_total(sh, A);
     const int j = (int)sh.depth;
-    for (uint32_t k = k0 + (uint32_t)tid; k < total && k < k0 + (uint32_t)kDefEmit; k += BLK) {
+    for (uint32_t k = (uint32_t)tid; k < total; k += BLK) {
       uint32_t code = select_code(sh, emit_rank(sh, A, k));
-      int src[4];
+      int src[4], order[4];
       unpack(code, j, src);
       if (sequence_legal(sh, src, j)) {
-        emit_store(sh, i, A, k, src, j);
+          emit_store(sh, i, A, k, src, j);
       } else {
-        uint32_t f = sm_fetch_add(&sh.n_fail, 1u);
-        sh.efail[f] = k;
-        sh.ecode[f] = code;
-        sh.ebest[f] = 0xFFFFFFFFu;
+          first_legal_order(sh, src, j, order);
+        emit_store(sh, i, A, k, order, j);
       }
     }
-  }
-  static NHD_NOINLINE void perm_order(const int* src, int j, uint32_t perm, int* order) {  // perm-th ordering, lexicographic
-    uint32_t used = 0, f = 1;
-    for (int k = 2; k < j; k++) f *= (uint32_t)k;  // (j-1)!
-    for (int pos = 0; pos < j; pos++) {
-      uint32_t pick = perm / f;
-      perm -= pick * f;
-      if (j - 1 - pos > 0) f /= (uint32_t)(j - 1 - pos);
-      int c = 0;
-      for (int e = 0; e < j; e++) {
-        if ((used >> e) & 1u) continue;
-        if ((uint32_t)c == pick) {
-          order[pos] = src[e];
-          used |= 1u << e;
-          break;
-        }
-        c++;
-      }
-    }
-  }
-  static NHD void ph_emit_test(int tid, Sh& sh) {
-    const int j = (int)sh.depth;
-    uint32_t nperm = 1;
-    for (int k = 2; k <= j; k++) nperm *= (uint32_t)k;
-    for (uint32_t item = (uint32_t)tid; item < sh.n_fail * nperm; item += BLK) {
-      uint32_t f = item / nperm, perm = item - f * nperm;
-      int src[4], order[4];
-      unpack(sh.ecode[f], j, src);
-      perm_order(src, j, perm, order);
-      if (sequence_legal(sh, order, j)) sm_min(&sh.ebest[f], perm);
-    }
-  }
-  static NHD void ph_emit_write(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {
-    const int j = (int)sh.depth;
-    for (uint32_t f = (uint32_t)tid; f < sh.n_fail; f += BLK) {
-      int src[4], order[4];
-      unpack(sh.ecode[f], j, src);
-      uint32_t perm = sh.ebest[f];
-      if (perm == 0xFFFFFFFFu) perm = 0;  // unreachable: the multiset was reached by a legal sequence
-      perm_order(src, j, perm, order);
-      emit_store(sh, i, A, sh.efail[f], order, j);
-    }
-  }
-  static NHD void ph_emit_reset(int tid, Sh& sh) {
-    if (tid == 0) sh.n_fail = 0;
   }
 };
 

@@ -371,18 +371,7 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
     DS::ph_bm_scan3(tid, sh, i, A);
     __syncthreads();
     DMARK(3);
-    for (uint32_t k0 = 0; k0 < DS::emit_total(sh, A); k0 += kDefEmit) {  // passes of kDefEmit ranks (one for cap <= 255)
-      DS::ph_emit_select(tid, sh, i, A, k0);
-      __syncthreads();
-      if (sh.n_fail) {  // some multisets cannot be played highest-source-first: search their orderings
-        DS::ph_emit_test(tid, sh);
-        __syncthreads();
-        DS::ph_emit_write(tid, sh, i, A);
-        __syncthreads();
-        DS::ph_emit_reset(tid, sh);
-        __syncthreads();
-      }
-    }
+    DS::ph_emit(tid, sh, i, A);
     __syncthreads();
     DMARK(4);
     if (tid == 0) {

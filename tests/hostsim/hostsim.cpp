@@ -203,14 +203,7 @@ static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float*
     for (int t = 0; t < BLK; t++) DS::ph_bm_scan1(t, sh);
     for (int t = 0; t < BLK; t++) DS::ph_bm_scan2(t, sh);
     for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_scan3(t, sh, i, A);
-    for (uint32_t k0 = 0; k0 < DS::emit_total(sh, A); k0 += kDefEmit) {
-      for (int t = BLK - 1; t >= 0; t--) DS::ph_emit_select(t, sh, i, A, k0);
-      if (sh.n_fail) {
-        for (int t = 0; t < BLK; t++) DS::ph_emit_test(t, sh);
-        for (int t = BLK - 1; t >= 0; t--) DS::ph_emit_write(t, sh, i, A);
-        for (int t = 0; t < BLK; t++) DS::ph_emit_reset(t, sh);
-      }
-    }
+    for (int t = BLK - 1; t >= 0; t--) DS::ph_emit(t, sh, i, A);
     StepFullLocal L;
     State st = sh.st;
     complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
