@@ -391,7 +391,7 @@ def run_cuda_arm(args):
         kernel_ms = total_ms / K                             # rank-0 kernel: one launch per step
         achieved = E * bytes_per_unit / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01d_step_full_v2.json")   # ncu --set full of the same kernel/workload
+        tp = os.path.join(ROOT, "profiles", "r01e_step_full_v2.json")   # ncu --set full of the same kernel/workload
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp))["launches"][0].get("dram_bytes_per_launch")
@@ -407,7 +407,7 @@ def run_cuda_arm(args):
                        "l2": "flushed between timed steps (256 MiB fill, untimed)" if flush is not None else "not flushed",
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "roofline": {"bound": "hbm", "kernel": "k_step_full_v2<128,true> + its programmatic dependent k_step_deferred<256> (order-dependent doubles turns, overlaps the tail), timed together as one step", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01d_step_full_v2.json (per launch)", "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01e_step_full_v2.json (per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 6 * E,
                     "ms_per_step": total_e2e_max / K,
@@ -423,7 +423,9 @@ def run_cuda_arm(args):
             "e2e_obs_to_host": {"value": world * E * k_obs / (sum(ms_e2e_obs) * 1e-3), "unit": UNIT, "steps": k_obs,
                                 "d2h_bytes_per_step": 5 * E + 792 * E, "ms_per_step": sum(ms_e2e_obs) / k_obs,
                                 "note": "same as e2e plus the full Box(198) float32 batch copied D2H every step (PCIe-bound; rank 0's time)"},
-            "gpu_launches": K * ((3 if env.use_graph else 2) * len(env._chunks)),   # k_advance_counter (graph replay) + k_step_full_v2 + k_step_deferred per step "wall_ms": wall_ms, "clocks": clocks,
+            # k_advance_counter (graph replay) + k_step_full_v2 + k_step_deferred per step
+            "gpu_launches": K * ((3 if env.use_graph else 2) * len(env._chunks)),
+            "wall_ms": wall_ms, "clocks": clocks,
             "config2_4096_envs": {"value": 4096 * len(ms_small) / (sum(ms_small) * 1e-3), "unit": UNIT,
                                   "ms_per_step": sum(ms_small) / len(ms_small)},
             "episode_stats": {k: int(v) for k, v in zip(_cabi.STAT_NAMES, st_all.sum(0).tolist())},
