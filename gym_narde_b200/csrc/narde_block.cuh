@@ -23,6 +23,10 @@ namespace narde {
 
 enum : uint8_t { K_NONE = 0, K_DONE = 1, K_ND = 2, K_D = 3 };
 
+#if defined(NARDE_HOSTSIM_HOOKS) && !defined(__CUDA_ARCH__)
+extern int g_hs_force_slow;  // defined by the test-only host harness (tests/hostsim/hostsim.cpp)
+#endif
+
 NHD void sm_add(uint32_t* p, uint32_t v) {
 #if defined(__CUDA_ARCH__)
   atomicAdd(p, v);
@@ -90,7 +94,7 @@ struct BlockShared {
   uint32_t d2base[kL1Cap + 1];
   uint8_t l1env[kL1Cap], l1src[kL1Cap];
   uint16_t itab[BLK * 24];               // ND work items in canonical order: env << 5 | source point
-  uint32_t n_l1;
+  uint32_t n_l1, n_l2;                   // level-1 / level-2 doubles items of the CTA
   // scan scratch (4 lanes)
   uint32_t part[4][BLK], base[4][BLK], ws[4][36];
 };
@@ -604,8 +608,24 @@ struct BlockStep {
   // level-2 doubles items share the item table with the pair rows when both fit (they practically always do;
   // otherwise the phases fall back to the searching iterator)
   static NHD bool l2_in_table(const Sh& sh, uint32_t n_l2) {
+#if defined(NARDE_HOSTSIM_HOOKS) && !defined(__CUDA_ARCH__)
+    if (g_hs_force_slow & 1) return false;  // test-only (tests/hostsim): exercise the searching iterator
+#endif
     return sh.n_l1 > 0 && sh.n_l1 < 1024u && sh.ibase[BLK] + n_l2 <= (uint32_t)(BLK * 24);
   }
+  // Per level-2 item, 16 bits: its action count (written by ph_count), then its offset inside the env's list
+  // (ph_env_bases).  The array lives on top of d2mask / d2base, which nobody reads once the items are in the table.
+  // With it the emit phase deals the items round-robin (a heavy env's items spread over all warps instead of
+  // sitting in one thread's contiguous chunk) and skips, without recounting, every item that lies beyond the
+  // stored capacity and does not hold the chosen action.
+  static constexpr uint32_t kL2OffCap = (uint32_t)((sizeof(uint32_t) * (2 * Sh::kL1Cap + 1)) / sizeof(uint16_t));
+  static NHD bool l2_fast(const Sh& sh) {
+#if defined(NARDE_HOSTSIM_HOOKS) && !defined(__CUDA_ARCH__)
+    if (g_hs_force_slow & 2) return false;  // test-only (tests/hostsim): exercise the recounting emit
+#endif
+    return l2_in_table(sh, sh.n_l2) && sh.n_l2 <= kL2OffCap;
+  }
+  static NHD uint16_t* l2_off(Sh& sh) { return reinterpret_cast<uint16_t*>(sh.d2mask); }
   struct L2Iter {  // items (level-1 item j, second source p) of [j0, j1): from the table, else by searching
     bool tab;
     int jj, j1;
@@ -613,7 +633,7 @@ struct BlockStep {
     ItemIter<uint32_t> it;
     NHD void init(const Sh& sh, int j0, int j1_) {
       const int n1 = (int)sh.n_l1;
-      tab = l2_in_table(sh, sh.d2base[n1]);
+      tab = l2_in_table(sh, sh.n_l2);
       jj = j0;
       j1 = j1_;
       t0 = sh.ibase[BLK];
@@ -649,7 +669,10 @@ struct BlockStep {
       }
       r += (uint32_t)popc32(m);
     }
-    if (tid == 0) sh.d2base[sh.n_l1] = sh.ws[1][32];
+    if (tid == 0) {
+      sh.d2base[sh.n_l1] = sh.ws[1][32];
+      sh.n_l2 = sh.ws[1][32];
+    }
   }
   // ---- phase 5: counts per item -> chunk sums (lanes 0/1) and per-env totals ----------------
   static NHD void ph_count(int tid, Sh& sh) {
@@ -675,10 +698,12 @@ struct BlockStep {
     int n1 = (int)sh.n_l1;
     sum = 0;
     if (n1 > 0) {
-      chunk((int)sh.d2base[n1], tid, &j0, &j1);
+      chunk((int)sh.n_l2, tid, &j0, &j1);
+      const bool fast = l2_fast(sh);
+      uint16_t* cnt16 = l2_off(sh);
       L2Iter it2;
       it2.init(sh, j0, j1);
-      int j;
+      int j, t = j0;
       while (it2.next(sh, &j, &p)) {
         e = sh.l1env[j];
         int s1 = sh.l1src[j];
@@ -692,10 +717,20 @@ struct BlockStep {
           if (c == 0) sm_max(&sh.maxd[e], deep);
         }
         if (c) sm_add(&sh.etotal[e], c);
+        if (fast) cnt16[t] = (uint16_t)c;  // <= 24 * 24 leaves per item
+        t++;
         sum += c;
       }
     }
     sh.part[1][tid] = sum;
+  }
+  // the same count again, without side effects (emit phase of the rare CTA whose items did not fit the tables)
+  static NHD_NOINLINE uint32_t recount_item(const Sh& sh, int e, int s1, int p) {
+    if (!DEFER && sh.blk[e]) {
+      if constexpr (!DEFER) return dbl_count2_exact(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p);
+    }
+    uint32_t deep = 0, taint = 0;
+    return dbl_count2(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p, &deep, sh.blk[e] != 0, &taint);
   }
   // per-env totals into scan lanes 2 (ND) / 3 (doubles): list starts in item space
   static NHD void ph_env_totals(int tid, Sh& sh) {
@@ -710,6 +745,32 @@ struct BlockStep {
   }
   static NHD void ph_env_bases(int tid, Sh& sh) {
     sh.ebase[tid] = sh.kind[tid] == K_ND ? sh.base[2][tid] : sh.base[3][tid];
+    {  // pair rows: the row's offset inside its env's list goes into the free top byte of its mask (a non-doubles
+       // turn has < 15 x 17 legal pairs), so the emit phase can deal the rows round-robin
+      int j0, j1;
+      chunk((int)sh.ibase[BLK], tid, &j0, &j1);
+      uint32_t G = sh.base[0][tid];
+      for (int jj = j0; jj < j1; jj++) {
+        const uint32_t v = sh.itab[jj];
+        const int e = (int)(v >> 5), p = (int)(v & 31u);
+        const uint32_t nd = sh.pres[e * 24 + p];
+        sh.pres[e * 24 + p] = nd | ((G - sh.base[2][e]) << 24);
+        G += (uint32_t)popc32(nd);
+      }
+    }
+    if (sh.n_l1 > 0 && l2_fast(sh)) {  // level-2 item counts -> offsets inside the env's list (lane 3 = doubles env starts)
+      int j0, j1;
+      chunk((int)sh.n_l2, tid, &j0, &j1);
+      uint16_t* off16 = l2_off(sh);
+      const uint32_t t0 = sh.ibase[BLK];
+      uint32_t G = sh.base[1][tid];
+      for (int t = j0; t < j1; t++) {
+        const int e = sh.l1env[sh.itab[t0 + (uint32_t)t] >> 5];
+        const uint32_t c = off16[t];
+        off16[t] = (uint16_t)(G - sh.base[3][e]);
+        G += c;
+      }
+    }
   }
   static NHD uint32_t pick_index(const Sh& sh, int e, int64_t i, uint32_t count, const StepFullArgs& A) {
     return pick_from_word(A, sh.rnd[e], count);
@@ -717,16 +778,16 @@ struct BlockStep {
   // ---- phase 7: write the action lists in canonical order, capture the chosen action ------
   static NHD void ph_emit(int tid, Sh& sh, int64_t row0, const StepFullArgs& A) {
     int j0, j1, e, p;
-    chunk((int)sh.ibase[BLK], tid, &j0, &j1);
-    uint32_t G = sh.base[0][tid];
-    for (int jj = j0; jj < j1; jj++) {
+    uint32_t G = 0;
+    const int n_nd = (int)sh.ibase[BLK];
+    for (int jj = tid; jj < n_nd; jj += BLK) {  // round-robin: neighbouring threads write neighbouring list slots
       const uint32_t v = sh.itab[jj];
       e = (int)(v >> 5);
       p = (int)(v & 31u);
-      uint32_t nd = sh.pres[e * 24 + p];  // already de-duplicated by ph_count
+      const uint32_t w = sh.pres[e * 24 + p];  // de-duplicated by ph_count, offset added by ph_env_bases
+      uint32_t nd = w & 0xFFFFFFu;
       uint32_t cnt = (uint32_t)popc32(nd);
-      uint32_t off = G - sh.ebase[e];
-      G += cnt;
+      uint32_t off = w >> 24;
       if (cnt == 0) continue;
       uint32_t idx = pick_index(sh, e, row0 + e, sh.etotal[e], A);
       uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
@@ -751,50 +812,61 @@ struct BlockStep {
     }
     int n1 = (int)sh.n_l1;
     if (n1 > 0) {
-      chunk((int)sh.d2base[n1], tid, &j0, &j1);
+      // level-2 doubles items.  Normal case: dealt round-robin, offset and count of an item read from the table
+      // ph_env_bases left (an item beyond the stored capacity that does not hold the chosen action costs
+      // nothing).  Fallback (tables did not fit): contiguous chunks, running offset, every item counted again.
+      const bool fast = l2_fast(sh);
+      const int n2 = (int)sh.n_l2;
+      const uint16_t* off16 = l2_off(sh);
+      const uint32_t t0 = sh.ibase[BLK];
       L2Iter it2;
-      it2.init(sh, j0, j1);
-      G = sh.base[1][tid];
-      int j;
-      while (it2.next(sh, &j, &p)) {
-        e = sh.l1env[j];
-        int s1 = sh.l1src[j];
-        uint32_t total = sh.etotal[e];
-        if (total == 0 || sh.defer[e]) {  // cannot use four dice (ph_finish) / deferred to the exact kernel
-          if (total && sh.defer[e]) {  // keep the running offset consistent with what ph_count added
-            uint32_t deep, taint = 0;
-            G += dbl_count2(pos_of(sh, e), sh.a[e], head_budget(sh, e), s1, p, &deep, true, &taint);
-          }
-          continue;
+      int t = tid, t1 = n2, dt = BLK;
+      if (!fast) {
+        chunk(n2, tid, &j0, &j1);
+        it2.init(sh, j0, j1);
+        G = sh.base[1][tid];
+        t = j0;
+        t1 = j1;
+        dt = 1;
+      }
+      for (; t < t1; t += dt) {
+        int j;
+        uint32_t off, cnt;
+        if (fast) {
+          const uint32_t v = sh.itab[t0 + (uint32_t)t];
+          j = (int)(v >> 5);
+          p = (int)(v & 31u);
+        } else {
+          it2.next(sh, &j, &p);
         }
-        uint32_t idx = pick_index(sh, e, row0 + e, total, A);
-        uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
-        uint32_t off = G - sh.ebase[e];
-        Pos P = pos_of(sh, e);
-        int d = sh.a[e], H = head_budget(sh, e);
-        bool store = slice && (int)off < A.cap;
-        bool exact = !DEFER && sh.blk[e] != 0;
-        if (store) {
-          if (exact) {
-            if constexpr (!DEFER) G += dbl_exact2<true>(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
-          } else {
-            G += dbl_emit2(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
-          }
-        } else {  // nothing to store: count, and walk again only if the chosen index is inside
-          uint32_t deep, cnt = 0;
-          if (exact) {
-            if constexpr (!DEFER) cnt = dbl_count2_exact(P, d, H, s1, p);
-          } else {
-            cnt = dbl_count2(P, d, H, s1, p, &deep);
-          }
+        e = sh.l1env[j];
+        const int s1 = sh.l1src[j];
+        const uint32_t total = sh.etotal[e];
+        if (fast) {
+          if (total == 0 || sh.defer[e]) continue;  // cannot use four dice (ph_finish) / deferred to the exact kernel
+          off = off16[t];
+          uint32_t nxt = total;                     // the next item of the same env starts where this one ends
+          if (t + 1 < n2 && sh.l1env[sh.itab[t0 + (uint32_t)t + 1u] >> 5] == e) nxt = off16[t + 1];
+          cnt = nxt - off;
+        } else {
+          cnt = total ? recount_item(sh, e, s1, p) : 0u;  // what ph_count added for this item
+          off = G - sh.ebase[e];
           G += cnt;
-          if (idx >= off && idx < off + cnt) {
-            if (exact) {
-              if constexpr (!DEFER) dbl_exact2<true>(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
-            } else {
-              dbl_emit2(P, d, H, s1, p, off, nullptr, A.cap, idx, &sh.chosen[e]);
-            }
-          }
+          if (total == 0 || sh.defer[e]) continue;
+        }
+        if (cnt == 0) continue;
+        const uint32_t idx = pick_index(sh, e, row0 + e, total, A);
+        uint64_t* slice = A.actions ? A.actions + (row0 + e) * (int64_t)A.cap : nullptr;
+        if (!(slice && (int)off < A.cap)) {
+          slice = nullptr;                          // nothing to store: walk only if the chosen index is inside
+          if (!(idx >= off && idx < off + cnt)) continue;
+        }
+        const Pos P = pos_of(sh, e);
+        const int d = sh.a[e], H = head_budget(sh, e);
+        if (!DEFER && sh.blk[e] != 0) {
+          if constexpr (!DEFER) dbl_exact2<true>(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
+        } else {
+          dbl_emit2(P, d, H, s1, p, off, slice, A.cap, idx, &sh.chosen[e]);
         }
       }
     }

@@ -8,11 +8,15 @@
 #include <stdint.h>
 #include <string.h>
 
+#define NARDE_HOSTSIM_HOOKS 1
 #include "../../gym_narde_b200/csrc/narde_block.cuh"
 #include "../../gym_narde_b200/csrc/narde_deferred.cuh"
 #include "../../gym_narde_b200/csrc/narde_env.cuh"
 
 using namespace narde;
+namespace narde { int g_hs_force_slow = 0; }
+// bit 0: level-2 doubles items are not put in the item table; bit 1: no per-item offset table (recounting emit)
+extern "C" void hs_set_force_slow(int v) { narde::g_hs_force_slow = v; }
 #ifdef NARDE_PROFILE
 namespace narde { ProfCounters g_prof; }
 extern "C" void hs_prof_get(long long* out) { memcpy(out, &narde::g_prof, sizeof(narde::g_prof)); }

@@ -158,3 +158,20 @@ def test_block_kernel_equals_per_thread_body(hostsim):
         assert o["deferred"] == 0
     finally:
         hostsim.defer = True
+
+
+def test_block_kernel_fallback_paths(hostsim):
+    """The rare CTA whose level-2 doubles items do not fit the item table (searching iterator) or the per-item
+    offset table (contiguous chunks, every item counted again in the emit phase): forced here through the
+    test-only hook of the host build, on both tiles, against the per-thread body and the oracle."""
+    import ctypes as C
+    for force in (1, 2):
+        hostsim.lib.hs_set_force_slow(C.c_int(force))
+        try:
+            test_block_kernel_equals_per_thread_body(hostsim)
+            P.check_step_full_lockstep(hostsim, 96, 100, 0xFA11 + force)
+            hostsim.lib.hs_set_small_batch(C.c_int64(0))
+            test_block_kernel_equals_per_thread_body(hostsim)
+        finally:
+            hostsim.lib.hs_set_small_batch(C.c_int64(16384))
+            hostsim.lib.hs_set_force_slow(C.c_int(0))
