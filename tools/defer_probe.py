@@ -9,7 +9,7 @@ from gym_narde_b200 import VecNardeEnv, _cabi
 lib = _cabi.load()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
-for flags in (0, 1, 0, 1):
+for flags in [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else '0,1,0,1'.split(','))]:
     env = VecNardeEnv(n, seed=0x5EED, max_actions=64)
     env.reset()
     for _ in range(300):
