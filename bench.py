@@ -391,7 +391,7 @@ def run_cuda_arm(args):
         kernel_ms = total_ms / K                             # rank-0 kernel: one launch per step
         achieved = E * bytes_per_unit / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01e_step_full_v2.json")   # ncu --set full of the same kernel/workload
+        tp = os.path.join(ROOT, "profiles", "r01f_step_full_v2.json")   # ncu --set full of the same kernel/workload
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp))["launches"][0].get("dram_bytes_per_launch")
@@ -407,7 +407,7 @@ def run_cuda_arm(args):
                        "l2": "flushed between timed steps (256 MiB fill, untimed)" if flush is not None else "not flushed",
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "roofline": {"bound": "hbm", "kernel": "k_step_full_v2<128,true> + its programmatic dependent k_step_deferred<256> (order-dependent doubles turns, overlaps the tail), timed together as one step", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01e_step_full_v2.json (per launch)", "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01f_step_full_v2.json (per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E, "d2h_bytes_per_step": 6 * E,
                     "ms_per_step": total_e2e_max / K,
