@@ -423,8 +423,8 @@ def run_cuda_arm(args):
             "e2e_obs_to_host": {"value": world * E * k_obs / (sum(ms_e2e_obs) * 1e-3), "unit": UNIT, "steps": k_obs,
                                 "d2h_bytes_per_step": 5 * E + 792 * E, "ms_per_step": sum(ms_e2e_obs) / k_obs,
                                 "note": "same as e2e plus the full Box(198) float32 batch copied D2H every step (PCIe-bound; rank 0's time)"},
-            # k_advance_counter (graph replay) + k_step_full_v2 + k_step_deferred per step
-            "gpu_launches": K * ((3 if env.use_graph else 2) * len(env._chunks)),
+            # k_step_full_v2 + k_step_deferred per step (+ k_advance_counter when a chunked env replays a graph)
+            "gpu_launches": K * ((3 if (env.use_graph and env._ws_adv is None) else 2) * len(env._chunks)),
             "wall_ms": wall_ms, "clocks": clocks,
             "config2_4096_envs": {"value": 4096 * len(ms_small) / (sum(ms_small) * 1e-3), "unit": UNIT,
                                   "ms_per_step": sum(ms_small) / len(ms_small)},

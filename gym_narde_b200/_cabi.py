@@ -18,6 +18,7 @@ AUTORESET = 2
 ACTION_FRACTION = 32
 ENUMERATE_ONLY = 64
 PACK_RESULT = 128
+DEVICE_ADVANCE = 256
 HALF_MOVES_ONLY = 4
 MAX_HALF_MOVES = 96
 NUM_STATS = 8
@@ -185,8 +186,8 @@ def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actio
     import torch
 
     cap = actions.shape[1] if actions is not None else 0
-    if workspace is not None and workspace.numel() < lo.shape[0] + 1:
-        raise NardeCudaError("workspace must hold n + 1 int32")
+    if workspace is not None and workspace.numel() < lo.shape[0] + (2 if flags & DEVICE_ADVANCE else 1):
+        raise NardeCudaError("workspace must hold n + 1 int32 (n + 2 with DEVICE_ADVANCE)")
     rc = load().narde_step_full(
         _ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"), lo.shape[0], env_base, seed, step,
         _ptr(dice_in, torch.uint8, "dice_in"), _ptr(action_idx, torch.int32, "action_idx"), cap,

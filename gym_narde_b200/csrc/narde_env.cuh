@@ -13,6 +13,7 @@ enum : int {
   F_ACTION_FRACTION = 32,
   F_ENUMERATE_ONLY = 64,
   F_PACK_RESULT = 128,
+  F_DEVICE_ADVANCE = 256,  // the step index is *step_dev + 1; the kernels store it back when the step is complete
   DONE_TERMINATED = 1,
   DONE_TRUNCATED = 2,
 };
@@ -83,6 +84,8 @@ struct StepFullArgs {
   // optional device-resident step counter (overrides `step`): lets the whole step be replayed as a
   // CUDA graph with frozen kernel arguments
   const uint64_t* step_dev;
+  // F_DEVICE_ADVANCE: arrival counter of the exact kernel's CTAs; the last one resets the list and adds 1 to *step_dev
+  int32_t* ticket;
 };
 
 // The index of the action to play among `count` legal ones: the caller's action_idx[i] (clamped; or,

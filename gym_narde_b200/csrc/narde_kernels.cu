@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
                                                       int64_t* stats) {
   typedef BlockStep<BLK, DEFER> BS;
   StepFullArgs A = A_in;
-  if (A.step_dev) A.step = *A.step_dev;
+  if (A.step_dev) A.step = *A.step_dev + ((A.flags & F_DEVICE_ADVANCE) ? 1u : 0u);
   __shared__ BlockShared<BLK> sh;
   const int tid = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.x * BLK;
@@ -327,7 +327,7 @@ template <int BLK>
 __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A_in, float* obs198, int64_t* stats) {
   typedef DeferredStep<BLK> DS;
   StepFullArgs A = A_in;
-  if (A.step_dev) A.step = *A.step_dev;
+  if (A.step_dev) A.step = *A.step_dev + ((A.flags & F_DEVICE_ADVANCE) ? 1u : 0u);
   __shared__ DeferredSharedT<BLK> sh;
   __shared__ float4 lut[16];
   obs_lut_init(lut);
@@ -398,6 +398,22 @@ __global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, Ste
 #undef DMARK
   // stream order: this grid must not complete before its primary has (the next step follows it)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // F_DEVICE_ADVANCE: the step's own bookkeeping instead of a memset and a counter kernel in front of every step
+  // (each is a node of the step's CUDA graph, ~2 us).  Every CTA of this grid has read the list length and the
+  // step index before it arrives here, and the primary grid is complete: the last arrival resets the list for
+  // the next step and publishes the new step index.
+  if (A.ticket) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(A.ticket, 1) == (int)gridDim.x - 1) {
+        *A.defer_count = 0;
+        *A.ticket = 0;
+        *const_cast<uint64_t*>(A.step_dev) = A.step;
+        __threadfence();
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {
@@ -663,6 +679,9 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.defer_count = nullptr;
   A.defer_list = nullptr;
   A.step_dev = step_dev;
+  A.ticket = nullptr;
+  const bool dev_advance = (flags & NARDE_DEVICE_ADVANCE) != 0;
+  if (dev_advance && (!workspace || !step_dev || (flags & (NARDE_PER_THREAD_KERNEL | NARDE_ENUMERATE_ONLY)))) return -1;
   if (flags & NARDE_PER_THREAD_KERNEL) {
     if (flags & NARDE_ENUMERATE_ONLY) return -1;
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
@@ -673,8 +692,12 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     if ((((uintptr_t)workspace) & 3u) != 0) return -1;
     A.defer_count = workspace;
     A.defer_list = workspace + 1;
-    cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t), (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
+    if (dev_advance) {  // [n + 1] = arrival counter; list length and counter are zero on entry and again on exit
+      A.ticket = workspace + n + 1;
+    } else {
+      cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t), (cudaStream_t)stream);
+      if (e != cudaSuccess) return (int)e;
+    }
   }
   const cudaStream_t st = (cudaStream_t)stream;
   uint4 *plo = (uint4*)lo, *phi = (uint4*)hi;

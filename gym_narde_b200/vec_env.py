@@ -64,6 +64,9 @@ class VecNardeEnv:
         # deferred-turn lists (see narde_b200.h: (n + 1) int32 per call)
         self._workspaces = [torch.zeros((e - b) + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
         self._enum_ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)   # get_valid_actions' deferred-turn list
+        # graph-replayed steps of an unchunked env let the kernels advance the step counter and clear the list
+        # themselves (DEVICE_ADVANCE: two graph nodes fewer per step); that workspace is never shared with other calls
+        self._ws_adv = torch.zeros(n + 2, dtype=torch.int32, device=dev) if len(self._chunks) == 1 else None
         # device-resident copy of step_count: kernel arguments stay frozen, so a step is one graph replay
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.action_in = torch.zeros(n, dtype=torch.int32, device=dev)   # persistent policy input (graph-replayable)
@@ -162,10 +165,14 @@ class VecNardeEnv:
                            max_episode_steps=self.max_episode_steps, truncated=self.trunc)
         return self.obs, self.reward, self.terminated, self.truncated, self.info
 
-    def _launch_full(self, actions, dice, flags):
-        """Enqueue one fused step: every chunk on its own stream (fork/join around the current stream)."""
+    def _launch_full(self, actions, dice, flags, dev_advance=False):
+        """Enqueue one fused step: every chunk on its own stream (fork/join around the current stream).
+        dev_advance (unchunked envs, graph capture): the step index is the device counter + 1 and the kernels store
+        it back themselves."""
         t = self.torch
         main = t.cuda.current_stream(self.device)
+        if dev_advance:
+            flags |= _cabi.DEVICE_ADVANCE
         for k, (b, e) in enumerate(self._chunks):
             stream = main if k == 0 else self._streams[k - 1]
             if k:
@@ -178,7 +185,8 @@ class VecNardeEnv:
                                 counts=self.counts[b:e], dice_out=self.dice[b:e], chosen=self.chosen[b:e],
                                 obs198=self.obs[b:e], reward=self.reward[b:e], done=self.done[b:e],
                                 stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
-                                truncated=self.trunc[b:e], workspace=self._workspaces[k], step_dev=self._step_dev)
+                                truncated=self.trunc[b:e], workspace=self._ws_adv if dev_advance else self._workspaces[k],
+                                step_dev=self._step_dev)
         for s_ in self._streams:
             main.wait_stream(s_)
 
@@ -190,8 +198,11 @@ class VecNardeEnv:
         t.cuda.synchronize(self.device)
         g = t.cuda.CUDAGraph()
         with t.cuda.graph(g):
-            _cabi.advance_counter(self._step_dev)
-            self._launch_full(actions, dice, flags)
+            if self._ws_adv is not None:
+                self._launch_full(actions, dice, flags, dev_advance=True)
+            else:
+                _cabi.advance_counter(self._step_dev)
+                self._launch_full(actions, dice, flags)
         return g
 
     # -- host-facing step: host buffers in, host buffers out, one graph replay ---------------------------
@@ -246,7 +257,11 @@ class VecNardeEnv:
             with t.cuda.graph(g):
                 if dma_in:
                     self.action_in.copy_(src, non_blocking=True)
-                _cabi.advance_counter(self._step_dev)
+                adv = self._ws_adv is not None
+                if adv:
+                    flags |= _cabi.DEVICE_ADVANCE
+                else:
+                    _cabi.advance_counter(self._step_dev)
                 # dma_in=False: the kernel fetches its CTA's action words from the host buffer itself (one bulk
                 # asynchronous copy of 512 B per CTA into shared memory)
                 _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, 0, action_idx=self.action_in if dma_in else src,
@@ -255,7 +270,7 @@ class VecNardeEnv:
                                 reward=None if packed else io["reward"], done=io["result"] if packed else io["done"],
                                 stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
                                 truncated=None if packed else io["truncated"],
-                                workspace=self._workspaces[0], step_dev=self._step_dev)
+                                workspace=self._ws_adv if adv else self._workspaces[0], step_dev=self._step_dev)
             self._hio_graphs[key] = (g, src)
         g.replay()
         return io

@@ -49,6 +49,11 @@ extern "C" {
 #define NARDE_PACK_RESULT 128     /* narde_step_full (CTA-cooperative kernels): done[i] receives one packed byte per env -- bit 0
                                     terminated, bit 1 truncated, bits 2-3 the reward (0, 1 or 2); reward[] and truncated[] are
                                     not written.  One byte instead of six per env for a host-resident consumer. */
+#define NARDE_DEVICE_ADVANCE 256   /* narde_step_full with workspace and step_dev: the step index is *step_dev + 1, and the kernels
+                                    themselves store it back and clear the workspace when the step is complete -- no memset and no
+                                    counter kernel in front of every step (two nodes of a replayed CUDA graph, ~2 us each).  The
+                                    workspace then holds n + 2 ints, is zero before the first call and is left zero by every call;
+                                    it must not be shared with calls that do not set this flag. */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 
 /* done[i] = 1 when the episode terminated (a player bore off 15 checkers); truncated[i] = 1 when
