@@ -348,13 +348,15 @@ class HostPipeline:
                     self._d_act[b].copy_(self.actions[k], non_blocking=True)
                     ev_in[k].record(self._s_in)
                 main.wait_event(ev_in[k])
-                _cabi.advance_counter(env._step_dev)
+                adv = env._ws_adv is not None
+                if not adv:
+                    _cabi.advance_counter(env._step_dev)
                 _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, action_idx=self._d_act[b],
                                 actions=env.actions if env.write_actions else None, counts=env.counts,
                                 dice_out=env.dice, chosen=env.chosen, obs198=env.obs, reward=self.reward[k],
-                                done=self.done[k], stats=env.stats, flags=flags,
+                                done=self.done[k], stats=env.stats, flags=flags | (_cabi.DEVICE_ADVANCE if adv else 0),
                                 max_episode_steps=env.max_episode_steps, truncated=self.truncated[k],
-                                workspace=env._workspaces[0], step_dev=env._step_dev)
+                                workspace=env._ws_adv if adv else env._workspaces[0], step_dev=env._step_dev)
                 ev_c[k].record(main)
             main.wait_stream(self._s_in)
         return g
