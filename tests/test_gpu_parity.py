@@ -216,3 +216,51 @@ def test_gpu_edge_sizes_and_ragged_batches(cuda_backend):
         _v1_v2_equal(cuda_backend, lo[:n].copy(), hi[:n].copy(), seed=n, step=5, cap=24, flags=2)
     _v1_v2_equal(cuda_backend, lo[:700].copy(), hi[:700].copy(), seed=3, step=2, cap=0, flags=0, want_actions=False)
     _v1_v2_equal(cuda_backend, lo[:700].copy(), hi[:700].copy(), seed=3, step=2, cap=1, flags=1)
+
+
+def test_device_advance_mode_equals_host_stepped_calls():
+    """NARDE_DEVICE_ADVANCE through the C ABI: the step index is *step_dev + 1, the kernels store it back and leave the
+    workspace (list length, arrival counter) zero -- six consecutive calls with no memset / counter kernel between them
+    give exactly the states and outputs of six calls with the step number passed from the host; both CTA tiles."""
+    import torch
+    from gym_narde_b200 import _cabi
+    dev = torch.device("cuda")
+    for n in (3000, 40000):
+        def alloc():
+            lo = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
+            hi = torch.zeros((n, 16), dtype=torch.uint8, device=dev)
+            _cabi.reset(lo, hi, 7, 0xD1CE, 0)
+            return dict(lo=lo, hi=hi, actions=torch.zeros((n, 16), dtype=torch.int64, device=dev),
+                        counts=torch.zeros(n, dtype=torch.int32, device=dev), dice=torch.zeros((n, 2), dtype=torch.uint8, device=dev),
+                        chosen=torch.zeros(n, dtype=torch.int64, device=dev), obs=torch.zeros((n, 198), device=dev),
+                        rew=torch.zeros(n, device=dev), done=torch.zeros(n, dtype=torch.uint8, device=dev),
+                        stats=torch.zeros(8, dtype=torch.int64, device=dev))
+
+        def call(b, step, flags, ws, step_dev):
+            _cabi.step_full(b["lo"], b["hi"], 7, 0xD1CE, step, actions=b["actions"], counts=b["counts"], dice_out=b["dice"],
+                            chosen=b["chosen"], obs198=b["obs"], reward=b["rew"], done=b["done"], stats=b["stats"],
+                            flags=flags, max_episode_steps=0, workspace=ws, step_dev=step_dev)
+
+        a, b = alloc(), alloc()
+        ws_a = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        ws_b = torch.zeros(n + 2, dtype=torch.int32, device=dev)
+        for k in range(40):                                   # into the middle game, where turns get deferred
+            call(a, 1 + k, _cabi.AUTORESET, ws_a, None)
+            call(b, 1 + k, _cabi.AUTORESET, ws_a, None)
+        ctr = torch.full((1,), 40, dtype=torch.int64, device=dev)
+        deferred = 0
+        for k in range(6):
+            call(a, 41 + k, _cabi.AUTORESET, ws_a, None)
+            call(b, 0, _cabi.AUTORESET | _cabi.DEVICE_ADVANCE, ws_b, ctr)
+            deferred += int(ws_a[0].item())
+            assert int(ctr.item()) == 41 + k
+            assert int(ws_b[0].item()) == 0 and int(ws_b[n + 1].item()) == 0
+            for key in a:
+                assert torch.equal(a[key], b[key]), (n, k, key)
+        assert deferred > 0          # the exact kernel had work on the way
+    # the mode needs its workspace and counter, and is not an enumerate-only call
+    lib = _cabi.load()
+    with pytest.raises(_cabi.NardeCudaError):
+        call(b, 0, _cabi.DEVICE_ADVANCE, ws_b, None)
+    with pytest.raises(_cabi.NardeCudaError):
+        call(b, 0, _cabi.DEVICE_ADVANCE, ws_a, ctr)
