@@ -73,6 +73,7 @@ struct DeferredSharedT {
   uint32_t count, idx;
   uint64_t chosen;
   uint32_t part[BLK], base[BLK], part2[33];
+  uint32_t bin[4][32];                         // bin[k][v] = C(v, k + 1): the rank <-> multiset arithmetic by lookup
   uint32_t bm[kDefBmWords];
   uint16_t a[kDefCap], b[kDefCap];             // level lists (levels 1..3: codes of <= 15 bits)
 };
@@ -112,29 +113,29 @@ struct DeferredStep {
   // lexicographic rank of the sorted digit tuple among all j-multisets of 24 values: with
   // y_i = x_i + i (strictly increasing, < n = 24 + j - 1) and z_m = n - 1 - y_{j-1-m},
   // rank = C(n, j) - 1 - sum_m C(z_m, m + 1)
-  static NHD uint32_t rank_of(uint32_t code, int j) {
+  static NHD uint32_t rank_of(const Sh& sh, uint32_t code, int j) {
     const uint32_t n = (uint32_t)(24 + j - 1);
     uint32_t colex = 0;
     for (int m = 0; m < j; m++) {
       int i = j - 1 - m;  // digit index, most significant first
       uint32_t y = ((code >> (5 * (j - 1 - i))) & 31u) + (uint32_t)i;
-      colex += binom(n - 1u - y, m + 1);
+      colex += sh.bin[m][n - 1u - y];
     }
     return multiset_total(j) - 1u - colex;
   }
-  static NHD uint32_t code_of_rank(uint32_t r, int j) {
+  static NHD uint32_t code_of_rank(const Sh& sh, uint32_t r, int j) {
     const uint32_t n = (uint32_t)(24 + j - 1);
     uint32_t c = multiset_total(j) - 1u - r, code = 0;
     for (int m = j - 1; m >= 0; m--) {  // greedy: largest z_m with C(z_m, m+1) <= c
       uint32_t v = (uint32_t)m, hi = n - 1u;  // binom(., m+1) is non-decreasing: binary search
       while (v < hi) {
         uint32_t mid = (v + hi + 1u) >> 1;
-        if (binom(mid, m + 1) <= c)
+        if (sh.bin[m][mid] <= c)
           v = mid;
         else
           hi = mid - 1u;
       }
-      c -= binom(v, m + 1);
+      c -= sh.bin[m][v];
       int i = j - 1 - m;                      // z_m belongs to digit i
       uint32_t x = (n - 1u - v) - (uint32_t)i;
       code |= x << (5 * (j - 1 - i));
@@ -145,6 +146,11 @@ struct DeferredStep {
 
   // ---- phase 0 (one thread): load, dice, decode ------------------------------------------
   static NHD void ph_init(int tid, Sh& sh, const State& s_in, int64_t i, const StepFullArgs& A) {
+    static_assert(BLK >= 128, "the lookup table is filled by 128 threads");
+    if (tid >= BLK - 128) {
+      const int t = tid - (BLK - 128);
+      sh.bin[t >> 5][t & 31] = binom((uint32_t)(t & 31), (t >> 5) + 1);
+    }
     if (tid != 0) return;
     sh.st = s_in;
     uint32_t env = (uint32_t)(A.env_base + i);
@@ -191,7 +197,7 @@ struct DeferredStep {
   static NHD void visit_child(Sh& sh, uint16_t* nxt, uint32_t code, int j, const Pos& P, int s, bool risky) {
     if (risky && violates_block(after_mask(P, s, s - sh.d), P.opp)) return;  // narde.py:78-89
     uint32_t child = insert(code, j, s);
-    uint32_t r = rank_of(child, j + 1);
+    uint32_t r = rank_of(sh, child, j + 1);
     uint32_t bit = 1u << (r & 31u);
     uint32_t old = sm_fetch_or(&sh.bm[r >> 5], bit);
     if (old & bit) return;  // this multiset was already reached through another ordering
@@ -257,7 +263,7 @@ struct DeferredStep {
     const uint16_t* cur = sh.which ? sh.b : sh.a;
     int j = (int)sh.depth;
     for (uint32_t k = (uint32_t)tid; k < sh.n_cur; k += BLK) {
-      uint32_t r = rank_of(cur[k], j);
+      uint32_t r = rank_of(sh, cur[k], j);
       sm_fetch_or(&sh.bm[r >> 5], 1u << (r & 31u));
     }
   }
@@ -324,7 +330,7 @@ struct DeferredStep {
       word = sh.bm[++w];
     }
     for (; k; k--) word &= word - 1u;
-    return code_of_rank((w << 5) + (uint32_t)ctz32(word), (int)sh.depth);
+    return code_of_rank(sh, (w << 5) + (uint32_t)ctz32(word), (int)sh.depth);
   }
   // ---- materialise the first `cap` actions of the canonical list and the chosen one -------------
   // Representative ordering = the lexicographically first legal ordering of the (descending) sources,
