@@ -367,11 +367,38 @@ struct DeferredStep {
     if (k < lim) slice[k] = act;
     if (emit_rank(sh, A, k) == sh.idx) sh.chosen = act;
   }
-  // the lexicographically first legal ordering of a multiset that cannot be played highest-source-first
-  // (depth-first over the <= 4! orderings, higher sources tried first; a few nodes in practice)
+  // the lexicographically first legal ordering of a multiset that cannot be played highest-source-first:
+  // depth-first over the <= 4! orderings, higher sources tried first (dbl_order_search's order and its rule
+  // for equal sources), as a compile-time recursion with the sources and the ordering packed 5 bits each, so
+  // that the positions of the path stay in registers instead of a local-memory stack
+  template <int D>
+  static NHD bool order_dfs(const Sh& sh, const Pos& P, int heads, uint32_t srcp, int j, uint32_t used, uint32_t* orderp) {
+    if constexpr (D >= 4) {
+      return true;
+    } else {
+      const uint32_t m = cand_mask(P.own, P.opp, sh.d, heads < sh.H);
+      for (int c = 0; c < j; c++) {
+        if ((used >> c) & 1u) continue;
+        const int s = (int)((srcp >> (5 * c)) & 31u);
+        bool same = false;  // an equal source already tried at this depth is the same move
+        for (int e = 0; e < c; e++)
+          if (!((used >> e) & 1u) && (int)((srcp >> (5 * e)) & 31u) == s) same = true;
+        if (same || !((m >> s) & 1u)) continue;
+        Pos nx = P;
+        nx.move(s, s - sh.d);
+        if (violates_block(nx.own, nx.opp)) continue;
+        *orderp = (*orderp & ~(31u << (5 * D))) | ((uint32_t)s << (5 * D));
+        if (D + 1 == j) return true;
+        if (order_dfs<D + 1>(sh, nx, heads + (s == 23), srcp, j, used | (1u << c), orderp)) return true;
+      }
+      return false;
+    }
+  }
   static NHD_NOINLINE void first_legal_order(const Sh& sh, const int* src, int j, int* order) {
-    if (!dbl_order_search(base_pos(sh), src, j, sh.d, sh.H, order))
-      for (int t = 0; t < j; t++) order[t] = src[t];  // unreachable: the multiset was reached by a legal sequence
+    uint32_t srcp = 0, orderp = 0;
+    for (int t = 0; t < j; t++) srcp |= (uint32_t)src[t] << (5 * t);
+    if (!order_dfs<0>(sh, base_pos(sh), 0, srcp, j, 0u, &orderp)) orderp = srcp;  // unreachable: the multiset was reached legally
+    for (int t = 0; t < j; t++) order[t] = (int)((orderp >> (5 * t)) & 31u);
   }
   // one thread per emitted rank: rank -> multiset -> representative ordering -> store
   static NHD void ph_emit(int tid, Sh& sh, int64_t i, const StepFullArgs& A) {

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
 // Exact doubles turns handed over by k_step_full_v2 (narde_deferred.cuh): persistent CTAs walk the
 // deferred list, one environment per CTA at a time.
 template <int BLK>
-__global__ void __launch_bounds__(BLK) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A_in, float* obs198, int64_t* stats) {
+__global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A_in, float* obs198, int64_t* stats) {
   typedef DeferredStep<BLK> DS;
   StepFullArgs A = A_in;
   if (A.step_dev) A.step = *A.step_dev + ((A.flags & F_DEVICE_ADVANCE) ? 1u : 0u);
