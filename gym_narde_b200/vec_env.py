@@ -82,7 +82,12 @@ class VecNardeEnv:
     def reset(self, *, seed=None, options=None):
         """NardeEnv.reset (narde_env.py:105-120) for every env; returns (obs, {})."""
         if seed is not None:
-            self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            if seed != self.seed:          # the seed is a frozen kernel argument of every captured step
+                self._graphs.clear()
+                if getattr(self, "_hio", None) is not None:
+                    self._hio_graphs.clear()
+            self.seed = seed
         self.step_count = 0
         self._step_dev.zero_()
         _cabi.reset(self.lo, self.hi, self.env_base, self.seed, 0)
