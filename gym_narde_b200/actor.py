@@ -108,6 +108,8 @@ class AfterstateActor:
         if len(env._chunks) != 1:
             raise ValueError("step_graph needs an unchunked env")
         env.step_count += 1
+        if self._graph is not None and self._graph_seed != env.seed:
+            self._graph = None           # the seed is a frozen kernel argument of the captured turn
         if self._graph is None:
             self._enqueue_turn_warmup()
             env._step_dev.fill_(env.step_count - 1)
@@ -116,6 +118,7 @@ class AfterstateActor:
             with t.cuda.graph(g):
                 self._enqueue_turn()
             self._graph = g
+            self._graph_seed = env.seed
         self._graph.replay()
         return env.obs, env.reward, env.terminated, env.truncated, env.info
 

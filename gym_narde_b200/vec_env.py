@@ -368,7 +368,10 @@ class HostPipeline:
 
     def run(self):
         """Play the next `depth` turns (one graph replay)."""
+        if self._graph is not None and self._graph_seed != self.env.seed:
+            self._graph = None               # the seed is a frozen kernel argument of the captured turns
         if self._graph is None:
             self._graph = self._capture()
+            self._graph_seed = self.env.seed
         self._graph.replay()
         self.env.step_count += self.depth
