@@ -259,8 +259,7 @@ class NardeGameManager:
         self.head_moves_count[player_color] = 0
         self.moves_count = 0
         self.first_move_made = False
-        self.turn_started = False
-        self._save_state_for_undo()
+        self._save_state_for_undo()          # the position the dice were rolled on (undo_moves returns to it)
         self.turn_started = False
         self._refresh()
         return dice, self.valid_moves_by_piece
@@ -285,8 +284,7 @@ class NardeGameManager:
         nxt = self._tree.children(self._nodes, from_pos, to)
         if not nxt:
             return {"error": "Invalid move"}
-        if not self.turn_started:
-            self.turn_started = True
+        self.turn_started = True
         self._nodes = nxt
         self._adopt(nxt[0])
         self.moves_count += 1
