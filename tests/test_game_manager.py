@@ -112,6 +112,41 @@ def _manager_kats(make):
     assert mgr.is_game_over() == (True, "white") and mgr.get_game_state()["winner"] == "white"
 
 
+def _rule_kats(make):
+    # no playable die: the roll offers nothing and the position stays as it is (a passed turn)
+    mgr = make()
+    g = mgr.game
+    g.board[:] = 0
+    g.board[23], g.board[17], g.board[18] = 15, -7, -8
+    g.first_turn_white = g.first_turn_black = False
+    dice, by = mgr.roll_dice("white", dice=(6, 5))
+    assert by == {} and mgr.get_valid_moves_for_position(23, "white") == []
+    assert "error" in mgr.make_move(23, 17, "white") and g.board[23] == 15
+    # either die can be played but not both: the higher one must be (narde.py:6 rule 4)
+    mgr = make()
+    g = mgr.game
+    g.board[:] = 0
+    g.board[23], g.board[10], g.board[17], g.board[18] = 1, 1, -7, -8
+    g.borne_off_white, g.first_turn_white, g.first_turn_black = 13, False, False
+    dice, by = mgr.roll_dice("white", dice=(5, 6))
+    assert dice == [6, 5] and by == {10: [(10, 4)]}
+    assert "error" in mgr.make_move(10, 5, "white")
+    assert mgr.make_move(10, 4, "white").get("turn_complete") and g.board[4] == 1
+    # both dice when possible: a first half-move that would strand the second die is not offered
+    mgr = make()
+    g = mgr.game
+    g.board[:] = 0
+    g.board[23], g.board[10], g.board[17], g.board[18], g.board[4] = 1, 1, -7, -7, -1
+    g.borne_off_white, g.first_turn_white, g.first_turn_black = 13, False, False
+    dice, by = mgr.roll_dice("white", dice=(6, 5))      # 10->4 is blocked; 10->5 then nothing for the 6
+    assert by == {10: [(10, 5)]}
+
+
+def test_manager_rule_kats_cpu(hostsim):
+    from gym_narde_b200.narde_game_manager import NardeGameManager
+    _rule_kats(lambda: NardeGameManager(_Env(), _ops=hostsim))
+
+
 def test_turn_tree_vs_oracle_cpu(hostsim):
     for lo, hi, dice in _corpora():
         assert P.check_turn_tree_vs_oracle(hostsim, lo, hi, dice) > 0
@@ -153,6 +188,7 @@ def test_manager_on_the_facade_gpu():
         return NardeGameManager(env)
 
     _manager_kats(make)
+    _rule_kats(make)
     mgr = make()
     turns, halves = _play_one_game(mgr, random.Random(5))
     assert turns > 20 and halves > turns
