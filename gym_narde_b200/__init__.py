@@ -38,22 +38,70 @@ def __getattr__(name):
     return _lazy(name)
 
 
-def make(env_id="narde-v0", **kwargs):
+class TimeLimit:
+    """gymnasium's TimeLimit for the make() fallback below: truncated=True once max_episode_steps steps were taken
+    since the last reset (the wrapper gym.make applies for gym_narde/__init__.py:6 `max_episode_steps=1000`)."""
+
+    def __init__(self, env, max_episode_steps):
+        self.env = env
+        self._max_episode_steps = int(max_episode_steps)
+        self._elapsed_steps = 0
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.env, name)
+
+    def reset(self, **kwargs):
+        self._elapsed_steps = 0
+        return self.env.reset(**kwargs)
+
+    def step(self, action):
+        obs, reward, terminated, truncated, info = self.env.step(action)
+        self._elapsed_steps += 1
+        if self._elapsed_steps >= self._max_episode_steps:
+            truncated = True
+        return obs, reward, terminated, truncated, info
+
+    def render(self):
+        return self.env.render()
+
+    def close(self):
+        return self.env.close()
+
+
+MAX_EPISODE_STEPS = 1000  # gym_narde/__init__.py:6
+
+
+def make(env_id="narde-v0", max_episode_steps=MAX_EPISODE_STEPS, **kwargs):
+    """gym.make('gym_narde:narde-v0') without gymnasium: the env wrapped in the TimeLimit the registration implies
+    (max_episode_steps=None or 0: no wrapper)."""
     from .envs.narde_env import NardeEnv
 
     base = env_id.split(":")[-1]
     if base == "narde-v0":
-        return NardeEnv(rules="reference", **kwargs)
-    if base == "Narde-v0":
-        return NardeEnv(rules="full", **kwargs)
-    raise ValueError("unknown env id %r" % env_id)
+        env = NardeEnv(rules="reference", **kwargs)
+    elif base == "Narde-v0":
+        env = NardeEnv(rules="full", **kwargs)
+    else:
+        raise ValueError("unknown env id %r" % env_id)
+    return TimeLimit(env, max_episode_steps) if max_episode_steps else env
 
 
-try:  # optional gymnasium registration (gym_narde/__init__.py:3-7)
-    from gymnasium.envs.registration import register as _register
-
-    _register(id="narde-v0", entry_point="gym_narde_b200.envs:NardeEnv", max_episode_steps=1000)
-    _register(id="Narde-v0", entry_point="gym_narde_b200.envs:NardeEnv", max_episode_steps=1000,
+def _register_with_gymnasium():
+    """gym_narde/__init__.py:3-7 for both ids; a no-op without gymnasium."""
+    try:
+        from gymnasium.envs.registration import register as _register
+    except ImportError:
+        return False
+    _register(id="narde-v0", entry_point="gym_narde_b200.envs:NardeEnv", max_episode_steps=MAX_EPISODE_STEPS)
+    _register(id="Narde-v0", entry_point="gym_narde_b200.envs:NardeEnv", max_episode_steps=MAX_EPISODE_STEPS,
               kwargs={"rules": "full"})
-except Exception:
-    pass
+    return True
+
+
+_register_with_gymnasium()

@@ -11,6 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnarde_b200.so")
+if os.environ.get("NARDE_B200_DEBUG_HOOKS") == "1":   # measurement tools only (tools/*.py): the -DNARDE_DEBUG_HOOKS build
+    LIB_PATH = os.path.join(_HERE, "libnarde_b200_debug.so")
 
 # flags / bits (include/narde_b200.h)
 REWARD_MOVER12 = 1
@@ -43,6 +45,8 @@ _SIGNATURES = {
     "narde_mlp_score": ([_vp, _i64, _vp, _vp, _vp, _vp], _int),
     "narde_mlp_forward_states": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp], _int),
     "narde_mlp_score_states": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], _int),
+    "narde_mlp_score_states_2sm": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], _int),
+    "narde_mlp_use_cluster_pair": ([_int], _int),
     "narde_mlp_forward_move2": ([_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_mlp_forward_move2_states": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_action_codes": ([_vp, _vp, _i64, _i32, _vp, _vp], _int),

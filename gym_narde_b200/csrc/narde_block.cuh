@@ -248,36 +248,8 @@ struct BlockStep {
     if (!bulk_words) sh.rnd[tid] = A.action_idx ? policy_word : rnd.z;  // the policy's choice, or the turn's uniform word
   }
 
-  // ---- block exclusive scan of part[l] -> base[l], totals in ws[l][32] (3 phases) ---------
-  static NHD void ph_scan1(int tid, Sh& sh) {
-    if (tid < 32) {
-      for (int l = 0; l < 4; l++) {
-        uint32_t s = 0;
-        for (int k = 0; k < PER; k++) s += sh.part[l][tid * PER + k];
-        sh.ws[l][tid] = s;
-      }
-    }
-  }
-  static NHD void ph_scan2(int tid, Sh& sh) {
-    if (tid < 4) {
-      uint32_t r = 0;
-      for (int k = 0; k < 32; k++) {
-        uint32_t t = sh.ws[tid][k];
-        sh.ws[tid][k] = r;
-        r += t;
-      }
-      sh.ws[tid][32] = r;
-    }
-  }
-  static NHD void ph_scan3(int tid, Sh& sh) {
-    int g = tid / PER;
-    for (int l = 0; l < 4; l++) {
-      uint32_t r = sh.ws[l][g];
-      for (int k = g * PER; k < tid; k++) r += sh.part[l][k];
-      sh.base[l][tid] = r;
-    }
-  }
-  // The same exclusive scan in ONE phase.  On the device warp l scans lane l with shuffles (BLK = 128: four
+  // ---- block exclusive scan of part[l] -> base[l], totals in ws[l][32] ----------------------
+  // One phase.  On the device warp l scans lane l with shuffles (BLK = 128: four
   // warps, four lanes); the host harness runs the plain serial scan.  lanes: bit mask of the lanes needed.
   static NHD void ph_scan_serial(int tid, Sh& sh, uint32_t lanes) {
 #if defined(__CUDA_ARCH__)

@@ -9,8 +9,11 @@
 #include <stdlib.h>
 
 #include "../../include/narde_b200.h"
-#define NARDE_DEBUG_HOOKS 1
+// NARDE_DEBUG_HOOKS (tools only: `python -m gym_narde_b200.build --debug-hooks` -> libnarde_b200_debug.so) compiles
+// in the A/B timing switches and the per-CTA phase clocks; the product library has neither.
+#ifdef NARDE_DEBUG_HOOKS
 namespace narde { __device__ int g_dbg_flags = 0; }
+#endif
 #include "narde_block.cuh"
 #include "narde_deferred.cuh"
 #include "narde_env.cuh"
@@ -198,13 +201,17 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
   write_obs198_cta(sm, lut, rows, row0, obs198);
 }
 
-// Debug aid: per-CTA phase timestamps (clock64) when a buffer was registered through
-// narde_debug_set_clock_buffer; [block][16] u64.  Not part of the public ABI.
+// Debug aid (NARDE_DEBUG_HOOKS builds only): per-CTA phase timestamps (clock64) when a buffer was registered
+// through narde_debug_set_clock_buffer; [block][16] u64.
+#ifdef NARDE_DEBUG_HOOKS
 __device__ unsigned long long* g_dbg_clk = nullptr;
 #define PHASE_MARK(k)                                                                  \
   do {                                                                                 \
     if (g_dbg_clk && threadIdx.x == 0) g_dbg_clk[(size_t)blockIdx.x * 16 + (k)] = clock64(); \
   } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
 
 // Fused full-rules step, CTA-cooperative (narde_block.cuh): the phases run with a CTA barrier
 // between them; everything between the state load and the Box(198) store stays in shared memory.
@@ -335,10 +342,14 @@ __global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, 
   // launched as a programmatic dependent of k_step_full_v2: every CTA of it has published its deferred
   // envs (fence + trigger) before this grid starts; read the list through L2
   const int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
+#ifdef NARDE_DEBUG_HOOKS
 #define DMARK(k)                                                                                      \
   do {                                                                                                \
     if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + (k)] = clock64();      \
   } while (0)
+#else
+#define DMARK(k) do { } while (0)
+#endif
   for (int q = blockIdx.x; q < n_def; q += gridDim.x) {
     const int64_t i = reinterpret_cast<volatile const int32_t*>(A.defer_list)[q];
     State s;
@@ -393,7 +404,9 @@ __global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, 
     if (obs198) write_obs198_cta(&sh.st, lut, 1, i, obs198);
     __syncthreads();
     DMARK(6);
+#ifdef NARDE_DEBUG_HOOKS
     if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + 7] = sh.count;
+#endif
   }
 #undef DMARK
   // stream order: this grid must not complete before its primary has (the next step follows it)
@@ -813,11 +826,13 @@ int narde_advance_counter(uint64_t* counter, void* stream) {
   return launch_status();
 }
 
+#ifdef NARDE_DEBUG_HOOKS
 int narde_debug_set_flags(int flags) { return (int)cudaMemcpyToSymbol(narde::g_dbg_flags, &flags, sizeof(flags)); }
 
 int narde_debug_set_clock_buffer(void* devptr) {
   unsigned long long* p = (unsigned long long*)devptr;
   return (int)cudaMemcpyToSymbol(g_dbg_clk, &p, sizeof(p));
 }
+#endif
 
 }  // extern "C"

@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_mlp2sm(Params P_in) {
 bool g_mlp_attr_set[8] = {false, false, false, false, false, false, false, false};
 // The cluster-pair variant halves the L2 weight traffic but measured no faster (0.178 vs 0.176 ms for 350 k rows:
 // the kernel is bound by the MMA issue path, not by the weight stream), so it is opt-in: NARDE_MLP_PAIR=1 in the
-// environment, or narde_debug_mlp_pair(1).
+// environment, or narde_mlp_use_cluster_pair(1).
 bool g_mlp_pair = false;
 bool g_mlp_env_read = false;
 
@@ -985,9 +985,9 @@ bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 extern "C" {
 
-// Debug / A-B entry (not part of the public ABI): the cta_group::2 scorer.  wpack2: weights packed with
-// pack_weights(two_sm=True).
-int narde_debug_mlp_score_states_2sm(const void* lo, const void* hi, int64_t rows, const int64_t* rows_dev, const void* wpack2,
+// narde_mlp_score_states through the cta_group::2 kernel (clusters of two CTAs, M = 256 per tcgen05.mma; same results).
+// wpack2: weights packed with pack_weights(two_sm=True).
+int narde_mlp_score_states_2sm(const void* lo, const void* hi, int64_t rows, const int64_t* rows_dev, const void* wpack2,
                                      const float* bias, float* score, void* stream) {
   if (rows == 0) return 0;
   if (rows < 0 || !lo || !hi || !wpack2 || !bias || !score) return -1;
@@ -1017,8 +1017,8 @@ int narde_debug_mlp_score_states_2sm(const void* lo, const void* hi, int64_t row
   return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
-// Debug / A-B switch (not part of the public ABI): 1 = cluster-pair variant with multicast weight stages.
-int narde_debug_mlp_pair(int on) {
+// 1 = run the narde_mlp_* entries as clusters of two CTAs sharing every weight stage by multicast (same results).
+int narde_mlp_use_cluster_pair(int on) {
   g_mlp_env_read = true;
   g_mlp_pair = on != 0;
   return 0;

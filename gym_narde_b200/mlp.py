@@ -188,12 +188,9 @@ class AfterstateMLP:
         k = lo.shape[0]
         if out is None:
             out = t.empty(k, dtype=t.float32, device=lo.device)
-        fn = self.lib.narde_debug_mlp_score_states_2sm
-        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        fn.restype = C.c_int
-        self._run(fn, (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k,
+        self._run(self.lib.narde_mlp_score_states_2sm, (C.c_void_p(lo.data_ptr()), C.c_void_p(hi.data_ptr()), k,
                        C.c_void_p(rows_dev.data_ptr() if rows_dev is not None else None), C.c_void_p(self.wpack2.data_ptr()),
-                       C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_debug_mlp_score_states_2sm")
+                       C.c_void_p(self.bias.data_ptr()), C.c_void_p(out.data_ptr())), "narde_mlp_score_states_2sm")
         return out
 
     __call__ = forward

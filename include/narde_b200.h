@@ -165,6 +165,13 @@ int narde_mlp_score_states(const void *lo, const void *hi, int64_t rows, const i
 /* rows_dev (may be NULL): device-resident row count, min(*rows_dev, rows) rows are scored -- lets the
  * afterstate generator and the scorer run back to back without a host synchronisation. */
 
+/* Variants with identical results (A/B): the scorer as a cta_group::2 kernel (wpack2 = weights packed for
+ * it by gym_narde_b200/mlp.py:pack_weights(two_sm=True)), and a process-wide switch that runs the narde_mlp_* entries
+ * above as clusters of two CTAs sharing every weight stage by multicast (also NARDE_MLP_PAIR=1 in the environment). */
+int narde_mlp_score_states_2sm(const void *lo, const void *hi, int64_t rows, const int64_t *rows_dev,
+                               const void *wpack2, const float *bias, float *score, void *stream);
+int narde_mlp_use_cluster_pair(int on);
+
 /* DecomposedDQN.forward(x, selected_move1) (train_deepq_pytorch.py:203-233): the Q-values of the SECOND move,
  * move2_head(cat(features, onehot(move1))).  The one-hot half of that layer is a column gather, so the kernel is
  * the same three-layer GEMM chain with wpack / bias built from the feature network and the first 256 input columns

@@ -610,3 +610,198 @@ int64_t o_selfplay(uint64_t seed, uint32_t env_base, int n_envs, int n_steps, ui
   if (obs_checksum) *obs_checksum = chk;
   return steps;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Bulk trace of full-rules self-play (tests + bench.py's cpu_baseline leg): what o_selfplay plays,
+ * written out turn by turn so that a run of the CUDA path at its benchmarked size (131 072 envs,
+ * hundreds of graph-replayed steps) can be compared record by record.  The state records use the
+ * boundary's own data format (include/narde_b200.h "State record": two 16-byte lanes per env).
+ * ---------------------------------------------------------------------------------------- */
+
+/* include/narde_b200.h:19-24 */
+void o_pack_state(const o_env *e, int terminated, int episode_steps, uint8_t *lo16, uint8_t *hi16) {
+  for (int k = 0; k < 16; k++) lo16[k] = (uint8_t)(int8_t)e->game.board[k];
+  for (int k = 0; k < 8; k++) hi16[k] = (uint8_t)(int8_t)e->game.board[16 + k];
+  hi16[8] = (uint8_t)e->game.borne_off_white;
+  hi16[9] = (uint8_t)e->game.borne_off_black;
+  hi16[10] = (uint8_t)(int8_t)e->current_player;
+  hi16[11] = (uint8_t)((e->game.first_turn_white ? 1 : 0) | (e->game.first_turn_black ? 2 : 0) |
+                       (terminated ? 4 : 0));
+  hi16[12] = (uint8_t)(episode_steps & 0xFF);
+  hi16[13] = (uint8_t)((episode_steps >> 8) & 0xFF);
+  hi16[14] = hi16[15] = 0;
+}
+
+void o_unpack_state(const uint8_t *lo16, const uint8_t *hi16, o_env *e, int *terminated,
+                    int *episode_steps) {
+  for (int k = 0; k < 16; k++) e->game.board[k] = (int8_t)lo16[k];
+  for (int k = 0; k < 8; k++) e->game.board[16 + k] = (int8_t)hi16[k];
+  e->game.borne_off_white = hi16[8];
+  e->game.borne_off_black = hi16[9];
+  e->current_player = (int8_t)hi16[10];
+  e->game.first_turn_white = (hi16[11] & 1) ? 1 : 0;
+  e->game.first_turn_black = (hi16[11] & 2) ? 1 : 0;
+  *terminated = (hi16[11] & 4) ? 1 : 0;
+  *episode_steps = hi16[12] | (hi16[13] << 8);
+}
+
+/* include/narde_b200.h:28-29: u64 = 4 x u16 half-moves (from | to << 8), 255 = bear off,
+ * 0xFFFF = unused slot */
+uint64_t o_pack_action(const o_turn_action *a) {
+  uint64_t v = 0;
+  for (int k = 0; k < 4; k++) {
+    uint64_t h = 0xFFFFu;
+    if (k < a->n_moves) {
+      int from = a->moves[2 * k], to = a->moves[2 * k + 1];
+      h = (uint64_t)(from & 0xFF) | ((uint64_t)(to == O_OFF ? 255 : to) << 8);
+    }
+    v |= h << (16 * k);
+  }
+  return v;
+}
+
+/* position-sensitive checksum of a stored action list: sum_k act[k] * m(k) mod 2^64, m(k) odd
+ * (splitmix64 of k) -- the test computes the same sum over the CUDA path's [N, cap] buffer */
+uint64_t o_list_weight(int k) {
+  uint64_t z = (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z | 1ull;
+}
+
+int64_t o_selfplay_trace(uint64_t seed, uint32_t env_base, int n_envs, int n_steps, uint64_t step0,
+                         const uint8_t *init_lo, const uint8_t *init_hi, const uint32_t *words,
+                         int64_t words_stride, int word_mode, int cap, int reward_mode, int autoreset,
+                         int max_episode_steps, int64_t row_stride, uint8_t *out_lo, uint8_t *out_hi,
+                         int64_t *out_chosen, int32_t *out_count, uint8_t *out_dice, uint8_t *out_done,
+                         float *out_reward, uint64_t *out_hash, int64_t *stats8) {
+  o_env *envs = (o_env *)malloc((size_t)n_envs * sizeof(o_env));
+  int *term = (int *)calloc((size_t)n_envs, sizeof(int));
+  int *esteps = (int *)calloc((size_t)n_envs, sizeof(int));
+  o_turn_action *scratch = (o_turn_action *)malloc(4096 * sizeof(o_turn_action));
+  uint64_t wt[4096];
+  for (int k = 0; k < 4096; k++) wt[k] = o_list_weight(k);
+  int64_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t turns = 0;
+  for (int i = 0; i < n_envs; i++) {
+    if (init_lo && init_hi) {
+      o_unpack_state(init_lo + 16 * (size_t)i, init_hi + 16 * (size_t)i, &envs[i], &term[i], &esteps[i]);
+    } else { /* narde_env.py:105-120 with the roll-off taken from the Philox stream */
+      o_game_init(&envs[i].game);
+      envs[i].current_player = o_opening_player(seed, env_base + (uint32_t)i, step0);
+    }
+  }
+  for (int t = 1; t <= n_steps; t++) {
+    const uint64_t step = step0 + (uint64_t)t;
+    for (int i = 0; i < n_envs; i++) {
+      o_env *e = &envs[i];
+      const size_t r = (size_t)(t - 1) * (size_t)row_stride + (size_t)i;
+      int32_t d1 = 0, d2 = 0, n = 0;
+      uint64_t chosen = ~0ull, hash = 0;
+      float rew = 0.0f;
+      int bits = 0;
+      if (term[i]) { /* without auto-reset a finished env idles: nothing changes, done stays set */
+        bits = 1;
+      } else {
+        uint32_t w;
+        o_turn_dice(seed, env_base + (uint32_t)i, step, &d1, &d2, &w);
+        int pl = e->current_player;
+        int32_t mover[24];
+        o_get_perspective_board(&e->game, pl, mover);
+        n = o_turn_enumerate(mover, pl == 1 ? e->game.borne_off_white : e->game.borne_off_black, d1, d2,
+                             pl == 1 ? e->game.first_turn_white : e->game.first_turn_black, 4096, scratch, 0);
+        int idx = 0;
+        if (n > 0) {
+          if (words && word_mode == 0) { /* caller's index, clamped */
+            int32_t v = (int32_t)words[(size_t)(t - 1) * (size_t)words_stride + (size_t)i];
+            idx = v < 0 ? 0 : (v >= n ? n - 1 : v);
+          } else { /* u32 fraction of the list: the caller's, or the turn's Philox word */
+            uint32_t f = words ? words[(size_t)(t - 1) * (size_t)words_stride + (size_t)i] : w;
+            idx = (int)(((uint64_t)f * (uint64_t)n) >> 32);
+          }
+          const o_turn_action *a = &scratch[idx];
+          chosen = o_pack_action(a);
+          for (int k = 0; k < a->n_moves; k++)
+            o_execute_rotated_move(&e->game, a->moves[2 * k], a->moves[2 * k + 1], pl);
+          int stored = n < cap ? n : cap;
+          if (stored > 4096) stored = 4096;
+          for (int k = 0; k < stored; k++) hash += o_pack_action(&scratch[k]) * wt[k];
+        }
+        int32_t r12;
+        int dn = o_check_game_ended(e, &r12); /* narde_env.py:96 */
+        rew = reward_mode == 1 ? (float)r12 : ((dn && pl == 1) ? 1.0f : 0.0f); /* README.md:107-108 */
+        if (!dn) e->current_player *= -1; /* narde_env.py:99-100 */
+        esteps[i] += 1;
+        bits = dn ? 1 : 0;
+        /* gymnasium TimeLimit (gym_narde/__init__.py:6 max_episode_steps) */
+        if (!dn && max_episode_steps > 0 && esteps[i] >= max_episode_steps) bits |= 2;
+        st[5] += n;
+        if (n > st[6]) st[6] = n;
+        if (n > cap) st[7] += 1;
+        if (bits) {
+          st[0] += 1;
+          st[4] += esteps[i];
+          if (dn) {
+            st[pl == 1 ? 1 : 2] += 1;
+            int loser_off = pl == 1 ? e->game.borne_off_black : e->game.borne_off_white;
+            if (loser_off == 0) st[3] += 1;
+          }
+          if (autoreset) {
+            o_game_init(&e->game);
+            e->current_player = o_opening_player(seed, env_base + (uint32_t)i, step);
+            esteps[i] = 0;
+          } else if (dn) {
+            term[i] = 1;
+          }
+        }
+        turns++;
+      }
+      if (out_lo && out_hi) o_pack_state(e, term[i], esteps[i], out_lo + 16 * r, out_hi + 16 * r);
+      if (out_chosen) out_chosen[r] = (int64_t)chosen;
+      if (out_count) out_count[r] = n;
+      if (out_dice) {
+        out_dice[2 * r] = (uint8_t)d1;
+        out_dice[2 * r + 1] = (uint8_t)d2;
+      }
+      if (out_done) out_done[r] = (uint8_t)bits;
+      if (out_reward) out_reward[r] = rew;
+      if (out_hash) out_hash[r] = hash;
+    }
+  }
+  if (stats8)
+    for (int k = 0; k < 8; k++) stats8[k] = st[k];
+  free(envs);
+  free(term);
+  free(esteps);
+  free(scratch);
+  return turns;
+}
+
+/* get_valid_actions (README.md:156-165) for n packed positions with given dice: legal-action count and the
+ * checksum of the first min(count, cap) canonical list entries (as o_selfplay_trace computes it). */
+void o_enumerate_batch(const uint8_t *lo, const uint8_t *hi, const uint8_t *dice, int64_t n, int cap,
+                       int32_t *out_count, uint64_t *out_hash) {
+  o_turn_action *scratch = (o_turn_action *)malloc(4096 * sizeof(o_turn_action));
+  for (int64_t i = 0; i < n; i++) {
+    o_env e;
+    int term, esteps;
+    o_unpack_state(lo + 16 * i, hi + 16 * i, &e, &term, &esteps);
+    int cnt = 0;
+    uint64_t hash = 0;
+    if (!term) {
+      int pl = e.current_player;
+      int32_t mover[24];
+      o_get_perspective_board(&e.game, pl, mover);
+      cnt = o_turn_enumerate(mover, pl == 1 ? e.game.borne_off_white : e.game.borne_off_black, dice[2 * i],
+                             dice[2 * i + 1], pl == 1 ? e.game.first_turn_white : e.game.first_turn_black, 4096,
+                             scratch, 0);
+      int stored = cnt < cap ? cnt : cap;
+      if (stored > 4096) stored = 4096;
+      for (int k = 0; k < stored; k++) hash += o_pack_action(&scratch[k]) * o_list_weight(k);
+    }
+    out_count[i] = cnt;
+    out_hash[i] = hash;
+  }
+  free(scratch);
+}

@@ -91,6 +91,33 @@ int o_opening_player(uint64_t seed, uint32_t env, uint64_t step);
 int64_t o_selfplay(uint64_t seed, uint32_t env_base, int n_envs, int n_steps, uint64_t step0,
                    int64_t *sum_actions, int64_t *episodes, double *obs_checksum);
 
+/* ---- bulk trace of full-rules self-play (parity at the benchmarked size; bench.py cpu_baseline) ----
+ * State records use the boundary's data format (include/narde_b200.h:19-24), actions its u64
+ * turn-action encoding (:28-29). */
+void o_pack_state(const o_env *e, int terminated, int episode_steps, uint8_t *lo16, uint8_t *hi16);
+void o_unpack_state(const uint8_t *lo16, const uint8_t *hi16, o_env *e, int *terminated,
+                    int *episode_steps);
+uint64_t o_pack_action(const o_turn_action *a);
+uint64_t o_list_weight(int k);
+/* Plays envs [env_base, env_base + n_envs) for turns step0+1 .. step0+n_steps the way the fused CUDA
+ * step does: Philox dice, full enumeration, action choice (words == NULL: the turn's Philox word as
+ * a fraction of the list; word_mode 0: words[t][i] is a clamped index, 1: a u32 fraction), apply,
+ * termination / reward (reward_mode as o_full_step), TimeLimit truncation, optional auto-reset.
+ * init_lo/init_hi: packed start states, NULL = fresh games whose roll-off is taken at step0.
+ * Every out_* array (each may be NULL) is [n_steps][row_stride]; row (t-1, i) describes env i after
+ * turn step0+t: packed state, chosen action, legal-action count, dice, done bits (1 terminated,
+ * 2 truncated), reward, checksum of the first min(count, cap) list entries.  stats8 = the counters
+ * of include/narde_b200.h:62-71 over this call.  Returns the number of env turns played. */
+int64_t o_selfplay_trace(uint64_t seed, uint32_t env_base, int n_envs, int n_steps, uint64_t step0,
+                         const uint8_t *init_lo, const uint8_t *init_hi, const uint32_t *words,
+                         int64_t words_stride, int word_mode, int cap, int reward_mode, int autoreset,
+                         int max_episode_steps, int64_t row_stride, uint8_t *out_lo, uint8_t *out_hi,
+                         int64_t *out_chosen, int32_t *out_count, uint8_t *out_dice, uint8_t *out_done,
+                         float *out_reward, uint64_t *out_hash, int64_t *stats8);
+/* get_valid_actions for n packed positions: count + checksum of the first min(count, cap) list entries */
+void o_enumerate_batch(const uint8_t *lo, const uint8_t *hi, const uint8_t *dice, int64_t n, int cap,
+                       int32_t *out_count, uint64_t *out_hash);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,15 @@ def lib():
         L.o_selfplay.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.o_selfplay.restype = C.c_int64
+        u8p, vp = C.POINTER(C.c_uint8), C.c_void_p
+        L.o_selfplay_trace.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, C.c_int64,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp,
+                                       vp, vp, vp, vp]
+        L.o_selfplay_trace.restype = C.c_int64
+        L.o_enumerate_batch.argtypes = [vp, vp, vp, C.c_int64, C.c_int, vp, vp]
+        L.o_enumerate_batch.restype = None
+        L.o_list_weight.argtypes = [C.c_int]
+        L.o_list_weight.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -236,3 +245,82 @@ def selfplay(seed, env_base, n_envs, n_steps, step0=0):
     n = lib().o_selfplay(int(seed), int(env_base), int(n_envs), int(n_steps), int(step0), C.byref(a), C.byref(e),
                          C.byref(c))
     return int(n), int(a.value), int(e.value)
+
+
+def list_weights(cap):
+    """The multipliers of o_selfplay_trace's action-list checksum, as int64 bit patterns [cap]."""
+    return np.array([lib().o_list_weight(k) for k in range(cap)], dtype=np.uint64).view(np.int64)
+
+
+def selfplay_trace(seed, env_base, n_envs, n_steps, step0=0, init=None, words=None, word_mode=1, cap=64,
+                   reward_mode=0, autoreset=True, max_episode_steps=1000, threads=None, want_states=True):
+    """o_selfplay_trace over envs [env_base, env_base + n_envs), split over `threads` host threads (ctypes
+    releases the GIL; every thread plays a contiguous block of envs into the shared [n_steps, n_envs] arrays).
+    init: (lo, hi) uint8 [n_envs, 16] start states or None (fresh games, roll-off at step0).
+    words: uint32 [n_steps, n_envs] policy words or None (the turn's Philox word).
+    Returns a dict of numpy arrays [n_steps, n_envs, ...] + "stats" int64[8] + "turns"."""
+    from concurrent.futures import ThreadPoolExecutor
+    L = lib()
+    T, n = int(n_steps), int(n_envs)
+    out = {"chosen": np.zeros((T, n), np.int64), "count": np.zeros((T, n), np.int32),
+           "dice": np.zeros((T, n, 2), np.uint8), "done": np.zeros((T, n), np.uint8),
+           "reward": np.zeros((T, n), np.float32), "hash": np.zeros((T, n), np.int64)}
+    if want_states:
+        out["lo"] = np.zeros((T, n, 16), np.uint8)
+        out["hi"] = np.zeros((T, n, 16), np.uint8)
+    if init is not None:
+        ilo = np.ascontiguousarray(init[0], dtype=np.uint8).reshape(n, 16)
+        ihi = np.ascontiguousarray(init[1], dtype=np.uint8).reshape(n, 16)
+    if words is not None:
+        words = np.ascontiguousarray(words).view(np.uint32).reshape(T, n)
+    threads = int(threads or os.cpu_count() or 1)
+    per = max(1, -(-n // threads))
+    blocks = [(b, min(b + per, n)) for b in range(0, n, per)]
+    stats = np.zeros((len(blocks), 8), np.int64)
+
+    def ptr(a, off):
+        return None if a is None else a.ctypes.data + off * a.itemsize
+
+    def run(k):
+        b, e = blocks[k]
+        return L.o_selfplay_trace(
+            int(seed) & 0xFFFFFFFFFFFFFFFF, (int(env_base) + b) & 0xFFFFFFFF, e - b, T, int(step0),
+            ptr(ilo, 16 * b) if init is not None else None, ptr(ihi, 16 * b) if init is not None else None,
+            ptr(words, b) if words is not None else None, n, int(word_mode), int(cap), int(reward_mode),
+            int(bool(autoreset)), int(max_episode_steps), n,
+            ptr(out.get("lo"), 16 * b), ptr(out.get("hi"), 16 * b), ptr(out["chosen"], b), ptr(out["count"], b),
+            ptr(out["dice"], 2 * b), ptr(out["done"], b), ptr(out["reward"], b), ptr(out["hash"], b),
+            stats[k].ctypes.data)
+
+    if len(blocks) == 1:
+        turns = run(0)
+    else:
+        with ThreadPoolExecutor(len(blocks)) as ex:
+            turns = sum(ex.map(run, range(len(blocks))))
+    st = stats.sum(0)
+    st[6] = stats[:, 6].max()
+    out["stats"] = st
+    out["turns"] = int(turns)
+    return out
+
+
+def enumerate_batch(lo, hi, dice, cap=64, threads=None):
+    """o_enumerate_batch on host threads: (counts int32 [n], list checksums int64 [n])."""
+    from concurrent.futures import ThreadPoolExecutor
+    L = lib()
+    lo = np.ascontiguousarray(lo, np.uint8).reshape(-1, 16)
+    hi = np.ascontiguousarray(hi, np.uint8).reshape(-1, 16)
+    dice = np.ascontiguousarray(dice, np.uint8).reshape(-1, 2)
+    n = lo.shape[0]
+    counts, hashes = np.zeros(n, np.int32), np.zeros(n, np.int64)
+    threads = int(threads or os.cpu_count() or 1)
+    per = max(1, -(-n // (threads * 4)))
+
+    def run(b):
+        e = min(b + per, n)
+        L.o_enumerate_batch(lo.ctypes.data + 16 * b, hi.ctypes.data + 16 * b, dice.ctypes.data + 2 * b, e - b, int(cap),
+                            counts.ctypes.data + 4 * b, hashes.ctypes.data + 8 * b)
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(run, range(0, n, per)))
+    return counts, hashes

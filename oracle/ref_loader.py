@@ -15,7 +15,6 @@ import contextlib
 import importlib
 import os
 import sys
-import types
 from unittest import mock
 
 import numpy as np
@@ -28,66 +27,12 @@ def available() -> bool:
 
 
 def _install_gymnasium_stub():
-    try:
-        import gymnasium  # noqa: F401
-        return
-    except Exception:
-        pass
-    gym = types.ModuleType("gymnasium")
-
-    class Env:
-        metadata = {}
-
-        def __init__(self, *a, **k):
-            pass
-
-        @property
-        def unwrapped(self):
-            return self
-
-    class _Space:
-        def sample(self):
-            raise NotImplementedError
-
-    class Box(_Space):
-        def __init__(self, low, high, shape=None, dtype=np.float32):
-            self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
-
-        def sample(self):
-            return np.random.randint(self.low, self.high + 1, size=self.shape).astype(self.dtype)
-
-    class Discrete(_Space):
-        def __init__(self, n):
-            self.n = n
-
-        def sample(self):
-            return int(np.random.randint(0, self.n))
-
-    class Tuple(_Space):
-        def __init__(self, spaces):
-            self.spaces = tuple(spaces)
-
-        def sample(self):
-            return tuple(s.sample() for s in self.spaces)
-
-    spaces = types.ModuleType("gymnasium.spaces")
-    spaces.Box, spaces.Discrete, spaces.Tuple = Box, Discrete, Tuple
-    envs = types.ModuleType("gymnasium.envs")
-    registration = types.ModuleType("gymnasium.envs.registration")
-    _registry = {}
-
-    def register(id, entry_point=None, **kw):
-        _registry[id] = (entry_point, kw)
-
-    registration.register = register
-    registration.registry = _registry
-    envs.registration = registration
-    gym.Env, gym.spaces, gym.envs = Env, spaces, envs
-    gym.register = register
-    sys.modules["gymnasium"] = gym
-    sys.modules["gymnasium.spaces"] = spaces
-    sys.modules["gymnasium.envs"] = envs
-    sys.modules["gymnasium.envs.registration"] = registration
+    """tests/gymnasium_stub.py (one stub for the whole test-suite)."""
+    tests = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")
+    if tests not in sys.path:
+        sys.path.insert(0, tests)
+    import gymnasium_stub
+    gymnasium_stub.install()
 
 
 _cache = {}

@@ -381,3 +381,45 @@ def check_turn_tree_vs_oracle(ops, lo, hi, dice):
         assert tree.launches <= 2 * (4 if d1 == d2 else 2)
         total += nref
     return total
+
+
+def list_hash_np(actions, counts, cap):
+    """sum_k act[k] * weight(k) mod 2^64 over the first min(count, cap) stored actions (o_selfplay_trace's checksum)."""
+    w = O.list_weights(cap).view(np.uint64)
+    k = np.minimum(counts, cap)
+    mask = np.arange(cap)[None, :] < k[:, None]
+    with np.errstate(over="ignore"):
+        return (np.where(mask, actions.view(np.uint64), 0) * w[None, :]).sum(1, dtype=np.uint64).view(np.int64)
+
+
+def check_trace_vs_backend(backend, n, T, seed, env_base=5, cap=16, flags=2, action_mode=None, max_episode_steps=0,
+                           threads=4):
+    """The oracle's bulk trace (o_selfplay_trace, what the full-size GPU parity test and bench.py compare against)
+    versus step-by-step calls of the backend: every record field at every step, and the accumulated stats."""
+    rng = np.random.default_rng(seed ^ 0x7A5E)
+    words = None
+    if action_mode == "index":
+        words = rng.integers(-3, 40, (T, n)).astype(np.int32)
+    elif action_mode == "fraction":
+        words = rng.integers(0, 1 << 32, (T, n), dtype=np.uint64).astype(np.uint32).view(np.int32)
+    tr = O.selfplay_trace(seed, env_base, n, T, step0=0, words=words, word_mode=0 if action_mode == "index" else 1,
+                          cap=cap, reward_mode=flags & 1, autoreset=bool(flags & 2),
+                          max_episode_steps=max_episode_steps, threads=threads)
+    lo, hi = backend.reset(n, env_base=env_base, seed=seed, step=0)
+    stats = np.zeros(8, np.int64)
+    for t in range(T):
+        out = backend.step_full(lo, hi, env_base=env_base, seed=seed, step=t + 1, cap=cap,
+                                action_idx=None if words is None else words[t],
+                                flags=flags | (32 if action_mode == "fraction" else 0), max_episode_steps=max_episode_steps)
+        assert (lo == tr["lo"][t]).all() and (hi == tr["hi"][t]).all(), t
+        assert (out["counts"] == tr["count"][t]).all() and (out["dice"] == tr["dice"][t]).all(), t
+        assert (out["chosen"].view(np.int64) == tr["chosen"][t]).all(), t
+        assert (out["reward"] == tr["reward"][t]).all(), t
+        assert ((out["done"] & 1) | (out["trunc"] << 1) == tr["done"][t]).all(), t
+        assert (list_hash_np(out["actions"], out["counts"], cap) == tr["hash"][t]).all(), t
+        st = out["stats"]
+        stats[:6] += st[:6]
+        stats[6] = max(stats[6], st[6])
+        stats[7] += st[7]
+    assert (stats == tr["stats"]).all(), (stats, tr["stats"])
+    return tr["turns"], int(tr["stats"][0])

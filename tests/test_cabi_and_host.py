@@ -20,6 +20,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_cabi.exported_symbols())
+    # and the other way round: every narde_* symbol the product library exports is declared (no debug hooks, no
+    # undeclared entry points)
+    import subprocess
+    nm = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (narde_[A-Za-z0-9_]+)$", nm, flags=re.M))
+    assert exported == declared, exported ^ declared
     assert lib.narde_abi_version() == 1 and lib.narde_build_arch() == b"sm_100a"
 
 

@@ -175,3 +175,16 @@ def test_block_kernel_fallback_paths(hostsim):
         finally:
             hostsim.lib.hs_set_small_batch(C.c_int64(16384))
             hostsim.lib.hs_set_force_slow(C.c_int(0))
+
+
+def test_oracle_bulk_trace_equals_stepwise_hostsim(hostsim):
+    """o_selfplay_trace (the C bulk trace the full-size GPU parity test and bench.py compare against) agrees field by
+    field with step-by-step calls: Philox policy, caller indices / fractions, TimeLimit truncation, no auto-reset."""
+    turns, eps = P.check_trace_vs_backend(hostsim, 300, 260, 0xBEEF, cap=16)
+    assert turns == 300 * 260 and eps > 300
+    P.check_trace_vs_backend(hostsim, 200, 120, 11, action_mode="index", cap=8)
+    P.check_trace_vs_backend(hostsim, 200, 120, 12, action_mode="fraction", cap=64)
+    _, eps = P.check_trace_vs_backend(hostsim, 150, 130, 13, max_episode_steps=40, cap=4)
+    assert eps >= 150 * 3                                   # every env truncated three times
+    turns, _ = P.check_trace_vs_backend(hostsim, 150, 260, 14, flags=1, cap=4)   # mover reward, finished envs idle
+    assert turns < 150 * 260

@@ -93,12 +93,12 @@ def test_mlp_cluster_pair_variant_is_bit_identical():
     for rows in (40000, 129, 1, 38017):
         lo, hi = env.lo[:rows].contiguous(), env.hi[:rows].contiguous()
         a_q, a_s = mlp.forward_states(lo, hi), mlp.score_states(lo, hi)
-        lib.narde_debug_mlp_pair(1)
+        lib.narde_mlp_use_cluster_pair(1)
         try:
             b_q, b_s = mlp.forward_states(lo, hi), mlp.score_states(lo, hi)
             torch.cuda.synchronize()
         finally:
-            lib.narde_debug_mlp_pair(0)
+            lib.narde_mlp_use_cluster_pair(0)
         assert torch.equal(a_q, b_q) and torch.equal(a_s, b_s), rows
 
 

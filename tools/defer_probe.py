@@ -3,6 +3,7 @@
 an upper bound of what the exact kernel's tail and the exact in-item arithmetic cost."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["NARDE_B200_DEBUG_HOOKS"] = "1"   # libnarde_b200_debug.so: build it first with `python -m gym_narde_b200.build --debug-hooks`
 import torch
 from gym_narde_b200 import VecNardeEnv, _cabi
 

@@ -2,6 +2,7 @@
 import ctypes as C
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["NARDE_B200_DEBUG_HOOKS"] = "1"   # libnarde_b200_debug.so: build it first with `python -m gym_narde_b200.build --debug-hooks`
 import numpy as np
 import torch
 from gym_narde_b200 import VecNardeEnv, _cabi
