@@ -496,7 +496,7 @@ def config3_enumeration_microbench(torch, dev, args, timed_loop, peak):
     actions = torch.zeros((n, cap), dtype=torch.int64, device=dev)
     counts = torch.zeros(n, dtype=torch.int32, device=dev)
     ovf = torch.zeros(n, dtype=torch.uint8, device=dev)
-    ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    ws = torch.zeros(_cabi.workspace_ints(n), dtype=torch.int32, device=dev)
     run = lambda: _cabi.enumerate_actions_fast(lo, hi, dice, actions, counts, ovf, ws)
     for _ in range(3):
         run()

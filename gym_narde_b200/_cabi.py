@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libnarde_b200.so")
 if os.environ.get("NARDE_B200_DEBUG_HOOKS") == "1":   # measurement tools only (tools/*.py): the -DNARDE_DEBUG_HOOKS build
     LIB_PATH = os.path.join(_HERE, "libnarde_b200_debug.so")
 
+ABI_VERSION = 2
 # flags / bits (include/narde_b200.h)
 REWARD_MOVER12 = 1
 AUTORESET = 2
@@ -26,6 +27,13 @@ MAX_HALF_MOVES = 96
 NUM_STATS = 8
 STAT_NAMES = ("episodes", "white_wins", "black_wins", "mars", "episode_steps", "legal_actions",
               "max_actions", "overflows")
+
+
+
+def workspace_ints(n):
+    """NARDE_WORKSPACE_INTS(n), include/narde_b200.h."""
+    return int(n) + 3
+
 
 _vp, _i64, _u64, _i32, _int = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_int
 
@@ -81,7 +89,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
         fn.argtypes = argtypes
         fn.restype = restype
-    if lib.narde_abi_version() != 1:
+    if lib.narde_abi_version() != ABI_VERSION:
         raise NardeCudaError("libnarde_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -174,8 +182,8 @@ def enumerate_actions_fast(lo, hi, dice, actions, counts, overflow=None, workspa
     import torch
 
     cap = actions.shape[1] if actions is not None else 0
-    if workspace is not None and workspace.numel() < lo.shape[0] + 1:
-        raise NardeCudaError("workspace must hold n + 1 int32")
+    if workspace is not None and workspace.numel() < workspace_ints(lo.shape[0]):
+        raise NardeCudaError("workspace must hold NARDE_WORKSPACE_INTS(n) = n + 3 int32")
     rc = load().narde_enumerate_fast(_ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"),
                                      _ptr(dice, torch.uint8, "dice"), lo.shape[0], cap,
                                      _ptr(actions, torch.int64, "actions"), _ptr(counts, torch.int32, "counts"),
@@ -190,8 +198,8 @@ def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actio
     import torch
 
     cap = actions.shape[1] if actions is not None else 0
-    if workspace is not None and workspace.numel() < lo.shape[0] + (2 if flags & DEVICE_ADVANCE else 1):
-        raise NardeCudaError("workspace must hold n + 1 int32 (n + 2 with DEVICE_ADVANCE)")
+    if workspace is not None and workspace.numel() < workspace_ints(lo.shape[0]):
+        raise NardeCudaError("workspace must hold NARDE_WORKSPACE_INTS(n) = n + 3 int32")
     rc = load().narde_step_full(
         _ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"), lo.shape[0], env_base, seed, step,
         _ptr(dice_in, torch.uint8, "dice_in"), _ptr(action_idx, torch.int32, "action_idx"), cap,

@@ -36,7 +36,7 @@ class AfterstateActor:
         self.dice = t.zeros((n, 2), dtype=t.uint8, device=dev)
         self.lib = _cabi.load()
         self._graph = None
-        self._enum_ws = t.zeros(n + 1, dtype=t.int32, device=dev)
+        self._enum_ws = t.zeros(_cabi.workspace_ints(n), dtype=t.int32, device=dev)
 
     def _stream(self):
         return C.c_void_p(self.env.torch.cuda.current_stream().cuda_stream)

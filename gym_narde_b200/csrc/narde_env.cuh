@@ -86,6 +86,11 @@ struct StepFullArgs {
   const uint64_t* step_dev;
   // F_DEVICE_ADVANCE: arrival counter of the exact kernel's CTAs; the last one resets the list and adds 1 to *step_dev
   int32_t* ticket;
+  // publication of the deferred list to the exact kernel (a programmatic dependent launch that starts before the
+  // main kernel has completed): every main CTA adds 1 with release semantics after pushing its entries, the exact
+  // kernel acquires `arrivals == n_primary` before it reads the list
+  int32_t* arrivals;
+  int32_t n_primary;
 };
 
 // The index of the action to play among `count` legal ones: the caller's action_idx[i] (clamped; or,

@@ -268,9 +268,13 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   BS::ph_env_totals(tid, sh);
   if (DEFER) {
     BS::ph_defer_push(tid, sh, valid, i, A);
-    __threadfence();  // the list entry is visible device-wide before this CTA lets the dependent grid go
+    __threadfence();
   }
   __syncthreads();
+  // Publication of this CTA's list entries: the barrier above orders every thread's pushes before thread 0's
+  // release-add; k_step_deferred acquires "all main CTAs have arrived" before it reads the list (the visibility
+  // of a primary grid's writes is otherwise only guaranteed after griddepcontrol.wait, i.e. after its completion).
+  if (DEFER && tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(A.arrivals) : "memory");
   // Programmatic dependent launch: k_step_deferred may start as soon as every CTA is past this point,
   // i.e. while the action lists and Box(198) rows of the other envs are still being written.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -339,8 +343,16 @@ __global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, 
   __shared__ float4 lut[16];
   obs_lut_init(lut);
   const int tid = threadIdx.x;
-  // launched as a programmatic dependent of k_step_full_v2: every CTA of it has published its deferred
-  // envs (fence + trigger) before this grid starts; read the list through L2
+  // Launched as a programmatic dependent of k_step_full_v2: this grid starts once every main CTA has executed its
+  // trigger, which each does AFTER its release-add to `arrivals` -- so the acquire below never really waits, it
+  // makes the list entries of all main CTAs formally visible here although the main grid is still running.
+  if (tid == 0) {
+    int32_t seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(A.arrivals) : "memory");
+    } while (seen < A.n_primary);
+  }
+  __syncthreads();
   const int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
 #ifdef NARDE_DEBUG_HOOKS
 #define DMARK(k)                                                                                      \
@@ -422,6 +434,7 @@ __global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, 
       if (atomicAdd(A.ticket, 1) == (int)gridDim.x - 1) {
         *A.defer_count = 0;
         *A.ticket = 0;
+        *A.arrivals = 0;
         *const_cast<uint64_t*>(A.step_dev) = A.step;
         __threadfence();
       }
@@ -693,6 +706,8 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.defer_list = nullptr;
   A.step_dev = step_dev;
   A.ticket = nullptr;
+  A.arrivals = nullptr;
+  A.n_primary = 0;
   const bool dev_advance = (flags & NARDE_DEVICE_ADVANCE) != 0;
   if (dev_advance && (!workspace || !step_dev || (flags & (NARDE_PER_THREAD_KERNEL | NARDE_ENUMERATE_ONLY)))) return -1;
   if (flags & NARDE_PER_THREAD_KERNEL) {
@@ -700,15 +715,18 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
     return launch_status();
   }
-  // Workspace: [0] = number of deferred envs, [1..n] = their indices.
+  // Workspace (NARDE_WORKSPACE_INTS(n) words): [0] = number of deferred envs, [1] = arrival counter of the exact
+  // kernel's CTAs (DEVICE_ADVANCE), [2] = arrival counter of the main kernel's CTAs, [3..] = the deferred indices.
   if (workspace) {
     if ((((uintptr_t)workspace) & 3u) != 0) return -1;
     A.defer_count = workspace;
-    A.defer_list = workspace + 1;
-    if (dev_advance) {  // [n + 1] = arrival counter; list length and counter are zero on entry and again on exit
-      A.ticket = workspace + n + 1;
+    A.arrivals = workspace + 2;
+    A.defer_list = workspace + 3;
+    A.n_primary = (int32_t)(n <= kSmallBatch ? (n + 31) / 32 : (n + 127) / 128);
+    if (dev_advance) {  // the three header words are zero on entry and again on exit
+      A.ticket = workspace + 1;
     } else {
-      cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t), (cudaStream_t)stream);
+      cudaError_t e = cudaMemsetAsync(workspace, 0, 3 * sizeof(int32_t), (cudaStream_t)stream);
       if (e != cudaSuccess) return (int)e;
     }
   }

@@ -61,12 +61,12 @@ class VecNardeEnv:
         per = -(-n // (128 * chunks)) * 128
         self._chunks = [(b, min(b + per, n)) for b in range(0, n, per)]
         self._streams = [torch.cuda.Stream(device=dev) for _ in self._chunks[1:]]
-        # deferred-turn lists (see narde_b200.h: (n + 1) int32 per call)
-        self._workspaces = [torch.zeros((e - b) + 1, dtype=torch.int32, device=dev) for b, e in self._chunks]
-        self._enum_ws = torch.zeros(n + 1, dtype=torch.int32, device=dev)   # get_valid_actions' deferred-turn list
+        # deferred-turn lists (see narde_b200.h: NARDE_WORKSPACE_INTS(n) int32 per call)
+        self._workspaces = [torch.zeros(_cabi.workspace_ints(e - b), dtype=torch.int32, device=dev) for b, e in self._chunks]
+        self._enum_ws = torch.zeros(_cabi.workspace_ints(n), dtype=torch.int32, device=dev)   # get_valid_actions' deferred-turn list
         # graph-replayed steps of an unchunked env let the kernels advance the step counter and clear the list
         # themselves (DEVICE_ADVANCE: two graph nodes fewer per step); that workspace is never shared with other calls
-        self._ws_adv = torch.zeros(n + 2, dtype=torch.int32, device=dev) if len(self._chunks) == 1 else None
+        self._ws_adv = torch.zeros(_cabi.workspace_ints(n), dtype=torch.int32, device=dev) if len(self._chunks) == 1 else None
         # device-resident copy of step_count: kernel arguments stay frozen, so a step is one graph replay
         self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.action_in = torch.zeros(n, dtype=torch.int32, device=dev)   # persistent policy input (graph-replayable)

@@ -36,8 +36,12 @@
 extern "C" {
 #endif
 
-#define NARDE_ABI_VERSION 1
+#define NARDE_ABI_VERSION 2
 #define NARDE_MAX_HALF_MOVES 96 /* 4 dice x 24 points */
+/* int32 words of the optional `workspace` of narde_step_full / narde_enumerate_fast for n environments:
+ * [0] number of deferred envs, [1] arrival counter of the exact kernel's CTAs, [2] arrival counter of the main
+ * kernel's CTAs (release/acquire publication of the list to the programmatic dependent), [3..n+2] the list */
+#define NARDE_WORKSPACE_INTS(n) ((n) + 3)
 
 /* narde_step_full flags */
 #define NARDE_REWARD_MOVER12 1   /* reward 1/2 to the mover (narde_env.py:134-141); default: README +1 iff WHITE wins */
@@ -52,7 +56,7 @@ extern "C" {
 #define NARDE_DEVICE_ADVANCE 256   /* narde_step_full with workspace and step_dev: the step index is *step_dev + 1, and the kernels
                                     themselves store it back and clear the workspace when the step is complete -- no memset and no
                                     counter kernel in front of every step (two nodes of a replayed CUDA graph, ~2 us each).  The
-                                    workspace then holds n + 2 ints, is zero before the first call and is left zero by every call;
+                                    workspace's three header words are zero before the first call and are left zero by every call;
                                     it must not be shared with calls that do not set this flag. */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 
@@ -110,7 +114,7 @@ int narde_enumerate(const void *lo, const void *hi, const uint8_t *dice, int64_t
 
 /* Same results as narde_enumerate through the CTA-cooperative kernels of the fused step (work items dealt
  * evenly over a 128-environment CTA, order-dependent doubles turns handed to the exact kernel when a
- * workspace of (n + 1) int32 is given): the fast path VecNardeEnv.get_valid_actions uses. */
+ * workspace of NARDE_WORKSPACE_INTS(n) int32 is given): the fast path VecNardeEnv.get_valid_actions uses. */
 int narde_enumerate_fast(const void *lo, const void *hi, const uint8_t *dice, int64_t n, int32_t cap,
                          uint64_t *actions, int32_t *counts, uint8_t *overflow, int32_t *workspace,
                          void *stream);
@@ -121,7 +125,7 @@ int narde_enumerate_fast(const void *lo, const void *hi, const uint8_t *dice, in
  *   choice (action_idx[i], clamped; NULL = Philox-uniform) -> apply -> termination / reward
  *   -> player switch -> optional auto-reset -> Box(198) observation (README.md:44-102).
  * Any of actions, counts, dice_out, obs198, reward, done, truncated, chosen, stats may be NULL.
- * workspace: optional scratch of (n + 1) int32 owned by the caller.  With it, the rare doubles
+ * workspace: optional scratch of NARDE_WORKSPACE_INTS(n) int32 owned by the caller.  With it, the rare doubles
  * turns in which the 6-prime block rule makes the move ORDER matter are handed to a second,
  * CTA-per-environment kernel (a programmatic dependent launch that overlaps the tail of the main
  * kernel; same results, shorter tail); without it they are resolved inline.

@@ -231,9 +231,9 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
   if (workspace) {
-    workspace[0] = 0;
+    workspace[0] = workspace[1] = workspace[2] = 0;   // NARDE_WORKSPACE_INTS layout (include/narde_b200.h)
     A.defer_count = workspace;
-    A.defer_list = workspace + 1;
+    A.defer_list = workspace + 3;
   }
   // same dispatch as narde_step_full: one-warp CTAs of 32 envs for small batches (g_small_batch can be
   // lowered by the tests so that both tile sizes are exercised on small inputs)

@@ -111,7 +111,7 @@ def test_benchmark_config_131072_envs_300_graph_replayed_steps_vs_oracle():
         rec.record(rew, env.done, env.trunc)
     # the timed path: one graph of two nodes (main kernel + programmatic dependent) that advances its own counter
     assert "random" in env._graphs and env._ws_adv is not None and env.use_graph
-    assert int(env._step_dev.item()) == T and int(env._ws_adv.abs().sum().item()) == 0
+    assert int(env._step_dev.item()) == T and env._ws_adv[:3].tolist() == [0, 0, 0]
     turns, stats = rec.compare(seed, base)
     assert turns == n * T
     assert rec.obs_ok, "a Box(198) batch differed from the rows re-derived from the state planes"
