@@ -48,6 +48,8 @@ _SIGNATURES = {
     "narde_enumerate_fast": ([_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_step_full": ([_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                          _vp, _vp, _i32, _i32, _vp, _vp, _vp], _int),
+    "narde_step_full_mirror": ([_vp, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp], _int),
     "narde_advance_counter": ([_vp, _vp], _int),
     "narde_mlp_forward": ([_vp, _i64, _vp, _vp, _vp, _vp], _int),
     "narde_mlp_score": ([_vp, _i64, _vp, _vp, _vp, _vp], _int),
@@ -194,13 +196,13 @@ def enumerate_actions_fast(lo, hi, dice, actions, counts, overflow=None, workspa
 
 def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actions=None, counts=None,
               dice_out=None, chosen=None, obs198=None, reward=None, done=None, stats=None, flags=0,
-              max_episode_steps=0, truncated=None, workspace=None, step_dev=None):
+              max_episode_steps=0, truncated=None, workspace=None, step_dev=None, mirror_lo=None, mirror_hi=None):
     import torch
 
     cap = actions.shape[1] if actions is not None else 0
     if workspace is not None and workspace.numel() < workspace_ints(lo.shape[0]):
         raise NardeCudaError("workspace must hold NARDE_WORKSPACE_INTS(n) = n + 3 int32")
-    rc = load().narde_step_full(
+    rc = load().narde_step_full_mirror(
         _ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"), lo.shape[0], env_base, seed, step,
         _ptr(dice_in, torch.uint8, "dice_in"), _ptr(action_idx, torch.int32, "action_idx"), cap,
         _ptr(actions, torch.int64, "actions"), _ptr(counts, torch.int32, "counts"),
@@ -208,7 +210,7 @@ def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actio
         _ptr(obs198, torch.float32, "obs198"), _ptr(reward, torch.float32, "reward"),
         _ptr(done, torch.uint8, "done"), _ptr(truncated, torch.uint8, "truncated"), _ptr(stats, torch.int64, "stats"),
         flags, max_episode_steps, _ptr(workspace, torch.int32, "workspace"), _ptr(step_dev, torch.int64, "step_dev"),
-        _stream())
+        _ptr(mirror_lo, torch.uint8, "mirror_lo"), _ptr(mirror_hi, torch.uint8, "mirror_hi"), _stream())
     _check(rc, "narde_step_full")
 
 

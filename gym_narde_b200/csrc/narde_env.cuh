@@ -91,6 +91,10 @@ struct StepFullArgs {
   // kernel acquires `arrivals == n_primary` before it reads the list
   int32_t* arrivals;
   int32_t n_primary;
+  // optional second destination of the state planes (16-byte lanes like lo / hi): pinned host memory of a host-side
+  // consumer, for which the 32-byte record IS the observation (gym_narde_b200.expand_obs198 decodes it to Box(198))
+  void* mirror_lo;
+  void* mirror_hi;
 };
 
 // The index of the action to play among `count` legal ones: the caller's action_idx[i] (clamped; or,

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
     State s = ld_state(lo, hi, i);
     step_full_env(s, i, A, L);
     st_state(lo, hi, i, s);
+    if (A.mirror_lo) st_state((uint4*)A.mirror_lo, (uint4*)A.mirror_hi, i, s);
     sm[threadIdx.x] = s;
   }
   if (stats) {
@@ -302,7 +303,10 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   __syncthreads();
   PHASE_MARK(8);
   // deferred envs belong to k_step_deferred, which may already be running: never store their state here
-  if (valid && !sh.defer[tid] && !(A.flags & F_ENUMERATE_ONLY)) st_state(lo, hi, i, sh.st[tid]);
+  if (valid && !sh.defer[tid] && !(A.flags & F_ENUMERATE_ONLY)) {
+    st_state(lo, hi, i, sh.st[tid]);
+    if (A.mirror_lo) st_state((uint4*)A.mirror_lo, (uint4*)A.mirror_hi, i, sh.st[tid]);  // posted PCIe writes (zero-copy)
+  }
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
     int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
@@ -402,7 +406,10 @@ __global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, 
       State st = sh.st;
       complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
       sh.st = st;
-      if (!(A.flags & F_ENUMERATE_ONLY)) st_state(lo, hi, i, st);
+      if (!(A.flags & F_ENUMERATE_ONLY)) {
+        st_state(lo, hi, i, st);
+        if (A.mirror_lo) st_state((uint4*)A.mirror_lo, (uint4*)A.mirror_hi, i, st);
+      }
       if (stats) {
         int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
         for (int k = 0; k < 6; k++)
@@ -682,7 +689,19 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
                     const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts, uint8_t* dice_out,
                     uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
                     int32_t flags, int32_t max_episode_steps, int32_t* workspace, const uint64_t* step_dev, void* stream) {
+  return narde_step_full_mirror(lo, hi, n, env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out, chosen,
+                                obs198, reward, done, truncated, stats, flags, max_episode_steps, workspace, step_dev, nullptr,
+                                nullptr, stream);
+}
+
+int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
+                           const uint8_t* dice_in, const int32_t* action_idx, int32_t cap, uint64_t* actions, int32_t* counts,
+                           uint8_t* dice_out, uint64_t* chosen, float* obs198, float* reward, uint8_t* done,
+                           uint8_t* truncated, int64_t* stats, int32_t flags, int32_t max_episode_steps, int32_t* workspace,
+                           const uint64_t* step_dev, void* mirror_lo, void* mirror_hi, void* stream) {
   if (n == 0) return 0;
+  if ((mirror_lo == nullptr) != (mirror_hi == nullptr) || !aligned16(mirror_lo) || !aligned16(mirror_hi)) return -1;
+  if (mirror_lo && (flags & NARDE_ENUMERATE_ONLY)) return -1;
   if (n < 0 || cap < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
   if (obs198 && (((uintptr_t)obs198) & 7u) != 0) return -1;
   if (n == 0) return 0;
@@ -708,6 +727,8 @@ int narde_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   A.ticket = nullptr;
   A.arrivals = nullptr;
   A.n_primary = 0;
+  A.mirror_lo = mirror_lo;
+  A.mirror_hi = mirror_hi;
   const bool dev_advance = (flags & NARDE_DEVICE_ADVANCE) != 0;
   if (dev_advance && (!workspace || !step_dev || (flags & (NARDE_PER_THREAD_KERNEL | NARDE_ENUMERATE_ONLY)))) return -1;
   if (flags & NARDE_PER_THREAD_KERNEL) {

@@ -85,3 +85,51 @@ def rotate_board(board):
     """Mover-frame view for Black (gym_narde/envs/narde.py:16-17)."""
     board = np.asarray(board)
     return np.concatenate((-board[..., 12:], -board[..., :12]), axis=-1)
+
+
+_OBS_LUT = None
+
+
+def expand_obs198(lo, hi, out=None):
+    """Decode packed state records into Box(198) rows (README.md:44-102): the observation a host-side consumer of
+    VecNardeEnv.step_host(obs="packed") reads, bit-equal to what narde_obs198 / the fused step write on the device.
+
+    CUDA tensors [n,16] uint8 -> the narde_obs198 kernel (returns a float32 CUDA tensor [n,198]);
+    numpy arrays / host tensors -> a table lookup on the host (returns float32 numpy [n,198]): this is a decoder of
+    the wire format, not an alternative to the kernels (nothing in the product calls it)."""
+    try:
+        import torch
+        is_t = isinstance(lo, torch.Tensor)
+    except ImportError:
+        is_t = False
+    if is_t and lo.is_cuda:
+        from . import _cabi
+        if out is None:
+            out = torch.empty((lo.shape[0], 198), dtype=torch.float32, device=lo.device)
+        _cabi.obs198(lo, hi, out)
+        return out
+    global _OBS_LUT
+    if _OBS_LUT is None:
+        # per signed point count v in [-15, 15]: WHITE's four features then BLACK's ([n>=1, n>=2, n>=3, (n-3)/2])
+        lut = np.zeros((256, 8), np.float32)
+        for v in range(-15, 16):
+            for c, n in ((0, max(v, 0)), (1, max(-v, 0))):
+                lut[v & 0xFF, 4 * c:4 * c + 4] = (n >= 1, n >= 2, n >= 3, (n - 3) / 2.0 if n > 3 else 0.0)
+        _OBS_LUT = (lut, np.array([np.float32(k / 15.0) for k in range(256)], np.float32))
+    lut, off15 = _OBS_LUT
+    lo = np.asarray(lo, dtype=np.uint8).reshape(-1, 16)
+    hi = np.asarray(hi, dtype=np.uint8).reshape(-1, 16)
+    n = lo.shape[0]
+    if out is None:
+        out = np.zeros((n, 198), np.float32)
+    f = lut[np.concatenate([lo, hi[:, :8]], axis=1)]            # [n, 24, 8]
+    out[:, 0:96] = f[:, :, :4].reshape(n, 96)
+    out[:, 96] = 0.0                                             # bar: no hitting in Narde (narde.py:71)
+    out[:, 97] = off15[hi[:, 8]]
+    out[:, 98:194] = f[:, :, 4:].reshape(n, 96)
+    out[:, 194] = 0.0
+    out[:, 195] = off15[hi[:, 9]]
+    white = hi[:, 10].view(np.int8) == 1
+    out[:, 196] = white
+    out[:, 197] = ~white
+    return out

@@ -221,11 +221,14 @@ class VecNardeEnv:
                          "reward": t.zeros(n, dtype=t.float32).pin_memory(),
                          "done": t.zeros(n, dtype=t.uint8).pin_memory(),
                          "truncated": t.zeros(n, dtype=t.uint8).pin_memory(),
-                         "result": t.zeros(n, dtype=t.uint8).pin_memory()}
+                         "result": t.zeros(n, dtype=t.uint8).pin_memory(),
+                         # obs="packed": the state planes after the turn, the 32-byte encoding of Box(198)
+                         "lo": t.zeros((n, 16), dtype=t.uint8).pin_memory(),
+                         "hi": t.zeros((n, 16), dtype=t.uint8).pin_memory()}
             self._hio_graphs = {}
         return self._hio
 
-    def step_host(self, fraction=False, packed=False, actions=None, dma_in=False):
+    def step_host(self, fraction=False, packed=False, actions=None, dma_in=False, obs=None):
         """One lock-step turn driven from the host (rules="full") with ZERO-COPY I/O: every CTA of the fused step
         fetches its envs' action words from the pinned host buffer with one bulk asynchronous copy (512 B over
         PCIe into shared memory, overlapped with the state load and the dice), and reward / done / truncated are
@@ -238,7 +241,11 @@ class VecNardeEnv:
         packed=True: one byte per env in host_io()["result"] instead (bit 0 terminated, bit 1 truncated, bits 2-3
         the reward 0/1/2) -- a sixth of the PCIe write traffic.
         actions: another pinned int32 [N] host tensor to read this turn's choices from (e.g. a row of a ring the
-        policy fills ahead); one graph is cached per buffer (up to 32)."""
+        policy fills ahead); one graph is cached per buffer (up to 32).
+        obs="packed": the OBSERVATION crosses to the host as well, in its packed form -- the kernel also writes every
+        env's 32-byte state record (after the turn, after an auto-reset) into host_io()["lo"] / ["hi"]; Box(198) is a
+        function of exactly those bytes (gym_narde_b200.expand_obs198(lo, hi) gives the float32 [N,198] rows, bit-equal
+        to the device's), so 32 B per env cross PCIe instead of 792."""
         t = self.torch
         if self.rules != "full":
             raise ValueError("step_host needs rules='full'")
@@ -250,7 +257,11 @@ class VecNardeEnv:
         src = io["actions"] if actions is None else actions
         if not (src.is_pinned() and src.dtype == t.int32 and src.is_contiguous() and src.numel() == self.num_envs):
             raise _cabi.NardeCudaError("step_host actions must be a pinned contiguous int32 [N] host tensor")
-        key = (src.data_ptr(), bool(fraction), bool(packed), bool(dma_in))
+        if obs not in (None, "packed"):
+            raise ValueError("obs must be None (Box(198) stays on the device) or 'packed'")
+        if len(self._chunks) != 1:
+            raise _cabi.NardeCudaError("step_host needs an unchunked env (chunks=1)")
+        key = (src.data_ptr(), bool(fraction), bool(packed), bool(dma_in), obs)
         ent = self._hio_graphs.get(key)
         g = ent[0] if ent is not None else None
         if g is None and len(self._hio_graphs) >= 32:
@@ -275,7 +286,9 @@ class VecNardeEnv:
                                 reward=None if packed else io["reward"], done=io["result"] if packed else io["done"],
                                 stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
                                 truncated=None if packed else io["truncated"],
-                                workspace=self._ws_adv if adv else self._workspaces[0], step_dev=self._step_dev)
+                                workspace=self._ws_adv if adv else self._workspaces[0], step_dev=self._step_dev,
+                                mirror_lo=io["lo"] if obs == "packed" else None,
+                                mirror_hi=io["hi"] if obs == "packed" else None)
             self._hio_graphs[key] = (g, src)
         g.replay()
         return io

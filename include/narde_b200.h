@@ -138,6 +138,17 @@ int narde_step_full(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t se
                     int32_t flags, int32_t max_episode_steps, int32_t *workspace, const uint64_t *step_dev,
                     void *stream);
 
+/* narde_step_full with a second destination for the state planes: mirror_lo / mirror_hi ([n] 16-byte lanes, e.g.
+ * pinned HOST memory) receive every environment's state after the turn as well.  For a host-side consumer the
+ * 32-byte record is a lossless encoding of the Box(198) observation (README.md:44-102 is a function of board, off
+ * counts and side to move): 32 B per env cross PCIe instead of 792 (gym_narde_b200.expand_obs198 decodes it). */
+int narde_step_full_mirror(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
+                           const uint8_t *dice_in, const int32_t *action_idx, int32_t cap, uint64_t *actions,
+                           int32_t *counts, uint8_t *dice_out, uint64_t *chosen, float *obs198, float *reward,
+                           uint8_t *done, uint8_t *truncated, int64_t *stats, int32_t flags, int32_t max_episode_steps,
+                           int32_t *workspace, const uint64_t *step_dev, void *mirror_lo, void *mirror_hi,
+                           void *stream);
+
 /* Observations of the current states: Box(198) float32 (README.md:44-102) / the reference's
  * mover-perspective int32[24] (narde_env.py:24-25). */
 int narde_obs198(const void *lo, const void *hi, int64_t n, float *obs198, void *stream);

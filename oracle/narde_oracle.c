@@ -675,8 +675,10 @@ int64_t o_selfplay_trace(uint64_t seed, uint32_t env_base, int n_envs, int n_ste
                          int64_t words_stride, int word_mode, int cap, int reward_mode, int autoreset,
                          int max_episode_steps, int64_t row_stride, uint8_t *out_lo, uint8_t *out_hi,
                          int64_t *out_chosen, int32_t *out_count, uint8_t *out_dice, uint8_t *out_done,
-                         float *out_reward, uint64_t *out_hash, int64_t *stats8) {
+                         float *out_reward, uint64_t *out_hash, int64_t *stats8, double *obs_checksum) {
   o_env *envs = (o_env *)malloc((size_t)n_envs * sizeof(o_env));
+  float obs[198];
+  double chk = 0.0;
   int *term = (int *)calloc((size_t)n_envs, sizeof(int));
   int *esteps = (int *)calloc((size_t)n_envs, sizeof(int));
   o_turn_action *scratch = (o_turn_action *)malloc(4096 * sizeof(o_turn_action));
@@ -757,6 +759,10 @@ int64_t o_selfplay_trace(uint64_t seed, uint32_t env_base, int n_envs, int n_ste
         }
         turns++;
       }
+      if (obs_checksum) { /* the CUDA step writes one Box(198) row per env turn: do that work here too */
+        o_obs198(e->game.board, e->game.borne_off_white, e->game.borne_off_black, e->current_player, obs);
+        for (int k = 0; k < 198; k++) chk += obs[k];
+      }
       if (out_lo && out_hi) o_pack_state(e, term[i], esteps[i], out_lo + 16 * r, out_hi + 16 * r);
       if (out_chosen) out_chosen[r] = (int64_t)chosen;
       if (out_count) out_count[r] = n;
@@ -771,6 +777,7 @@ int64_t o_selfplay_trace(uint64_t seed, uint32_t env_base, int n_envs, int n_ste
   }
   if (stats8)
     for (int k = 0; k < 8; k++) stats8[k] = st[k];
+  if (obs_checksum) *obs_checksum = chk;
   free(envs);
   free(term);
   free(esteps);

@@ -107,13 +107,14 @@ uint64_t o_list_weight(int k);
  * Every out_* array (each may be NULL) is [n_steps][row_stride]; row (t-1, i) describes env i after
  * turn step0+t: packed state, chosen action, legal-action count, dice, done bits (1 terminated,
  * 2 truncated), reward, checksum of the first min(count, cap) list entries.  stats8 = the counters
- * of include/narde_b200.h:62-71 over this call.  Returns the number of env turns played. */
+ * of include/narde_b200.h:62-71 over this call; obs_checksum (may be NULL): the Box(198) row of every env turn is
+ * computed (o_obs198) and summed into it.  Returns the number of env turns played. */
 int64_t o_selfplay_trace(uint64_t seed, uint32_t env_base, int n_envs, int n_steps, uint64_t step0,
                          const uint8_t *init_lo, const uint8_t *init_hi, const uint32_t *words,
                          int64_t words_stride, int word_mode, int cap, int reward_mode, int autoreset,
                          int max_episode_steps, int64_t row_stride, uint8_t *out_lo, uint8_t *out_hi,
                          int64_t *out_chosen, int32_t *out_count, uint8_t *out_dice, uint8_t *out_done,
-                         float *out_reward, uint64_t *out_hash, int64_t *stats8);
+                         float *out_reward, uint64_t *out_hash, int64_t *stats8, double *obs_checksum);
 /* get_valid_actions for n packed positions: count + checksum of the first min(count, cap) list entries */
 void o_enumerate_batch(const uint8_t *lo, const uint8_t *hi, const uint8_t *dice, int64_t n, int cap,
                        int32_t *out_count, uint64_t *out_hash);

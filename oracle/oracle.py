@@ -89,7 +89,7 @@ def lib():
         u8p, vp = C.POINTER(C.c_uint8), C.c_void_p
         L.o_selfplay_trace.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_uint64, vp, vp, vp, C.c_int64,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, vp,
-                                       vp, vp, vp, vp]
+                                       vp, vp, vp, vp, vp]
         L.o_selfplay_trace.restype = C.c_int64
         L.o_enumerate_batch.argtypes = [vp, vp, vp, C.c_int64, C.c_int, vp, vp]
         L.o_enumerate_batch.restype = None
@@ -253,7 +253,8 @@ def list_weights(cap):
 
 
 def selfplay_trace(seed, env_base, n_envs, n_steps, step0=0, init=None, words=None, word_mode=1, cap=64,
-                   reward_mode=0, autoreset=True, max_episode_steps=1000, threads=None, want_states=True):
+                   reward_mode=0, autoreset=True, max_episode_steps=1000, threads=None, want_states=True,
+                   with_obs=False):
     """o_selfplay_trace over envs [env_base, env_base + n_envs), split over `threads` host threads (ctypes
     releases the GIL; every thread plays a contiguous block of envs into the shared [n_steps, n_envs] arrays).
     init: (lo, hi) uint8 [n_envs, 16] start states or None (fresh games, roll-off at step0).
@@ -277,6 +278,7 @@ def selfplay_trace(seed, env_base, n_envs, n_steps, step0=0, init=None, words=No
     per = max(1, -(-n // threads))
     blocks = [(b, min(b + per, n)) for b in range(0, n, per)]
     stats = np.zeros((len(blocks), 8), np.int64)
+    obs_chk = np.zeros(len(blocks), np.float64)
 
     def ptr(a, off):
         return None if a is None else a.ctypes.data + off * a.itemsize
@@ -290,7 +292,7 @@ def selfplay_trace(seed, env_base, n_envs, n_steps, step0=0, init=None, words=No
             int(bool(autoreset)), int(max_episode_steps), n,
             ptr(out.get("lo"), 16 * b), ptr(out.get("hi"), 16 * b), ptr(out["chosen"], b), ptr(out["count"], b),
             ptr(out["dice"], 2 * b), ptr(out["done"], b), ptr(out["reward"], b), ptr(out["hash"], b),
-            stats[k].ctypes.data)
+            stats[k].ctypes.data, obs_chk[k:].ctypes.data if with_obs else None)
 
     if len(blocks) == 1:
         turns = run(0)
@@ -300,6 +302,7 @@ def selfplay_trace(seed, env_base, n_envs, n_steps, step0=0, init=None, words=No
     st = stats.sum(0)
     st[6] = stats[:, 6].max()
     out["stats"] = st
+    out["obs_checksum"] = float(obs_chk.sum())
     out["turns"] = int(turns)
     return out
 

@@ -108,6 +108,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
                  int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
+  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.mirror_lo = A.mirror_hi = nullptr;
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
     StepFullLocal L;
@@ -230,6 +231,7 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
                     int32_t flags, int32_t max_episode_steps, int32_t* workspace, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
+  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.mirror_lo = A.mirror_hi = nullptr;
   if (workspace) {
     workspace[0] = workspace[1] = workspace[2] = 0;   // NARDE_WORKSPACE_INTS layout (include/narde_b200.h)
     A.defer_count = workspace;

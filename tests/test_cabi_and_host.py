@@ -97,3 +97,17 @@ def test_state_pack_roundtrip():
     acts = [[(23, 17), (17, 11)], [(3, 'off')], [], [(5, 4), (4, 3), (3, 2), (2, 'off')]]
     for a in acts:
         assert S.decode_action(S.encode_action(a)) == a
+
+
+def test_expand_obs198_on_the_host_equals_the_oracle():
+    """gym_narde_b200.expand_obs198 (decoder of the packed observation a host consumer of step_host(obs="packed")
+    receives) against o_obs198 (README.md:44-102), bit for bit."""
+    import gym_narde_b200
+    import parity as P
+    from oracle import oracle as O
+    lo, hi = P.pack_corpus(P.selfplay_corpus(12, 3))
+    got = gym_narde_b200.expand_obs198(lo, hi)
+    u = S.unpack_states(lo, hi)
+    for i in range(lo.shape[0]):
+        ref = O.obs198(u["board"][i], int(u["off_w"][i]), int(u["off_b"][i]), int(u["turn"][i]))
+        assert (ref == got[i]).all(), i

@@ -176,3 +176,50 @@ def test_torch_obs198_encoder_equals_oracle():
     for i in range(lo.shape[0]):
         ref = O.obs198(u["board"][i], int(u["off_w"][i]), int(u["off_b"][i]), int(u["turn"][i]))
         assert (ref == got[i]).all(), i
+
+
+def test_step_host_packed_observation_is_lossless():
+    """step_host(obs="packed"): the state planes the kernel mirrors into pinned host memory equal the device planes,
+    and expanding them on the host gives the device's Box(198) batch bit for bit (deferred envs included)."""
+    import torch
+    import gym_narde_b200
+    from gym_narde_b200 import VecNardeEnv
+    for n in (N_FULL, 5000):
+        env = VecNardeEnv(n, seed=21, max_actions=64, env_base=17)
+        env.reset()
+        for _ in range(60):
+            env.step()
+        rows = torch.randint(-(1 << 31), (1 << 31) - 1, (4, n), dtype=torch.int64).to(torch.int32).pin_memory()
+        for t in range(12):
+            io = env.step_host(fraction=True, actions=rows[t % 4], obs="packed")
+            torch.cuda.synchronize()
+            assert torch.equal(io["lo"], env.lo.cpu()) and torch.equal(io["hi"], env.hi.cpu()), (n, t)
+            host_rows = gym_narde_b200.expand_obs198(io["lo"].numpy(), io["hi"].numpy())
+            assert (host_rows == env.obs.cpu().numpy()).all(), (n, t)
+            dev_rows = gym_narde_b200.expand_obs198(env.lo, env.hi)
+            assert torch.equal(dev_rows, env.obs)
+
+
+def test_config3_synthetic_positions_vs_oracle():
+    """BASELINE config 3's three strata (self-play / forced doubles / bear-off), 262 144 positions through
+    narde_enumerate_fast (main kernel + exact kernel for the order-dependent doubles), every position's count and
+    stored list against the oracle's o_enumerate_batch."""
+    import torch
+    from gym_narde_b200 import _cabi
+    from gym_narde_b200.workloads import config3_positions
+    n, cap = 1 << 18, 64
+    lo, hi, dice, strata = config3_positions("cuda", n=n, seed=1234)
+    actions = torch.zeros((n, cap), dtype=torch.int64, device="cuda")
+    counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ovf = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(_cabi.workspace_ints(n), dtype=torch.int32, device="cuda")
+    _cabi.enumerate_actions_fast(lo, hi, dice, actions, counts, ovf, ws)
+    w = torch.from_numpy(O.list_weights(cap)).cuda()
+    got_hash = _gpu_list_hash(torch, actions, counts, w).cpu().numpy()
+    want_counts, want_hash = O.enumerate_batch(lo.cpu().numpy(), hi.cpu().numpy(), dice.cpu().numpy(), cap)
+    assert (counts.cpu().numpy() == want_counts).all()
+    assert (got_hash == want_hash).all()
+    assert (ovf.cpu().numpy() == (want_counts > cap)).all()
+    assert int(ws[0].item()) > n // 200                     # the exact kernel had its ~2 % share
+    for name, (b, e) in strata.items():
+        assert want_counts[b:e].max() > 20, name

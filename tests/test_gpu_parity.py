@@ -263,4 +263,4 @@ def test_device_advance_mode_equals_host_stepped_calls():
     with pytest.raises(_cabi.NardeCudaError):
         call(b, 0, _cabi.DEVICE_ADVANCE, ws_b, None)
     with pytest.raises(_cabi.NardeCudaError):
-        call(b, 0, _cabi.DEVICE_ADVANCE, ws_a, ctr)
+        call(b, 0, _cabi.DEVICE_ADVANCE, ws_a[:n + 2], ctr)     # shorter than NARDE_WORKSPACE_INTS(n)
