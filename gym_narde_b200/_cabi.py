@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libnarde_b200.so")
 if os.environ.get("NARDE_B200_DEBUG_HOOKS") == "1":   # measurement tools only (tools/*.py): the -DNARDE_DEBUG_HOOKS build
     LIB_PATH = os.path.join(_HERE, "libnarde_b200_debug.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 # flags / bits (include/narde_b200.h)
 REWARD_MOVER12 = 1
 AUTORESET = 2
@@ -32,7 +32,7 @@ STAT_NAMES = ("episodes", "white_wins", "black_wins", "mars", "episode_steps", "
 
 def workspace_ints(n):
     """NARDE_WORKSPACE_INTS(n), include/narde_b200.h."""
-    return int(n) + 3
+    return int(n) + 8
 
 
 _vp, _i64, _u64, _i32, _int = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_int
@@ -185,7 +185,7 @@ def enumerate_actions_fast(lo, hi, dice, actions, counts, overflow=None, workspa
 
     cap = actions.shape[1] if actions is not None else 0
     if workspace is not None and workspace.numel() < workspace_ints(lo.shape[0]):
-        raise NardeCudaError("workspace must hold NARDE_WORKSPACE_INTS(n) = n + 3 int32")
+        raise NardeCudaError("workspace must hold NARDE_WORKSPACE_INTS(n) = n + 8 int32")
     rc = load().narde_enumerate_fast(_ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"),
                                      _ptr(dice, torch.uint8, "dice"), lo.shape[0], cap,
                                      _ptr(actions, torch.int64, "actions"), _ptr(counts, torch.int32, "counts"),
@@ -201,7 +201,7 @@ def step_full(lo, hi, env_base, seed, step, dice_in=None, action_idx=None, actio
 
     cap = actions.shape[1] if actions is not None else 0
     if workspace is not None and workspace.numel() < workspace_ints(lo.shape[0]):
-        raise NardeCudaError("workspace must hold NARDE_WORKSPACE_INTS(n) = n + 3 int32")
+        raise NardeCudaError("workspace must hold NARDE_WORKSPACE_INTS(n) = n + 8 int32")
     rc = load().narde_step_full_mirror(
         _ptr(lo, torch.uint8, "lo"), _ptr(hi, torch.uint8, "hi"), lo.shape[0], env_base, seed, step,
         _ptr(dice_in, torch.uint8, "dice_in"), _ptr(action_idx, torch.int32, "action_idx"), cap,

@@ -91,6 +91,7 @@ struct StepFullArgs {
   // kernel acquires `arrivals == n_primary` before it reads the list
   int32_t* arrivals;
   int32_t n_primary;
+  int32_t* last_count;  // diagnostic: number of deferred envs of the completed call (F_DEVICE_ADVANCE clears the counter)
   // optional second destination of the state planes (16-byte lanes like lo / hi): pinned host memory of a host-side
   // consumer, for which the 32-byte record IS the observation (gym_narde_b200.expand_obs198 decodes it to Box(198))
   void* mirror_lo;
@@ -200,8 +201,9 @@ NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal
 
 // End-of-turn completion shared by the kernels: apply, termination / reward / switch, auto-reset,
 // outputs and per-env stats contributions.
+// apply = false: the caller has applied `act` already (the exact kernel, with its rolled-up copy of apply_action)
 NHD void complete_env(State& s, int64_t i, const StepFullArgs& A, int player, uint32_t count, uint64_t act, int d1, int d2,
-                      StepFullLocal& L) {
+                      StepFullLocal& L, bool apply = true) {
   uint64_t* slice = A.actions ? A.actions + (int64_t)i * A.cap : nullptr;
   L.count = (int)count;
   L.overflow = (slice && (int)count > A.cap) ? 1 : 0;
@@ -212,7 +214,7 @@ NHD void complete_env(State& s, int64_t i, const StepFullArgs& A, int player, ui
     if (A.done) A.done[i] = (uint8_t)L.overflow;  // the "done" output carries the overflow flag in this mode
     return;
   }
-  if (count) apply_action(s, player, act);
+  if (count && apply) apply_action(s, player, act);
   float rew;
   int dn;
   finish_turn(s, player, (A.flags & F_REWARD_MOVER12) ? 1 : 0, &rew, &dn);

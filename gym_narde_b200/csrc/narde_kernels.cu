@@ -26,8 +26,8 @@ constexpr int kThreads = 128;
 // envs (= threads) per CTA of the fused step: 128 for large batches; one-warp CTAs of 32 envs when the batch
 // cannot fill the machine otherwise (4096 envs: 128 CTAs instead of 32; measured 0.081 -> 0.053 ms/step)
 constexpr int64_t kSmallBatch = 16384;
-constexpr int kDeferredThreads = 256;  // exact-doubles kernel: one 256-thread CTA per env at a time, ~18 KB shared memory
-constexpr int kDeferredGrid = 148 * 4;  // 4 CTAs per SM (measured: 512x2 and 128x8 are slower on the self-play mix)
+constexpr int kDeferredThreads = 128;  // exact-doubles kernel: four warps per CTA, one env per warp at a time (7 KB of shared memory each)
+constexpr int kDeferredGrid = 148 * 8;  // 8 CTAs per SM (64 registers, 27 KB)
 
 __device__ __forceinline__ State ld_state(const uint4* __restrict__ lo, const uint4* __restrict__ hi, int64_t i) {
   uint4 a = lo[i], b = hi[i];
@@ -54,14 +54,15 @@ __device__ __forceinline__ void obs_lut_init(float4* lut) {
   }
 }
 __device__ __forceinline__ void write_obs198_cta(const State* sm, const float4* lut, int rows, int64_t row0,
-                                                 float* __restrict__ obs, const uint32_t* skip = nullptr) {
+                                                 float* __restrict__ obs, const uint32_t* skip = nullptr,
+                                                 int tid = (int)threadIdx.x, int nthreads = (int)blockDim.x) {
   float* base = obs + row0 * 198;
   const int items = rows * 24;
   // rows are 792 B: in a 16-byte aligned row the WHITE block (4 floats per point from offset 0) is made of
   // aligned 16-byte lanes and the BLACK block (from offset 392 B) of 8-byte ones; in the next row it is the
   // other way round -- one 16-byte and two 8-byte stores per (env, point) instead of four 8-byte stores
   const bool even_aligned = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0);
-  for (int g = threadIdx.x; g < items; g += blockDim.x) {
+  for (int g = tid; g < items; g += nthreads) {
     int e = g / 24, pt = g - e * 24;
     if (skip && skip[e]) continue;  // row written by the deferred kernel
     int v = sm[e].point(pt);
@@ -78,7 +79,7 @@ __device__ __forceinline__ void write_obs198_cta(const State* sm, const float4* 
       *reinterpret_cast<float4*>(rb) = fb;
     }
   }
-  for (int g = threadIdx.x; g < rows * 3; g += blockDim.x) {
+  for (int g = tid; g < rows * 3; g += nthreads) {
     int e = g / 3, k = g - e * 3;
     if (skip && skip[e]) continue;
     const State& s = sm[e];
@@ -336,15 +337,79 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   PHASE_MARK(9);
 }
 
-// Exact doubles turns handed over by k_step_full_v2 (narde_deferred.cuh): persistent CTAs walk the
-// deferred list, one environment per CTA at a time.
+// Exact doubles turns handed over by k_step_full_v2 (narde_deferred.cuh).  A short list (self-play: ~0.2 % of the envs,
+// fewer entries than CTAs) is latency-bound -- the step ends when the slowest of these envs does -- so the whole CTA
+// works on one env; a long list (the doubles-heavy microbench) is throughput-bound: one env per warp.
+struct TeamExec {  // ExactStep's executor on the device: the calling thread runs the phase, then its team synchronises
+  int tid;         // thread index inside the team
+  bool cta;        // team = the CTA (else: the warp)
+  template <class F>
+  __device__ __forceinline__ void run(F&& f) {
+    f(tid);
+    if (cta) __syncthreads(); else __syncwarp();
+  }
+#ifdef NARDE_DEBUG_HOOKS
+  unsigned long long* clk;  // phase marks of the env being solved (tools/phase_clock.py)
+  __device__ __forceinline__ void mark(int k) {
+    if (clk && tid == 0) clk[k] = clock64();
+  }
+#else
+  __device__ __forceinline__ void mark(int) {}
+#endif
+};
+template <int NT, class ShT>
+__device__ __forceinline__ void exact_env(TeamExec& ex, ShT& sh, const float4* lut, uint4* lo, uint4* hi, int64_t i,
+                                          const StepFullArgs& A, float* obs198, int64_t* stats) {
+  State s;
+  ex.mark(0);
+  if (ex.tid == 0) s = ld_state(lo, hi, i);
+  ExactStep<NT>::solve(ex, sh, s, i, A);
+  ex.mark(8);
+  if (ex.tid == 0) {
+    StepFullLocal L;
+    State st = sh.st;
+    if (sh.count && !(A.flags & F_ENUMERATE_ONLY)) {  // apply_action, rolled up (code size: see narde_deferred.cuh)
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) {
+        const uint32_t h = (uint32_t)(sh.chosen >> (16 * k)) & 0xFFFFu;
+        if (h == 0xFFFFu) break;
+        apply_half_move(st, sh.player, (int)(h & 0xFF), (h >> 8) == 255u ? -1 : (int)(h >> 8));
+      }
+    }
+    complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L, false);
+    sh.st = st;
+    if (!(A.flags & F_ENUMERATE_ONLY)) {
+      st_state(lo, hi, i, st);
+      if (A.mirror_lo) st_state((uint4*)A.mirror_lo, (uint4*)A.mirror_hi, i, st);
+    }
+    if (stats) {
+      int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
+      for (int k = 0; k < 6; k++)
+        if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
+      if (L.count) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)L.count);
+      if (L.overflow) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), 1ull);
+    }
+  }
+  ex.run([](int) {});
+  ex.mark(9);
+  if (obs198) write_obs198_cta(&sh.st, lut, 1, i, obs198, nullptr, ex.tid, NT);
+  ex.run([](int) {});
+  ex.mark(10);
+#ifdef NARDE_DEBUG_HOOKS
+  if (ex.clk && ex.tid == 0) ex.clk[11] = sh.count | ((unsigned long long)sh.n_cand << 32);
+#endif
+}
 template <int BLK>
-__global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A_in, float* obs198, int64_t* stats) {
-  typedef DeferredStep<BLK> DS;
+__global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, StepFullArgs A_in, float* obs198, int64_t* stats) {
   StepFullArgs A = A_in;
   if (A.step_dev) A.step = *A.step_dev + ((A.flags & F_DEVICE_ADVANCE) ? 1u : 0u);
-  __shared__ DeferredSharedT<BLK> sh;
+  union Smem {
+    ExactSharedT<32> warp[BLK / 32];
+    ExactSharedT<BLK> cta;
+  };
+  __shared__ Smem sm;
   __shared__ float4 lut[16];
+  __shared__ int32_t s_last;
   obs_lut_init(lut);
   const int tid = threadIdx.x;
   // Launched as a programmatic dependent of k_step_full_v2: this grid starts once every main CTA has executed its
@@ -357,88 +422,47 @@ __global__ void __launch_bounds__(BLK, 4) k_step_deferred(uint4* lo, uint4* hi, 
     } while (seen < A.n_primary);
   }
   __syncthreads();
-  const int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
+  int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
 #ifdef NARDE_DEBUG_HOOKS
-#define DMARK(k)                                                                                      \
-  do {                                                                                                \
-    if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + (k)] = clock64();      \
-  } while (0)
-#else
-#define DMARK(k) do { } while (0)
+  if (g_dbg_flags & 4) n_def = 0;  // timing experiment only (wrong results): the deferred envs are not solved
 #endif
-  for (int q = blockIdx.x; q < n_def; q += gridDim.x) {
-    const int64_t i = reinterpret_cast<volatile const int32_t*>(A.defer_list)[q];
-    State s;
-    DMARK(0);
-    if (tid == 0) s = ld_state(lo, hi, i);
-    DS::ph_init(tid, sh, s, i, A);
-    __syncthreads();
-    DMARK(1);
-    for (int level = 1; level <= 4; level++) {
-      DS::ph_clear(tid, sh, level);
-      __syncthreads();
-      DS::ph_expand(tid, sh, level);
-      __syncthreads();
-      bool more = DS::level_found(sh, level);
-      DS::ph_advance(tid, sh, level);
-      __syncthreads();
-      if (!more) break;
-    }
-    DMARK(2);
-    if (sh.depth > 0 && sh.depth < 4) {  // the bitmap holds the (empty) next level: rebuild the deepest one
-      DS::ph_rebuild(tid, sh);
-      __syncthreads();
-    }
-    DS::ph_bm_count(tid, sh);
-    __syncthreads();
-    DS::ph_bm_scan1(tid, sh);
-    __syncthreads();
-    DS::ph_bm_scan2(tid, sh);
-    __syncthreads();
-    DS::ph_bm_scan3(tid, sh, i, A);
-    __syncthreads();
-    DMARK(3);
-    DS::ph_emit(tid, sh, i, A);
-    __syncthreads();
-    DMARK(4);
-    if (tid == 0) {
-      StepFullLocal L;
-      State st = sh.st;
-      complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
-      sh.st = st;
-      if (!(A.flags & F_ENUMERATE_ONLY)) {
-        st_state(lo, hi, i, st);
-        if (A.mirror_lo) st_state((uint4*)A.mirror_lo, (uint4*)A.mirror_hi, i, st);
-      }
-      if (stats) {
-        int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
-        for (int k = 0; k < 6; k++)
-          if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
-        if (L.count) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)L.count);
-        if (L.overflow) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), 1ull);
-      }
-    }
-    __syncthreads();
-    DMARK(5);
-    if (obs198) write_obs198_cta(&sh.st, lut, 1, i, obs198);
-    __syncthreads();
-    DMARK(6);
+  const volatile int32_t* list = reinterpret_cast<const volatile int32_t*>(A.defer_list);
+  TeamExec ex;
+  if (n_def <= 2 * (int)gridDim.x) {  // consecutive CTAs sit on different SMs: a short list spreads over all of them
+    ex.tid = tid;
+    ex.cta = true;
+    for (int q = blockIdx.x; q < n_def; q += gridDim.x) {
 #ifdef NARDE_DEBUG_HOOKS
-    if (g_dbg_clk && tid == 0 && q < 148) g_dbg_clk[(size_t)(2048 + q) * 16 + 7] = sh.count;
+      ex.clk = (g_dbg_clk && q < 1024) ? g_dbg_clk + (size_t)(2048 + q) * 16 : nullptr;
 #endif
+      exact_env<BLK>(ex, sm.cta, lut, lo, hi, list[q], A, obs198, stats);
+    }
+  } else {
+    ex.tid = tid & 31;
+    ex.cta = false;
+    for (int q = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x; q < n_def; q += (int)gridDim.x * (BLK / 32)) {
+#ifdef NARDE_DEBUG_HOOKS
+      ex.clk = (g_dbg_clk && q < 1024) ? g_dbg_clk + (size_t)(2048 + q) * 16 : nullptr;
+#endif
+      exact_env<32>(ex, sm.warp[tid >> 5], lut, lo, hi, list[q], A, obs198, stats);
+    }
   }
-#undef DMARK
   // stream order: this grid must not complete before its primary has (the next step follows it)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // F_DEVICE_ADVANCE: the step's own bookkeeping instead of a memset and a counter kernel in front of every step
-  // (each is a node of the step's CUDA graph, ~2 us).  Every CTA of this grid has read the list length and the
-  // step index before it arrives here, and the primary grid is complete: the last arrival resets the list for
-  // the next step and publishes the new step index.
+  // (each is a node of the step's CUDA graph, ~2 us).  Every CTA of this grid is done with the list and has read the
+  // step index before it arrives here, and the primary grid is complete: the last arrival clears the list and its
+  // header for the next step and publishes the new step index.
   if (A.ticket) {
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      if (atomicAdd(A.ticket, 1) == (int)gridDim.x - 1) {
+      s_last = atomicAdd(A.ticket, 1) == (int)gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      if (tid == 0) {
+        *A.last_count = n_def;
         *A.defer_count = 0;
         *A.ticket = 0;
         *A.arrivals = 0;
@@ -727,6 +751,7 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
   A.ticket = nullptr;
   A.arrivals = nullptr;
   A.n_primary = 0;
+  A.last_count = nullptr;
   A.mirror_lo = mirror_lo;
   A.mirror_hi = mirror_hi;
   const bool dev_advance = (flags & NARDE_DEVICE_ADVANCE) != 0;
@@ -736,15 +761,17 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
     k_step_full<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, obs198, stats);
     return launch_status();
   }
-  // Workspace (NARDE_WORKSPACE_INTS(n) words): [0] = number of deferred envs, [1] = arrival counter of the exact
-  // kernel's CTAs (DEVICE_ADVANCE), [2] = arrival counter of the main kernel's CTAs, [3..] = the deferred indices.
+  // Workspace (NARDE_WORKSPACE_INTS(n) words, layout in include/narde_b200.h): header [0] number of deferred envs,
+  // [1] arrival counter of the exact kernel's CTAs (DEVICE_ADVANCE), [2] arrival counter of the main kernel's CTAs,
+  // [3] deferred envs of the last completed DEVICE_ADVANCE call; [NARDE_WORKSPACE_HEADER..] the deferred indices.
   if (workspace) {
     if ((((uintptr_t)workspace) & 3u) != 0) return -1;
     A.defer_count = workspace;
     A.arrivals = workspace + 2;
-    A.defer_list = workspace + 3;
+    A.last_count = workspace + 3;
+    A.defer_list = workspace + NARDE_WORKSPACE_HEADER;
     A.n_primary = (int32_t)(n <= kSmallBatch ? (n + 31) / 32 : (n + 127) / 128);
-    if (dev_advance) {  // the three header words are zero on entry and again on exit
+    if (dev_advance) {  // the three counters are zero on entry and again on exit
       A.ticket = workspace + 1;
     } else {
       cudaError_t e = cudaMemsetAsync(workspace, 0, 3 * sizeof(int32_t), (cudaStream_t)stream);

@@ -36,12 +36,15 @@
 extern "C" {
 #endif
 
-#define NARDE_ABI_VERSION 2
+#define NARDE_ABI_VERSION 3
 #define NARDE_MAX_HALF_MOVES 96 /* 4 dice x 24 points */
-/* int32 words of the optional `workspace` of narde_step_full / narde_enumerate_fast for n environments:
- * [0] number of deferred envs, [1] arrival counter of the exact kernel's CTAs, [2] arrival counter of the main
- * kernel's CTAs (release/acquire publication of the list to the programmatic dependent), [3..n+2] the list */
-#define NARDE_WORKSPACE_INTS(n) ((n) + 3)
+/* int32 words of the optional `workspace` of narde_step_full / narde_enumerate_fast for n environments (the caller
+ * zero-fills it once): header [0] number of deferred envs of the call (cleared again by a NARDE_DEVICE_ADVANCE call),
+ * [1] arrival counter of the exact kernel's CTAs, [2] arrival counter of the main kernel's CTAs (release/acquire
+ * publication of the list to the programmatic dependent), [3] number of deferred envs of the last completed
+ * NARDE_DEVICE_ADVANCE call, [4..7] reserved; [8..n+7] the list of deferred env indices */
+#define NARDE_WORKSPACE_HEADER 8
+#define NARDE_WORKSPACE_INTS(n) ((n) + NARDE_WORKSPACE_HEADER)
 
 /* narde_step_full flags */
 #define NARDE_REWARD_MOVER12 1   /* reward 1/2 to the mover (narde_env.py:134-141); default: README +1 iff WHITE wins */
@@ -56,7 +59,7 @@ extern "C" {
 #define NARDE_DEVICE_ADVANCE 256   /* narde_step_full with workspace and step_dev: the step index is *step_dev + 1, and the kernels
                                     themselves store it back and clear the workspace when the step is complete -- no memset and no
                                     counter kernel in front of every step (two nodes of a replayed CUDA graph, ~2 us each).  The
-                                    workspace's three header words are zero before the first call and are left zero by every call;
+                                    workspace's three counters are zero before the first call and are left zero by every call;
                                     it must not be shared with calls that do not set this flag. */
 #define NARDE_HALF_MOVES_ONLY 4  /* narde_apply_actions: Narde.execute_rotated_move semantics (no end-of-turn bookkeeping) */
 

@@ -15,7 +15,8 @@
 
 using namespace narde;
 namespace narde { int g_hs_force_slow = 0; }
-// bit 0: level-2 doubles items are not put in the item table; bit 1: no per-item offset table (recounting emit)
+// bit 0: level-2 doubles items are not put in the item table; bit 1: no per-item offset table (recounting emit);
+// bit 2: exact phases with a window of 8 candidates; bit 3: exact phases with a team of 128 threads instead of 32
 extern "C" void hs_set_force_slow(int v) { narde::g_hs_force_slow = v; }
 #ifdef NARDE_PROFILE
 namespace narde { ProfCounters g_prof; }
@@ -109,6 +110,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
   A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.mirror_lo = A.mirror_hi = nullptr;
+  A.last_count = nullptr;
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
     StepFullLocal L;
@@ -186,29 +188,25 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
   }
 }
 
-// CTA-per-env exact kernel (narde_deferred.cuh), emulated phase by phase
-template <int BLK>
+// CTA-per-env exact kernel (narde_deferred.cuh): the same driver, a phase = a loop over the team's tids
+// (descending, so that a read-after-write hazard between the threads of one phase shows up)
+template <int NT>
+struct HostTeamExec {
+  template <class F>
+  void run(F&& f) {
+    for (int t = NT - 1; t >= 0; t--) f(t);
+  }
+  void mark(int) {}
+};
+template <int NT>   // the device kernel's teams: the CTA (128 threads) for a short list, one warp per env for a long one
 static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float* obs198, int64_t* stats) {
-  typedef DeferredStep<BLK> DS;
-  static DeferredSharedT<BLK> sh;
+  typedef ExactStep<NT> ES;
+  static ExactSharedT<NT> sh;
+  HostTeamExec<NT> ex;
   for (int q = 0; q < A.defer_count[0]; q++) {
     int64_t i = A.defer_list[q];
     State s = load_state(lo, hi, i);
-    for (int t = 0; t < BLK; t++) DS::ph_init(t, sh, s, i, A);
-    for (int level = 1; level <= 4; level++) {
-      for (int t = 0; t < BLK; t++) DS::ph_clear(t, sh, level);
-      for (int t = BLK - 1; t >= 0; t--) DS::ph_expand(t, sh, level);
-      bool more = DS::level_found(sh, level);
-      for (int t = 0; t < BLK; t++) DS::ph_advance(t, sh, level);
-      if (!more) break;
-    }
-    if (sh.depth > 0 && sh.depth < 4)
-      for (int t = BLK - 1; t >= 0; t--) DS::ph_rebuild(t, sh);
-    for (int t = 0; t < BLK; t++) DS::ph_bm_count(t, sh);
-    for (int t = 0; t < BLK; t++) DS::ph_bm_scan1(t, sh);
-    for (int t = 0; t < BLK; t++) DS::ph_bm_scan2(t, sh);
-    for (int t = BLK - 1; t >= 0; t--) DS::ph_bm_scan3(t, sh, i, A);
-    for (int t = BLK - 1; t >= 0; t--) DS::ph_emit(t, sh, i, A);
+    ES::solve(ex, sh, s, i, A);
     StepFullLocal L;
     State st = sh.st;
     complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
@@ -232,10 +230,11 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
   A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.mirror_lo = A.mirror_hi = nullptr;
+  A.last_count = nullptr;
   if (workspace) {
-    workspace[0] = workspace[1] = workspace[2] = 0;   // NARDE_WORKSPACE_INTS layout (include/narde_b200.h)
+    for (int k = 0; k < 8; k++) workspace[k] = 0;   // NARDE_WORKSPACE_INTS layout (include/narde_b200.h)
     A.defer_count = workspace;
-    A.defer_list = workspace + 3;
+    A.defer_list = workspace + 8;
   }
   // same dispatch as narde_step_full: one-warp CTAs of 32 envs for small batches (g_small_batch can be
   // lowered by the tests so that both tile sizes are exercised on small inputs)
@@ -249,7 +248,10 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
   } else {
     step_full_v2_host<128, false>(lo, hi, n, A, obs198, stats);
   }
-  if (workspace) step_deferred_host<256>(lo, hi, A, obs198, stats);
+  if (workspace) {
+    if (g_hs_force_slow & 8) step_deferred_host<128>(lo, hi, A, obs198, stats);
+    else step_deferred_host<32>(lo, hi, A, obs198, stats);
+  }
   return 0;
 }
 

@@ -74,7 +74,7 @@ class HostSim:
         overflow = np.zeros(n, np.uint8)
         if self.enumerate_fast:
             lo0, hi0 = lo.copy(), hi.copy()
-            ws = np.zeros(n + 3, np.int32)
+            ws = np.zeros(n + 8, np.int32)
             self.lib.hs_enumerate_fast(_p(lo), _p(hi), _p(dice), C.c_int64(n), C.c_int32(cap), _p(actions), _p(counts),
                                        _p(overflow), _p(ws), None)
             assert (lo == lo0).all() and (hi == hi0).all()   # states untouched
@@ -117,7 +117,7 @@ class HostSim:
             "stats": np.zeros(8, np.int64),
         }
         v1 = self.per_thread or (flags & 8)
-        ws = np.zeros(n + 3, np.int32) if (self.defer and not v1) else None
+        ws = np.zeros(n + 8, np.int32) if (self.defer and not v1) else None
         fn = self.lib.hs_step_full if v1 else self.lib.hs_step_full_v2
         tail = (None,) if v1 else (_p(ws), None)
         fn(_p(lo), _p(hi), C.c_int64(n), C.c_int64(env_base), C.c_uint64(seed), C.c_uint64(step),
@@ -204,7 +204,7 @@ class CudaBackend:
         counts = t.zeros(n, dtype=t.int32, device=self.dev)
         overflow = t.zeros(n, dtype=t.uint8, device=self.dev)
         if self.enumerate_fast:
-            ws = t.zeros(n + 3, dtype=t.int32, device=self.dev)
+            ws = t.zeros(n + 8, dtype=t.int32, device=self.dev)
             self.cabi.enumerate_actions_fast(tlo, thi, self._up(np.asarray(dice, np.uint8)), actions, counts, overflow, ws)
             assert t.equal(tlo.cpu(), t.from_numpy(lo)) and t.equal(thi.cpu(), t.from_numpy(hi))   # states untouched
             return actions.cpu().numpy().view(np.uint64), counts.cpu().numpy(), overflow.cpu().numpy()
@@ -237,7 +237,7 @@ class CudaBackend:
         done = t.zeros(n, dtype=t.uint8, device=self.dev)
         stats = t.zeros(8, dtype=t.int64, device=self.dev)
         trunc = t.zeros(n, dtype=t.uint8, device=self.dev)
-        ws = t.zeros(n + 3, dtype=t.int32, device=self.dev) if (getattr(self, "defer", True) and not (flags & 8)) else None
+        ws = t.zeros(n + 8, dtype=t.int32, device=self.dev) if (getattr(self, "defer", True) and not (flags & 8)) else None
         if getattr(self, "per_thread", False):
             flags |= 8  # NARDE_PER_THREAD_KERNEL
         self.cabi.step_full(tlo, thi, env_base, seed, step,

@@ -177,6 +177,31 @@ def test_block_kernel_fallback_paths(hostsim):
             hostsim.lib.hs_set_force_slow(C.c_int(0))
 
 
+def test_exact_kernel_multi_window_levels(hostsim):
+    """The exact (block-rule) doubles phases test a level's candidates in windows of 1024, with a team of one warp
+    (long lists) or of the whole 128-thread CTA (short lists).  Test-only hooks of the host build shrink the window
+    to 8 so that ordinary positions take the multi-window route (actions stored window by window, the chosen action
+    read back from the stored list or found by the second pass: cap 0 / 4) and select the 128-thread team."""
+    import ctypes as C
+    for force in (4, 8, 12):
+        hostsim.lib.hs_set_force_slow(C.c_int(force))
+        try:
+            test_block_kernel_equals_per_thread_body(hostsim)
+            b, off, ft = P.synthetic_boards(4000, 61)
+            lo, hi, _, _ = P.pack_mover_boards(b, off, ft, 62)
+            dice = P.random_dice(4000, 63, 0.8)
+            o = _v1_v2_equal(hostsim, lo, hi, seed=7, step=2, dice_in=dice, cap=4, flags=0)
+            assert o["deferred"] > 50
+            _v1_v2_equal(hostsim, lo, hi, seed=8, step=3, dice_in=dice, cap=0, flags=0, want_actions=False)
+            hostsim.enumerate_fast = True
+            try:
+                assert P.check_enumerate_vs_oracle(hostsim, lo[:1500].copy(), hi[:1500].copy(), dice[:1500], cap=8) > 0
+            finally:
+                hostsim.enumerate_fast = False
+        finally:
+            hostsim.lib.hs_set_force_slow(C.c_int(0))
+
+
 def test_oracle_bulk_trace_equals_stepwise_hostsim(hostsim):
     """o_selfplay_trace (the C bulk trace the full-size GPU parity test and bench.py compare against) agrees field by
     field with step-by-step calls: Philox policy, caller indices / fractions, TimeLimit truncation, no auto-reset."""

@@ -242,8 +242,8 @@ def test_device_advance_mode_equals_host_stepped_calls():
                             flags=flags, max_episode_steps=0, workspace=ws, step_dev=step_dev)
 
         a, b = alloc(), alloc()
-        ws_a = torch.zeros(n + 3, dtype=torch.int32, device=dev)
-        ws_b = torch.zeros(n + 3, dtype=torch.int32, device=dev)
+        ws_a = torch.zeros(n + 8, dtype=torch.int32, device=dev)
+        ws_b = torch.zeros(n + 8, dtype=torch.int32, device=dev)
         for k in range(40):                                   # into the middle game, where turns get deferred
             call(a, 1 + k, _cabi.AUTORESET, ws_a, None)
             call(b, 1 + k, _cabi.AUTORESET, ws_a, None)
@@ -254,7 +254,8 @@ def test_device_advance_mode_equals_host_stepped_calls():
             call(b, 0, _cabi.AUTORESET | _cabi.DEVICE_ADVANCE, ws_b, ctr)
             deferred += int(ws_a[0].item())
             assert int(ctr.item()) == 41 + k
-            assert ws_b[:3].tolist() == [0, 0, 0]
+            assert ws_b[:3].tolist() == [0, 0, 0]                                 # the counters are left clean
+            assert int(ws_b[3].item()) == int(ws_a[0].item())                     # ... the count kept for diagnostics
             for key in a:
                 assert torch.equal(a[key], b[key]), (n, k, key)
         assert deferred > 0          # the exact kernel had work on the way

@@ -13,7 +13,7 @@ env.reset()
 for _ in range(300):
     env.step()
 nb = (E + 127) // 128
-buf = torch.zeros((max(nb, 2048) + 148, 16), dtype=torch.int64, device="cuda")
+buf = torch.zeros((max(nb, 2048) + 1024, 16), dtype=torch.int64, device="cuda")
 lib = _cabi.load()
 lib.narde_debug_set_clock_buffer.argtypes = [C.c_void_p]
 assert lib.narde_debug_set_clock_buffer(C.c_void_p(buf.data_ptr())) == 0
@@ -22,6 +22,7 @@ if len(sys.argv) > 2:
     lib0 = _cabi.load(); lib0.narde_debug_set_flags(int(sys.argv[2]))
 acc = []
 for _ in range(5):
+    buf.zero_()
     env.step()
     torch.cuda.synchronize()
     acc.append(buf.cpu().numpy().copy())
@@ -39,14 +40,21 @@ for k, nm in enumerate(names):
 span = a[:, :, 9].max(axis=1) - a[:, :, 0].min(axis=1)
 print("kernel span cycles per step (max end - min start, per-SM clocks differ slightly):", span)
 
-dd = full[:, 2048:2048 + 148]
-ok = dd[:, :, 6] > dd[:, :, 0]
-dn = ["init", "search", "count+scan", "emit", "complete", "obs"]
+dd = full[:, 2048:2048 + 1024]
+dn = ["init", "items", "item counts", "scan", "materialise", "test", "rank", "(end of solve)", "complete", "obs"]
 for st in range(dd.shape[0]):
-    x = dd[st][ok[st]]
+    x = dd[st]
+    x = x[(x[:, 10] > x[:, 0]) & (x[:, 0] > 0)]
+    if st > 0:                      # rows not rewritten since the previous step are stale
+        prev = dd[st - 1]
     if len(x) == 0:
         continue
-    dur = np.diff(x[:, :7], axis=1)
-    w = np.argmax(x[:, 6] - x[:, 0])
-    print("step", st, "deferred envs", len(x), "slowest total %.0f cycles count %d:" % (x[w, 6] - x[w, 0], x[w, 7]),
-          " ".join("%s=%.0f" % (n, v) for n, v in zip(dn, dur[w])), "| mean total %.0f" % (x[:, 6] - x[:, 0]).mean())
+    dur = np.diff(x[:, :11], axis=1)
+    tot = x[:, 10] - x[:, 0]
+    w = np.argmax(tot)
+    meta = x[:, 11].astype(np.int64)
+    cnt, ncand = meta & 0xFFFFFFFF, meta >> 32
+    print("step", st, "deferred envs (first 1024)", len(x), "| total mean %.0f p50 %.0f p90 %.0f max %.0f | candidates mean %.0f p90 %.0f max %d" % (
+        tot.mean(), np.percentile(tot, 50), np.percentile(tot, 90), tot.max(), ncand.mean(), np.percentile(ncand, 90), ncand.max()))
+    print("   mean per phase:", " ".join("%s=%.0f" % (n, v) for n, v in zip(dn, dur.mean(axis=0))))
+    print("   slowest env   :", " ".join("%s=%.0f" % (n, v) for n, v in zip(dn, dur[w])), "count %d candidates %d" % (cnt[w], ncand[w]))

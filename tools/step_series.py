@@ -18,7 +18,7 @@ for t in range(T):
     torch.cuda.synchronize()
     st = env.stats.clone()
     d = (st - prev).tolist(); prev = st
-    rows.append((t, a.elapsed_time(b), int(env._workspaces[0][0].item()), d[5] / E, d[0], int((env.counts > 64).sum().item())))
+    rows.append((t, a.elapsed_time(b), int((env._ws_adv if env._ws_adv is not None else env._workspaces[0])[3].item()), d[5] / E, d[0], int((env.counts > 64).sum().item())))
 for r in rows:
     if r[0] % 10 == 0 or r[1] > 0.25:
         print("step %4d  ms %.4f  deferred %5d  meanA %6.2f  finished %6d  overflow %6d" % r)
