@@ -128,6 +128,10 @@ def _ptr(t, dtype=None, name="tensor"):
         raise NardeCudaError("%s must be contiguous" % name)
     if dtype is not None and t.dtype != dtype:
         raise NardeCudaError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    # launches go to the CURRENT device's current stream: a tensor of another GPU would be an illegal address there
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise NardeCudaError("%s lives on %s but the current CUDA device is cuda:%d: call torch.cuda.set_device(...) "
+                             "or wrap the call in `with torch.cuda.device(...)`" % (name, t.device, torch.cuda.current_device()))
     return C.c_void_p(t.data_ptr())
 
 

@@ -91,6 +91,21 @@ class AfterstateMLP:
         return cls(l1.weight.data, l1.bias.data, l2.weight.data, l2.bias.data, move1_head.weight.data, move1_head.bias.data,
                    *m2)
 
+    @classmethod
+    def from_state_dict(cls, sd):
+        """Weights from a `DecomposedDQN.state_dict()` (train_deepq_pytorch.py:184-201: keys `feature_network.{0,2}.*`,
+        `move1_head.*`, `move2_head.*`) built with state_size=198.  The reference's own scripts construct
+        DecomposedDQN(state_size=24) (train_deepq_pytorch.py:831, evaluate_model.py): those checkpoints feed the raw
+        24-int board, not the README's Box(198), and are NOT supported by this kernel -- a clear error instead of
+        silently wrong scores."""
+        w1 = sd["feature_network.0.weight"]
+        if tuple(w1.shape) != (HID, IN):
+            raise ValueError("AfterstateMLP needs a DecomposedDQN(state_size=198) checkpoint; got first layer %s "
+                             "(the reference's state_size=24 checkpoints are unsupported)" % (tuple(w1.shape),))
+        m2 = (sd["move2_head.weight"], sd["move2_head.bias"]) if "move2_head.weight" in sd else (None, None)
+        return cls(w1, sd["feature_network.0.bias"], sd["feature_network.2.weight"], sd["feature_network.2.bias"],
+                   sd["move1_head.weight"], sd["move1_head.bias"], *m2)
+
     def _move1(self, selected_move1, k):
         t = self.torch
         if self.wpack_m2 is None:

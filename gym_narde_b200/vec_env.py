@@ -16,7 +16,7 @@ from . import _cabi
 
 class VecNardeEnv:
     def __init__(self, num_envs, seed=0, rules="full", reward=None, max_actions=64, device="cuda",
-                 env_base=0, autoreset=True, max_episode_steps=1000, write_actions=True, chunks=None,
+                 env_base=0, autoreset=None, max_episode_steps=1000, write_actions=True, chunks=None,
                  graph=True):
         torch = _cabi.require_cuda()
         _cabi.load()
@@ -32,7 +32,12 @@ class VecNardeEnv:
         self.max_actions = int(max_actions)
         self.device = torch.device(device)
         self.env_base = int(env_base)
-        self.autoreset = bool(autoreset)
+        # autoreset: rules="full" resets finished games inside the fused step (default on).  The reference-exact step
+        # has no reset inside (NardeEnv.step, narde_env.py:27-103: the caller resets), so asking for it is an error
+        # rather than a silently ignored flag; use reset_done() between steps.
+        if rules == "reference" and autoreset:
+            raise ValueError("autoreset=True is not available with rules='reference' (call reset_done() instead)")
+        self.autoreset = bool(rules == "full") if autoreset is None else bool(autoreset)
         self.max_episode_steps = int(max_episode_steps)
         self.write_actions = bool(write_actions)
         self.step_count = 0  # Philox step counter (global, shared by all envs)
@@ -93,6 +98,14 @@ class VecNardeEnv:
         _cabi.reset(self.lo, self.hi, self.env_base, self.seed, 0)
         self.stats.zero_()
         return self.observe(), {}
+
+    def reset_done(self):
+        """Reset the envs whose last step ended the game (terminated or truncated), like a caller of the reference env
+        does after `done`; returns the refreshed observation.  (rules="full" with autoreset does this inside the step.)"""
+        t = self.torch
+        mask = t.bitwise_or(self.done, self.trunc)
+        _cabi.reset(self.lo, self.hi, self.env_base, self.seed, self.step_count, mask=mask)
+        return self.observe()
 
     def observe(self):
         if self.rules == "full":
