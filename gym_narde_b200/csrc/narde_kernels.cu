@@ -25,6 +25,7 @@ namespace {
 constexpr int kThreads = 128;
 // envs (= threads) per CTA of the fused step: 128 for large batches; one-warp CTAs of 32 envs when the batch
 // cannot fill the machine otherwise (4096 envs: 128 CTAs instead of 32; measured 0.081 -> 0.053 ms/step)
+unsigned g_extra_smem = 0;
 int64_t kSmallBatch = 16384;  // (NARDE_SMALL_BATCH in the environment overrides it: A/B timing of the two tiles)
 constexpr int kDeferredThreads = 128;  // exact-doubles kernel: four warps per CTA, one env per warp at a time (7 KB of shared memory each)
 constexpr int kDeferredGrid = 148 * 8;  // 8 CTAs per SM (64 registers, 27 KB)
@@ -653,6 +654,10 @@ int narde_abi_version(void) {
     if (v && v[0] == '1') g_use_pdl = false;
     v = getenv("NARDE_SMALL_BATCH");
     if (v) kSmallBatch = atoll(v);
+#ifdef NARDE_DEBUG_HOOKS
+    v = getenv("NARDE_EXTRA_SMEM");  // occupancy experiment: unused dynamic shared memory per main CTA (fewer CTAs per SM)
+    if (v) g_extra_smem = (unsigned)atoi(v);
+#endif
     env_read = true;
   }
   // one-time function attributes are set here (outside any stream capture)
@@ -797,7 +802,7 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
   } else {
     const int g = (int)((n + 127) / 128);
     if (workspace)
-      k_step_full_v2<128, true><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
+      k_step_full_v2<128, true><<<g, 128, g_extra_smem, st>>>(plo, phi, n, A, obs198, stats);
     else
       k_step_full_v2<128, false><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
   }

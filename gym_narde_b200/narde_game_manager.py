@@ -358,6 +358,66 @@ class NardeGameManager:
                 "valid_moves_by_piece": self.valid_moves_by_piece, "first_move_made": self.first_move_made,
                 "borne_off": self._borne_off(), "game_over": over, "winner": winner}
 
+    # ---- the AI's turn (my_game/narde_game_manager.py:890-1099) ---------------------------------------
+    def _q_values(self, ai_model, device):
+        """Q-values [576] of the position the AI is looking at.  A DecomposedDQN-like torch module gets the env's
+        observation as the reference passes it (narde_game_manager.py:1045-1050: FloatTensor(env._get_obs())[None]);
+        an AfterstateMLP (the tcgen05 kernel, 198 inputs) gets the packed state of the turn's current node and encodes
+        Box(198) itself."""
+        import torch
+        node = self._nodes[0]
+        if hasattr(ai_model, "forward_states"):
+            lo = torch.frombuffer(bytearray(node.lo), dtype=torch.uint8).reshape(1, 16).cuda()
+            hi = torch.frombuffer(bytearray(node.hi), dtype=torch.uint8).reshape(1, 16).cuda()
+            return ai_model.forward_states(lo, hi)[0].float().cpu()
+        obs = torch.as_tensor(np.asarray(self.env._get_obs(), dtype=np.float32)).unsqueeze(0).to(device)
+        with torch.no_grad():
+            return ai_model.forward(obs)[0].float().cpu()
+
+    def _select_ai_move(self, valid_moves, ai_model, device, move_index):
+        """narde_game_manager.py:1027-1072: the legal half-move with the largest Q[from*24 + to] ('off' -> from*24);
+        ties go to the first move in the offered order, as Python's max does."""
+        q = self._q_values(ai_model, device)
+        best, best_v = None, None
+        for f, to in valid_moves:
+            v = float(q[f * 24 + (0 if to == "off" else to)])
+            if best is None or v > best_v:
+                best, best_v = (f, to), v
+        return best
+
+    def execute_ai_moves(self, ai_model, device=None, dice=None):
+        """my_game/narde_game_manager.py:890-939: BLACK's whole turn -- roll, then half-move by half-move the legal
+        move the model scores highest, then either the game-over response or White's roll.  Same response keys.
+        The half-moves offered at every point are those of the turn tree (a legal end of turn stays reachable), so the
+        AI cannot strand a die the way the reference's per-move filter can.  `dice` injects the AI's roll (tests)."""
+        dice_rolled, _ = self.roll_dice("black", dice)
+        ai_dice = list(self.dice_state["original"])
+        if not self.valid_moves:
+            self._tree, self._nodes = None, []
+            self.set_current_player("white")
+            d, by_piece = self.roll_dice("white")
+            return {"board": np.asarray(self.game.board).tolist(), "current_player": "white", "dice": d,
+                    "valid_moves_by_piece": by_piece, "ai_had_no_moves": True, "borne_off": self._borne_off()}
+        ai_moves, moved_from_head, k = [], False, 0
+        while self._tree is not None and self.valid_moves:
+            f, to = self._select_ai_move(self.valid_moves, ai_model, device, k)
+            r = self.make_move(f, to, "black")
+            if "error" in r:                      # cannot happen: the move came from the offered list
+                raise RuntimeError("AI move rejected: %s" % r["error"])
+            ai_moves.append({"from": f, "to": -1 if to == "off" else to})
+            moved_from_head = moved_from_head or f == HEAD
+            k += 1
+        over, winner = self.is_game_over()
+        if over:
+            return {"board": np.asarray(self.game.board).tolist(), "game_over": True, "winner": winner,
+                    "ai_moves": ai_moves, "ai_moved_from_head": moved_from_head, "ai_dice": ai_dice,
+                    "borne_off": self._borne_off()}
+        self.set_current_player("white")
+        d, by_piece = self.roll_dice("white")
+        return {"board": np.asarray(self.game.board).tolist(), "current_player": "white", "dice": d,
+                "valid_moves_by_piece": by_piece, "ai_moves": ai_moves, "ai_moved_from_head": moved_from_head,
+                "ai_dice": ai_dice, "borne_off": self._borne_off()}
+
     def set_current_player(self, player_color):
         """my_game/narde_game_manager.py:881-888."""
         if player_color not in _TURN:

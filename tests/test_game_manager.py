@@ -159,6 +159,66 @@ def test_manager_kats_and_game_cpu(hostsim):
     assert turns > 20 and halves > turns
 
 
+class _EnvObs(_Env):
+    def _get_obs(self):               # what the reference env hands the model (narde_env.py:24-25)
+        return np.asarray(self.game.board, dtype=np.int32)
+
+
+def _ai_turns(make):
+    """execute_ai_moves (my_game/narde_game_manager.py:890-1099): response keys, the greedy Q[from*24+to] choice
+    among the offered half-moves, the no-move branch and the game-over branch."""
+    import torch
+
+    class Net(torch.nn.Module):       # a fixed scorer: prefers low sources, then short moves -> the choice is predictable
+        def forward(self, x):
+            q = torch.zeros(1, 576)
+            for f in range(24):
+                for t in range(24):
+                    q[0, f * 24 + t] = -f + 0.01 * t
+            return q
+
+    net = Net()
+    mgr = make()
+    res = mgr.execute_ai_moves(net, "cpu", dice=(6, 5))
+    assert set(res) >= {"board", "current_player", "dice", "valid_moves_by_piece", "ai_moves", "ai_moved_from_head",
+                        "ai_dice", "borne_off"}
+    assert res["ai_dice"] == [6, 5] and res["current_player"] == "white" and res["ai_moved_from_head"] is True
+    # opening: only the head has checkers; one head move per turn, then the moved checker carries on
+    assert res["ai_moves"] == [{"from": 23, "to": 17}, {"from": 17, "to": 12}] or \
+        res["ai_moves"] == [{"from": 23, "to": 18}, {"from": 18, "to": 12}]
+    assert res["board"][11] == -14 and res["board"][0] == -1          # black checker: mover point 12 = absolute point 0
+    assert mgr.current_player == "white" and res["valid_moves_by_piece"]
+    # among several offered half-moves the arg-max of Q[from*24 + to] is played: source 3 beats source 10
+    mgr = make()
+    g = mgr.game
+    g.board[:] = 0
+    g.board[12 + 10], g.board[12 + 3], g.board[5] = -1, -1, 15       # black's points 10 and 3 (mover frame), white far away
+    g.borne_off_black, g.first_turn_white, g.first_turn_black = 13, False, False
+    res = mgr.execute_ai_moves(net, "cpu", dice=(2, 1))
+    assert res["ai_moves"][0]["from"] == 3
+    # no playable die: ai_had_no_moves and White is on roll
+    mgr = make()
+    g = mgr.game
+    g.board[:] = 0
+    g.board[11], g.board[5], g.board[6] = -15, 7, 8                   # black head (mover 23) blocked at 17 and 18
+    g.first_turn_white = g.first_turn_black = False
+    res = mgr.execute_ai_moves(net, "cpu", dice=(6, 5))
+    assert res.get("ai_had_no_moves") is True and res["current_player"] == "white" and "ai_moves" not in res
+    # last checker borne off: game over, winner black
+    mgr = make()
+    g = mgr.game
+    g.board[:] = 0
+    g.board[12 + 2], g.board[20] = -1, 15
+    g.borne_off_black, g.first_turn_white, g.first_turn_black = 14, False, False
+    res = mgr.execute_ai_moves(net, "cpu", dice=(6, 4))
+    assert res["game_over"] is True and res["winner"] == "black" and res["ai_moves"] == [{"from": 2, "to": -1}]
+
+
+def test_execute_ai_moves_cpu(hostsim):
+    from gym_narde_b200.narde_game_manager import NardeGameManager
+    _ai_turns(lambda: NardeGameManager(_EnvObs(), _ops=hostsim))
+
+
 def test_manager_needs_cuda():
     import torch
     if torch.cuda.is_available():
@@ -189,6 +249,17 @@ def test_manager_on_the_facade_gpu():
 
     _manager_kats(make)
     _rule_kats(make)
+    _ai_turns(make)
+    # the AI turn driven by the tcgen05 scorer (AfterstateMLP.forward_states on the packed node)
+    import torch
+    import torch.nn as nn
+    from gym_narde_b200 import AfterstateMLP
+    torch.manual_seed(4)
+    fn = nn.Sequential(nn.Linear(198, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU()).cuda()
+    mlp = AfterstateMLP.from_module(fn, nn.Linear(256, 576).cuda())
+    mgr = make()
+    res = mgr.execute_ai_moves(mlp, dice=(4, 2))
+    assert len(res["ai_moves"]) == 2 and res["current_player"] == "white"
     mgr = make()
     turns, halves = _play_one_game(mgr, random.Random(5))
     assert turns > 20 and halves > turns
