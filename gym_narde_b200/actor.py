@@ -14,10 +14,40 @@ import ctypes as C
 from . import _cabi
 
 
+class _SideBatch:
+    """Buffers of the second pass over the environments whose legal list exceeds env.max_actions."""
+
+    def __init__(self, t, dev, m, cap):
+        self.m, self.cap = m, cap
+        self.lo = t.zeros((m, 16), dtype=t.uint8, device=dev)
+        self.hi = t.zeros((m, 16), dtype=t.uint8, device=dev)
+        self.dice = t.ones((m, 2), dtype=t.uint8, device=dev)
+        self.idx = t.full((m,), -1, dtype=t.int32, device=dev)
+        self.ctrl = t.zeros(4, dtype=t.int32, device=dev)
+        self.actions = t.zeros((m, cap), dtype=t.int64, device=dev)
+        self.counts = t.zeros(m, dtype=t.int32, device=dev)
+        self.counts_eff = t.zeros(m, dtype=t.int32, device=dev)
+        self.ovf = t.zeros(m, dtype=t.uint8, device=dev)
+        self.ws = t.zeros(_cabi.workspace_ints(m), dtype=t.int32, device=dev)
+        self.scan_ws = t.zeros((m + 127) // 128 + 4, dtype=t.int64, device=dev)
+        self.offsets = t.zeros(m, dtype=t.int64, device=dev)
+        self.rows_dev = t.zeros(1, dtype=t.int64, device=dev)
+        self.choice = t.zeros(m, dtype=t.int32, device=dev)
+        self.value = t.zeros(m, dtype=t.float32, device=dev)
+
+
 class AfterstateActor:
-    def __init__(self, env, mlp, mode="max"):
+    def __init__(self, env, mlp, mode="max", overflow_slots=None, overflow_cap=2048, overflow_rows=None):
         """env: VecNardeEnv(rules="full"); mlp: AfterstateMLP; mode: "max" (the mover maximises the score)
-        or "white_value" (the net scores positions for WHITE: WHITE maximises, BLACK minimises)."""
+        or "white_value" (the net scores positions for WHITE: WHITE maximises, BLACK minimises).
+
+        Every legal action is scored, as DQNAgent.act does (train_deepq_pytorch.py:430-507): environments whose list
+        is longer than env.max_actions (doubles turns, up to ~1300 actions; 0.5-1 % of the envs in self-play) get a
+        second pass with capacity `overflow_cap` in a side batch of `overflow_slots` environments (default N/16, at
+        least 256) sharing `overflow_rows` afterstate rows (default 192 per slot).  Environments that do not fit --
+        more overflowing envs than slots, a list longer than overflow_cap, or the row pool exhausted -- are counted in
+        `uncovered_envs()` and keep the choice among their first max_actions actions; overflow_slots=0 switches the
+        second pass off."""
         if env.rules != "full":
             raise ValueError("AfterstateActor needs rules='full'")
         if mode not in ("max", "white_value"):
@@ -31,10 +61,20 @@ class AfterstateActor:
         self.scores = t.zeros(n * cap, dtype=t.float32, device=dev)
         self.offsets = t.zeros(n, dtype=t.int64, device=dev)
         self.rows_dev = t.zeros(1, dtype=t.int64, device=dev)
+        self._scan_ws = t.zeros((n + 127) // 128 + 4, dtype=t.int64, device=dev)   # NARDE_AFTERSTATE_SCRATCH_WORDS(n)
         self.choice = t.zeros(n, dtype=t.int32, device=dev)
         self.value = t.zeros(n, dtype=t.float32, device=dev)
         self.dice = t.zeros((n, 2), dtype=t.uint8, device=dev)
         self.lib = _cabi.load()
+        m = max(256, n // 16) if overflow_slots is None else int(overflow_slots)
+        self.side = None
+        if m > 0:
+            self.side = sb = _SideBatch(t, dev, m, int(overflow_cap))
+            rows = int(overflow_rows) if overflow_rows is not None else 192 * m
+            sb.rows_cap = rows
+            sb.as_lo = t.zeros((rows, 16), dtype=t.uint8, device=dev)
+            sb.as_hi = t.zeros((rows, 16), dtype=t.uint8, device=dev)
+            sb.scores = t.zeros(rows, dtype=t.float32, device=dev)
         self._graph = None
         self._enum_ws = t.zeros(_cabi.workspace_ints(n), dtype=t.int32, device=dev)
 
@@ -43,19 +83,54 @@ class AfterstateActor:
 
     def afterstates(self, actions, counts):
         """Fill as_lo/as_hi with the afterstates of actions[i, :min(counts[i], cap)]; returns offsets [N]."""
-        t, env = self.env.torch, self.env
-        c = counts.clamp(max=self.cap).to(t.int64)
-        incl = t.cumsum(c, 0)
-        t.sub(incl, c, out=self.offsets)
-        self.rows_dev.copy_(incl[-1:])
-        rc = self.lib.narde_afterstates(C.c_void_p(env.lo.data_ptr()), C.c_void_p(env.hi.data_ptr()),
-                                        C.c_void_p(actions.data_ptr()), C.c_void_p(counts.data_ptr()),
-                                        C.c_void_p(self.offsets.data_ptr()), env.num_envs, self.cap,
-                                        C.c_void_p(self.as_lo.data_ptr()), C.c_void_p(self.as_hi.data_ptr()), None,
-                                        self._stream())
+        env = self.env
+        # one launch: the device-wide exclusive scan of min(counts, cap) (decoupled look-back), the row count and the
+        # rows themselves (narde_afterstates_scan) -- no host-side prefix sum, no torch ops
+        rc = self.lib.narde_afterstates_scan(C.c_void_p(env.lo.data_ptr()), C.c_void_p(env.hi.data_ptr()),
+                                             C.c_void_p(actions.data_ptr()), C.c_void_p(counts.data_ptr()),
+                                             env.num_envs, self.cap, C.c_void_p(self.offsets.data_ptr()),
+                                             C.c_void_p(self.rows_dev.data_ptr()), C.c_void_p(self.as_lo.data_ptr()),
+                                             C.c_void_p(self.as_hi.data_ptr()), None,
+                                             C.c_void_p(self._scan_ws.data_ptr()), 0, None, self._stream())
         if rc != 0:
-            raise _cabi.NardeCudaError("narde_afterstates failed: %d" % rc)
+            raise _cabi.NardeCudaError("narde_afterstates_scan failed: %d" % rc)
         return self.offsets
+
+    def _overflow_pass(self, dice):
+        """Second pass (see __init__): gather -> enumerate with the large capacity -> afterstates -> score -> arg-max ->
+        scatter into self.choice / self.value.  Seven launches on a few thousand positions; no host synchronisation."""
+        sb, env, P = self.side, self.env, C.c_void_p
+        if sb is None:
+            return
+        st = self._stream()
+        rc = self.lib.narde_gather_overflow(P(env.lo.data_ptr()), P(env.hi.data_ptr()), P(dice.data_ptr()),
+                                            P(env.overflow.data_ptr()), env.num_envs, sb.m, P(sb.lo.data_ptr()),
+                                            P(sb.hi.data_ptr()), P(sb.dice.data_ptr()), P(sb.idx.data_ptr()),
+                                            P(sb.ctrl.data_ptr()), st)
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_gather_overflow failed: %d" % rc)
+        _cabi.enumerate_actions_fast(sb.lo, sb.hi, sb.dice, sb.actions, sb.counts, sb.ovf, sb.ws)
+        rc = self.lib.narde_afterstates_scan(P(sb.lo.data_ptr()), P(sb.hi.data_ptr()), P(sb.actions.data_ptr()),
+                                             P(sb.counts.data_ptr()), sb.m, sb.cap, P(sb.offsets.data_ptr()),
+                                             P(sb.rows_dev.data_ptr()), P(sb.as_lo.data_ptr()), P(sb.as_hi.data_ptr()),
+                                             None, P(sb.scan_ws.data_ptr()), sb.rows_cap, P(sb.counts_eff.data_ptr()), st)
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_afterstates_scan failed: %d" % rc)
+        self.mlp.score_states(sb.as_lo, sb.as_hi, out=sb.scores, rows_dev=sb.rows_dev)
+        rc = self.lib.narde_segment_argmax(P(sb.scores.data_ptr()), P(sb.offsets.data_ptr()), P(sb.counts_eff.data_ptr()),
+                                           P(sb.hi.data_ptr()), sb.m, sb.cap, self.mode, P(sb.choice.data_ptr()),
+                                           P(sb.value.data_ptr()), st)
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
+        rc = self.lib.narde_scatter_choice(P(sb.choice.data_ptr()), P(sb.value.data_ptr()), P(sb.idx.data_ptr()),
+                                           P(sb.counts_eff.data_ptr()), P(sb.counts.data_ptr()), sb.m, sb.cap,
+                                           P(self.choice.data_ptr()), P(self.value.data_ptr()), P(sb.ctrl.data_ptr()), st)
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_scatter_choice failed: %d" % rc)
+
+    def uncovered_envs(self):
+        """Env turns whose choice was made among the first max_actions actions only (one D2H copy)."""
+        return int(self.side.ctrl[2].item()) if self.side is not None else -1
 
     def choose(self):
         """roll -> enumerate -> afterstates -> score -> greedy index.  Returns (choice [N] int32, dice [N,2])."""
@@ -70,6 +145,7 @@ class AfterstateActor:
                                            C.c_void_p(self.value.data_ptr()), self._stream())
         if rc != 0:
             raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
+        self._overflow_pass(self.dice)
         return self.choice, self.dice
 
     def step(self):
@@ -96,6 +172,7 @@ class AfterstateActor:
                                            C.c_void_p(self.value.data_ptr()), self._stream())
         if rc != 0:
             raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
+        self._overflow_pass(self.dice)
         _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, action_idx=self.choice,
                         actions=env.actions if env.write_actions else None, counts=env.counts, dice_out=env.dice,
                         chosen=env.chosen, obs198=env.obs, reward=env.reward, done=env.done, stats=env.stats,

@@ -71,7 +71,10 @@ NHD_NOINLINE int walk_short_double(const Pos& P, int d, bool first_turn, int H, 
 
 constexpr int kL1PerEnv = 5;  // level-1 doubles items a CTA can hold per env (all-doubles CTAs with > 8 sources per env overflow to the sequential walk; never observed)
 
-template <int BLK>
+// BLK = environments per CTA, NT = threads per CTA (NT >= BLK, both multiples of 32).  NT = BLK: a thread per env.
+// NT = 2 BLK: the same work items dealt to twice the threads -- shared memory is what limits the number of
+// environments resident on an SM, so this is how the SM gets more warps (the kernel is latency-bound).
+template <int BLK, int NT = BLK>
 struct BlockShared {
   static constexpr int kL1Cap = kL1PerEnv * BLK;
   State st[BLK];
@@ -96,7 +99,7 @@ struct BlockShared {
   uint16_t itab[BLK * 24];               // ND work items in canonical order: env << 5 | source point
   uint32_t n_l1, n_l2;                   // level-1 / level-2 doubles items of the CTA
   // scan scratch (4 lanes)
-  uint32_t part[4][BLK], base[4][BLK], ws[4][36];
+  uint32_t part[4][NT], base[4][NT], ws[4][36];
 };
 
 template <class BaseT>
@@ -138,10 +141,11 @@ struct ItemIter {  // items (parent e, bit p) over masks[e], parents ascending, 
 
 // DEFER = true: order-dependent doubles turns are handed to the exact CTA-per-env kernel (the caller
 // gave a workspace) and the inline exact walk is not even compiled into the kernel (smaller code).
-template <int BLK, bool DEFER = true>
+template <int BLK, bool DEFER = true, int NT = BLK>
 struct BlockStep {
-  typedef BlockShared<BLK> Sh;
-  static constexpr int PER = BLK / 32;  // partial sums per scan lane
+  typedef BlockShared<BLK, NT> Sh;
+  static_assert(NT >= BLK && NT % 32 == 0 && BLK % 32 == 0, "threads per CTA: a multiple of 32, at least one per env");
+  static constexpr int PER = NT / 32;  // partial sums per scan lane
 
   static NHD Pos pos_of(const Sh& sh, int e) {
     Pos P;
@@ -156,7 +160,7 @@ struct BlockStep {
     return (sh.first[e] && (d == 3 || d == 4 || d == 6)) ? 2 : 1;  // narde.py:100-103, per turn
   }
   static NHD void chunk(int total, int tid, int* j0, int* j1) {
-    int c = (total + BLK - 1) / BLK;
+    int c = (total + NT - 1) / NT;
     int a = tid * c, b = a + c;
     *j0 = a < total ? a : total;
     *j1 = b < total ? b : total;
@@ -171,6 +175,7 @@ struct BlockStep {
     uint32_t policy_word = 0;
     if (valid && A.action_idx && !bulk_words) policy_word = (uint32_t)A.action_idx[i];
     for (int l = 0; l < 4; l++) sh.part[l][tid] = 0;
+    if (NT > BLK && tid >= BLK) return;  // threads beyond the envs only take part in the item phases
     sh.rowmask[tid] = 0;
     sh.dmask[tid] = 0;
     sh.chosen[tid] = ACT_EMPTY;
@@ -254,7 +259,7 @@ struct BlockStep {
   static NHD void ph_scan_serial(int tid, Sh& sh, uint32_t lanes) {
 #if defined(__CUDA_ARCH__)
     const int lane = tid & 31;
-    for (int l = tid >> 5; l < 4; l += BLK / 32) {  // a warp per scan lane (BLK = 128), fewer warps take several
+    for (int l = tid >> 5; l < 4; l += NT / 32) {  // a warp per scan lane (NT = 128), fewer warps take several
       if (!((lanes >> l) & 1u)) continue;
       uint32_t v[PER], sum = 0;
 #pragma unroll
@@ -280,7 +285,7 @@ struct BlockStep {
     if (tid >= 4 || !((lanes >> tid) & 1u)) return;
     const int l = tid;
     uint32_t r = 0;
-    for (int k = 0; k < BLK; k++) {
+    for (int k = 0; k < NT; k++) {
       uint32_t t = sh.part[l][k];
       sh.base[l][k] = r;
       r += t;
@@ -290,6 +295,7 @@ struct BlockStep {
   }
   // after the first scan: bases of the ND row items and of the doubles level-1 items
   static NHD void ph_item_bases(int tid, Sh& sh) {
+    if (NT > BLK && tid >= BLK) return;
     sh.ibase[tid] = sh.base[0][tid];
     sh.dbase[tid] = sh.base[1][tid];
     // item table of the pair rows: every later phase deals out [j0, j1) and reads (env, point) from here
@@ -706,6 +712,7 @@ struct BlockStep {
   }
   // per-env totals into scan lanes 2 (ND) / 3 (doubles): list starts in item space
   static NHD void ph_env_totals(int tid, Sh& sh) {
+    if (NT > BLK && tid >= BLK) return;  // part[2], part[3] of those threads stay 0 (ph_load)
     uint8_t k = sh.kind[tid];
     sh.part[2][tid] = k == K_ND ? sh.etotal[tid] : 0u;
     sh.part[3][tid] = k == K_D ? sh.etotal[tid] : 0u;
@@ -716,7 +723,7 @@ struct BlockStep {
     if (valid && sh.defer[tid]) A.defer_list[gl_fetch_add(A.defer_count, 1)] = (int32_t)i;
   }
   static NHD void ph_env_bases(int tid, Sh& sh) {
-    sh.ebase[tid] = sh.kind[tid] == K_ND ? sh.base[2][tid] : sh.base[3][tid];
+    if (NT == BLK || tid < BLK) sh.ebase[tid] = sh.kind[tid] == K_ND ? sh.base[2][tid] : sh.base[3][tid];
     {  // pair rows: the row's offset inside its env's list goes into the free top byte of its mask (a non-doubles
        // turn has < 15 x 17 legal pairs), so the emit phase can deal the rows round-robin
       int j0, j1;
@@ -752,7 +759,7 @@ struct BlockStep {
     int j0, j1, e, p;
     uint32_t G = 0;
     const int n_nd = (int)sh.ibase[BLK];
-    for (int jj = tid; jj < n_nd; jj += BLK) {  // round-robin: neighbouring threads write neighbouring list slots
+    for (int jj = tid; jj < n_nd; jj += NT) {  // round-robin: neighbouring threads write neighbouring list slots
       const uint32_t v = sh.itab[jj];
       e = (int)(v >> 5);
       p = (int)(v & 31u);
@@ -792,7 +799,7 @@ struct BlockStep {
       const uint16_t* off16 = l2_off(sh);
       const uint32_t t0 = sh.ibase[BLK];
       L2Iter it2;
-      int t = tid, t1 = n2, dt = BLK;
+      int t = tid, t1 = n2, dt = NT;
       if (!fast) {
         chunk(n2, tid, &j0, &j1);
         it2.init(sh, j0, j1);

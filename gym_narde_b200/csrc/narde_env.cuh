@@ -212,6 +212,10 @@ NHD void complete_env(State& s, int64_t i, const StepFullArgs& A, int player, ui
     if (A.counts) A.counts[i] = (int32_t)count;
     if (A.chosen) A.chosen[i] = count ? act : ACT_EMPTY;
     if (A.done) A.done[i] = (uint8_t)L.overflow;  // the "done" output carries the overflow flag in this mode
+    if (A.dice_out) {  // the turn's dice (Philox, or the caller's echoed): a later pass over the same turn needs them
+      A.dice_out[2 * i] = (uint8_t)d1;
+      A.dice_out[2 * i + 1] = (uint8_t)d2;
+    }
     return;
   }
   if (count && apply) apply_action(s, player, act);

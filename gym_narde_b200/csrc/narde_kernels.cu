@@ -25,7 +25,8 @@ namespace {
 constexpr int kThreads = 128;
 // envs (= threads) per CTA of the fused step: 128 for large batches; one-warp CTAs of 32 envs when the batch
 // cannot fill the machine otherwise (4096 envs: 128 CTAs instead of 32; measured 0.081 -> 0.053 ms/step)
-unsigned g_extra_smem = 0;
+int g_variant = 0;
+int g_tile = 64;  // envs per CTA of the large-batch fused step: 64 (two threads per env) or 128 (NARDE_TILE in the environment: A/B timing)
 int64_t kSmallBatch = 16384;  // (NARDE_SMALL_BATCH in the environment overrides it: A/B timing of the two tiles)
 constexpr int kDeferredThreads = 128;  // exact-doubles kernel: four warps per CTA, one env per warp at a time (7 KB of shared memory each)
 constexpr int kDeferredGrid = 148 * 8;  // 8 CTAs per SM (64 registers, 27 KB)
@@ -212,25 +213,42 @@ __device__ unsigned long long* g_dbg_clk = nullptr;
   do {                                                                                 \
     if (g_dbg_clk && threadIdx.x == 0) g_dbg_clk[(size_t)blockIdx.x * 16 + (k)] = clock64(); \
   } while (0)
+__device__ __forceinline__ unsigned long long dbg_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wall-clock (ns, one timer for the whole GPU) marks: rows [0, 2048) slots 10/11 = a main CTA's start / end,
+// rows [3072 + block) slots 0..4 = a CTA of the exact kernel (tools/timeline_probe.py)
+#define GT_MARK(row, k)                                                                          \
+  do {                                                                                           \
+    if (g_dbg_clk && threadIdx.x == 0) g_dbg_clk[(size_t)(row) * 16 + (k)] = dbg_globaltimer();  \
+  } while (0)
 #else
 #define PHASE_MARK(k) do { } while (0)
+#define GT_MARK(row, k) do { } while (0)
 #endif
 
 // Fused full-rules step, CTA-cooperative (narde_block.cuh): the phases run with a CTA barrier
 // between them; everything between the state load and the Box(198) store stays in shared memory.
-template <int BLK, bool DEFER>
-__global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int64_t n, StepFullArgs A_in, float* obs198,
-                                                      int64_t* stats) {
-  typedef BlockStep<BLK, DEFER> BS;
+// BLK envs per CTA, NT threads.  <64, ., 128> is the large-batch tile: the kernel is latency-bound (a warp issues once
+// in ~8 cycles) and shared memory holds ~350 B per env, so with a thread per env an SM tops out at 20 warps; two
+// threads per env and a 64-register budget (8 CTAs of 128 threads) give it 32.
+// MINB: CTAs per SM the register budget is cut for (65536 / (NT * MINB) registers per thread).
+template <int BLK, bool DEFER, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_step_full_v2(uint4* lo, uint4* hi, int64_t n, StepFullArgs A_in, float* obs198,
+                                                           int64_t* stats) {
+  typedef BlockStep<BLK, DEFER, NT> BS;
   StepFullArgs A = A_in;
   if (A.step_dev) A.step = *A.step_dev + ((A.flags & F_DEVICE_ADVANCE) ? 1u : 0u);
-  __shared__ BlockShared<BLK> sh;
+  __shared__ BlockShared<BLK, NT> sh;
   const int tid = threadIdx.x;
   const int64_t row0 = (int64_t)blockIdx.x * BLK;
   const int64_t i = row0 + tid;
-  const bool valid = i < n;
+  const bool valid = (NT == BLK || tid < BLK) && i < n;
   State s;
   PHASE_MARK(0);
+  GT_MARK(blockIdx.x, 10);
   // The caller's action words of this CTA (BLK x 4 B, contiguous) come in as ONE bulk asynchronous copy into
   // shared memory.  When the buffer is pinned host memory (zero-copy step_host) that is one PCIe read of 512 B
   // per CTA instead of a 32-byte read per warp sector: the host step was bound by the NUMBER of small reads.
@@ -336,6 +354,7 @@ __global__ void __launch_bounds__(BLK) k_step_full_v2(uint4* lo, uint4* hi, int6
   write_obs198_cta(sh.st, lut, rows, row0, obs198, sh.defer);
   __syncthreads();
   PHASE_MARK(9);
+  GT_MARK(blockIdx.x, 11);
 }
 
 // Exact doubles turns handed over by k_step_full_v2 (narde_deferred.cuh).  A short list (self-play: ~0.2 % of the envs,
@@ -419,6 +438,7 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
   __shared__ int32_t s_last;
   obs_lut_init(lut);
   const int tid = threadIdx.x;
+  GT_MARK(3072 + blockIdx.x, 0);
   // Launched as a programmatic dependent of k_step_full_v2: this grid starts once every main CTA has executed its
   // trigger, which each does AFTER its release-add to `arrivals` -- so the acquire below never really waits, it
   // makes the list entries of all main CTAs formally visible here although the main grid is still running.
@@ -429,6 +449,7 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
     } while (seen < A.n_primary);
   }
   __syncthreads();
+  GT_MARK(3072 + blockIdx.x, 1);
   int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
 #ifdef NARDE_DEBUG_HOOKS
   if (g_dbg_flags & 4) n_def = 0;  // timing experiment only (wrong results): the deferred envs are not solved
@@ -454,8 +475,10 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
       exact_env<32>(ex, sm.warp[tid >> 5], lut, lo, hi, list[q], A, obs198, stats);
     }
   }
+  GT_MARK(3072 + blockIdx.x, 2);
   // stream order: this grid must not complete before its primary has (the next step follows it)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  GT_MARK(3072 + blockIdx.x, 3);
   // F_DEVICE_ADVANCE: the step's own bookkeeping instead of a memset and a counter kernel in front of every step
   // (each is a node of the step's CUDA graph, ~2 us).  Every CTA of this grid is done with the list and has read the
   // step index before it arrives here, and the primary grid is complete: the last arrival clears the list and its
@@ -478,6 +501,7 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
       }
     }
   }
+  GT_MARK(3072 + blockIdx.x, 4);
 }
 
 __global__ void __launch_bounds__(kThreads) k_obs198(const uint4* lo, const uint4* hi, int64_t n, float* obs198) {
@@ -540,6 +564,176 @@ __global__ void __launch_bounds__(kThreads) k_afterstates(const uint4* lo, const
     st_state(as_lo, as_hi, base + k, t);
     if (row_env) row_env[base + k] = (int32_t)i;
   }
+}
+
+// Afterstate rows in ONE pass (replaces a host-side clamp / cumsum / subtract / copy chain and the thread-per-env
+// kernel above): a CTA owns a tile of 128 environments.  Row offsets are a device-wide exclusive scan of
+// min(count, cap) done inside the kernel as a decoupled look-back: tiles are handed out by a ticket (so every tile with
+// a smaller number is already running), a CTA publishes its tile total tagged with the launch epoch and then sums the
+// totals of the tiles before it (warp 0, 32 tiles per trip).  Rows are then dealt to the threads one by one -- thread r
+// finds its (env, action) by a search over the tile's 128 offsets in shared memory -- so neighbouring threads read
+// neighbouring action words and write neighbouring 16-byte row halves, whatever the counts are.
+// scratch (u64 words, zeroed once by the caller, restored by the last CTA of every launch):
+//   [0] ticket  [1] finished CTAs  [2] launch epoch  [4 ..] one word per tile: epoch << 32 | rows of the tile.
+__global__ void __launch_bounds__(kThreads) k_afterstates_scan(const uint4* lo, const uint4* hi, const uint64_t* actions,
+                                                              const int32_t* counts, int64_t n, int cap, int64_t* offsets,
+                                                              int64_t* rows_out, uint4* as_lo, uint4* as_hi, int32_t* row_env,
+                                                              unsigned long long* scratch, int64_t rows_cap,
+                                                              int32_t* counts_eff) {
+  __shared__ State st[kThreads];
+  __shared__ uint32_t excl[kThreads + 1];
+  __shared__ uint32_t wtot[kThreads / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = (uint32_t)atomicAdd(&scratch[0], 1ull);
+  __syncthreads();
+  const uint32_t tile = s_tile, ntiles = gridDim.x;
+  unsigned long long epoch = (*reinterpret_cast<volatile unsigned long long*>(&scratch[2]) + 1ull) & 0xFFFFFFFFull;
+  if (epoch == 0ull) epoch = 1ull;  // 0 is the tag of a never-written word
+  const int64_t row0 = (int64_t)tile * kThreads, i = row0 + tid;
+  uint32_t c = 0;
+  if (i < n) {
+    st[tid] = ld_state(lo, hi, i);
+    const int cc = counts[i];
+    c = (uint32_t)(cc < 0 ? 0 : cc < cap ? cc : cap);
+  }
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; w++) {
+    if (w < warp) before += wtot[w];
+    total += wtot[w];
+  }
+  excl[tid] = before + incl - c;
+  if (tid == 0) {
+    excl[kThreads] = total;
+    atomicExch(&scratch[4 + tile], (epoch << 32) | (unsigned long long)total);  // publish before looking back
+  }
+  if (warp == 0) {  // look-back: rows of all tiles before this one
+    unsigned long long sum = 0;
+    for (int64_t j0 = (int64_t)tile - 1; j0 >= 0; j0 -= 32) {
+      const int64_t j = j0 - lane;
+      if (j >= 0) {
+        unsigned long long v;
+        do {
+          v = *reinterpret_cast<volatile unsigned long long*>(&scratch[4 + j]);
+        } while ((v >> 32) != epoch);
+        sum += v & 0xFFFFFFFFull;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) {
+      s_base = sum;
+      if (tile == ntiles - 1 && rows_out) {
+        const int64_t all = (int64_t)(sum + total);
+        *rows_out = rows_cap > 0 && all > rows_cap ? rows_cap : all;
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t base = (int64_t)s_base;
+  if (i < n && offsets) offsets[i] = base + excl[tid];
+  // a bounded row pool (rows_cap > 0): an env whose rows do not all fit has no rows at all (counts_eff = 0)
+  if (i < n && counts_eff) counts_eff[i] = (rows_cap <= 0 || base + excl[tid] + c <= rows_cap) ? (int32_t)c : 0;
+  for (uint32_t r = (uint32_t)tid; r < total; r += kThreads) {
+    if (rows_cap > 0 && base + r >= rows_cap) break;
+    int a = 0, b = kThreads - 1;  // the last env whose first row is <= r (envs without rows share their successor's offset)
+    while (a < b) {
+      const int mid = (a + b + 1) >> 1;
+      if (excl[mid] <= r) a = mid; else b = mid - 1;
+    }
+    const int e = a;
+    const uint32_t k = r - excl[e];
+    State t = st[e];
+    float rw;
+    int dn;
+    apply_actions_env(t, actions[(row0 + e) * (int64_t)cap + k], 0, &rw, &dn);
+    st_state(as_lo, as_hi, base + r, t);
+    if (row_env) row_env[base + r] = (int32_t)(row0 + e);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&scratch[1], 1ull) == (unsigned long long)ntiles - 1ull) {  // every CTA is past its look-back
+      scratch[0] = 0ull;
+      scratch[1] = 0ull;
+      scratch[2] = epoch;
+      __threadfence();
+    }
+  }
+}
+
+// Second pass of the greedy actor for environments whose legal list exceeds the stored capacity (0.5-1 % of the envs
+// in self-play, up to ~1300 actions): their states and dice are gathered into a small side batch that is enumerated
+// with a large capacity, scored and arg-maxed like the main batch; k_scatter_choice puts the results back.
+// ctrl: [0] overflowing envs seen (all of them, also beyond m), [1] finished CTAs, [2] envs not covered so far (total).
+// Slots beyond the gathered ones are marked finished games (no legal action, no afterstate rows) by the last CTA.
+__global__ void __launch_bounds__(kThreads) k_gather_overflow(const uint4* lo, const uint4* hi, const uint8_t* dice,
+                                                             const uint8_t* overflow, int64_t n, int m, uint4* sub_lo,
+                                                             uint4* sub_hi, uint8_t* sub_dice, int32_t* sub_idx, int32_t* ctrl) {
+  __shared__ int s_last;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && overflow[i]) {
+    const int slot = atomicAdd(&ctrl[0], 1);
+    if (slot < m) {
+      sub_lo[slot] = lo[i];
+      sub_hi[slot] = hi[i];
+      reinterpret_cast<uint16_t*>(sub_dice)[slot] = reinterpret_cast<const uint16_t*>(dice)[i];
+      sub_idx[slot] = (int32_t)i;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&ctrl[1], 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int seen = *reinterpret_cast<volatile int32_t*>(&ctrl[0]);
+  State fin;
+  for (int k = 0; k < 6; k++) fin.w[k] = 0;
+  fin.set_meta(15, 0, 1, FLAG_DONE);
+  fin.aux = 0;
+  for (int sl = (seen < m ? seen : m) + (int)threadIdx.x; sl < m; sl += (int)blockDim.x) {
+    st_state(sub_lo, sub_hi, sl, fin);
+    reinterpret_cast<uint16_t*>(sub_dice)[sl] = 0x0101;
+    sub_idx[sl] = -1;
+  }
+  if (threadIdx.x == 0) {
+    ctrl[1] = 0;
+    if (seen > m) ctrl[2] += seen - m;
+  }
+}
+__global__ void __launch_bounds__(1024) k_scatter_choice(const int32_t* sub_choice, const float* sub_value, const int32_t* sub_idx,
+                                                        const int32_t* sub_counts_eff, const int32_t* sub_counts, int m, int cap,
+                                                        int32_t* choice, float* value, int32_t* ctrl) {
+  const int seen = ctrl[0];
+  const int used = seen < m ? seen : m;
+  int missed = 0;
+  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
+    const int32_t i = sub_idx[sl];
+    if (i < 0) continue;
+    if (sub_counts_eff && sub_counts_eff[sl] == 0) {  // its rows did not fit the row pool: the first pass's choice stands
+      missed++;
+      continue;
+    }
+    if (sub_counts && sub_counts[sl] > cap) missed++;  // longer than the side batch's capacity: best of the first `cap`
+    choice[i] = sub_choice[sl];
+    if (value && sub_value) value[i] = sub_value[sl];
+  }
+  if (missed) atomicAdd(&ctrl[2], missed);
+  __syncthreads();
+  if (threadIdx.x == 0) ctrl[0] = 0;  // ready for the next turn's gather
 }
 
 // Greedy choice per env over its segment of afterstate scores: mode 0 = maximise; mode 1 = WHITE
@@ -654,10 +848,10 @@ int narde_abi_version(void) {
     if (v && v[0] == '1') g_use_pdl = false;
     v = getenv("NARDE_SMALL_BATCH");
     if (v) kSmallBatch = atoll(v);
-#ifdef NARDE_DEBUG_HOOKS
-    v = getenv("NARDE_EXTRA_SMEM");  // occupancy experiment: unused dynamic shared memory per main CTA (fewer CTAs per SM)
-    if (v) g_extra_smem = (unsigned)atoi(v);
-#endif
+    v = getenv("NARDE_TILE");
+    if (v && atoi(v) == 128) g_tile = 128;
+    v = getenv("NARDE_VARIANT");
+    if (v) g_variant = atoi(v);
     env_read = true;
   }
   // one-time function attributes are set here (outside any stream capture)
@@ -783,7 +977,7 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
     A.arrivals = workspace + 2;
     A.last_count = workspace + 3;
     A.defer_list = workspace + NARDE_WORKSPACE_HEADER;
-    A.n_primary = (int32_t)(n <= kSmallBatch ? (n + 31) / 32 : (n + 127) / 128);
+    A.n_primary = (int32_t)(n <= kSmallBatch ? (n + 31) / 32 : (n + g_tile - 1) / g_tile);
     if (dev_advance) {  // the three counters are zero on entry and again on exit
       A.ticket = workspace + 1;
     } else {
@@ -796,15 +990,35 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
   if (n <= kSmallBatch) {
     const int g = (int)((n + 31) / 32);
     if (workspace)
-      k_step_full_v2<32, true><<<g, 32, 0, st>>>(plo, phi, n, A, obs198, stats);
+      k_step_full_v2<32, true, 32, 1><<<g, 32, 0, st>>>(plo, phi, n, A, obs198, stats);
     else
-      k_step_full_v2<32, false><<<g, 32, 0, st>>>(plo, phi, n, A, obs198, stats);
+      k_step_full_v2<32, false, 32, 1><<<g, 32, 0, st>>>(plo, phi, n, A, obs198, stats);
+  } else if (g_tile == 64) {
+    const int g = (int)((n + 63) / 64);
+    if (!workspace)
+      k_step_full_v2<64, false, 128, 8><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
+#ifdef NARDE_DEBUG_HOOKS  // A/B variants of the tile (NARDE_VARIANT): register budget / threads per env
+    else if (g_variant == 1)
+      k_step_full_v2<64, true, 128, 5><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
+    else if (g_variant == 2)
+      k_step_full_v2<64, true, 128, 6><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
+    else if (g_variant == 3)
+      k_step_full_v2<64, true, 64, 10><<<g, 64, 0, st>>>(plo, phi, n, A, obs198, stats);
+#endif
+    else
+      k_step_full_v2<64, true, 128, 8><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
   } else {
     const int g = (int)((n + 127) / 128);
-    if (workspace)
-      k_step_full_v2<128, true><<<g, 128, g_extra_smem, st>>>(plo, phi, n, A, obs198, stats);
+    if (!workspace)
+      k_step_full_v2<128, false, 128, 5><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
+#ifdef NARDE_DEBUG_HOOKS
+    else if (g_variant == 1)
+      k_step_full_v2<128, true, 128, 8><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
+    else if (g_variant == 2)
+      k_step_full_v2<128, true, 256, 4><<<g, 256, 0, st>>>(plo, phi, n, A, obs198, stats);
+#endif
     else
-      k_step_full_v2<128, false><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
+      k_step_full_v2<128, true, 128, 5><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
   }
   if (workspace) {
     if (g_use_pdl) {
@@ -856,6 +1070,39 @@ int narde_afterstates(const void* lo, const void* hi, const uint64_t* actions, c
   if (!aligned16(lo) || !aligned16(hi) || !aligned16(as_lo) || !aligned16(as_hi)) return -1;
   k_afterstates<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, actions, counts, offsets, n,
                                                                     cap, (uint4*)as_lo, (uint4*)as_hi, row_env);
+  return launch_status();
+}
+
+int narde_afterstates_scan(const void* lo, const void* hi, const uint64_t* actions, const int32_t* counts, int64_t n,
+                           int32_t cap, int64_t* offsets, int64_t* rows_out, void* as_lo, void* as_hi, int32_t* row_env,
+                           uint64_t* scratch, int64_t rows_cap, int32_t* counts_eff, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || cap <= 0 || !lo || !hi || !actions || !counts || !as_lo || !as_hi || !scratch) return -1;
+  if (!aligned16(lo) || !aligned16(hi) || !aligned16(as_lo) || !aligned16(as_hi) || (((uintptr_t)scratch) & 7u) != 0) return -1;
+  k_afterstates_scan<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, actions, counts, n, cap,
+                                                                         offsets, rows_out, (uint4*)as_lo, (uint4*)as_hi, row_env,
+                                                                         reinterpret_cast<unsigned long long*>(scratch), rows_cap,
+                                                                         counts_eff);
+  return launch_status();
+}
+
+int narde_gather_overflow(const void* lo, const void* hi, const uint8_t* dice, const uint8_t* overflow, int64_t n, int32_t m,
+                          void* sub_lo, void* sub_hi, uint8_t* sub_dice, int32_t* sub_idx, int32_t* ctrl, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || m <= 0 || !lo || !hi || !dice || !overflow || !sub_lo || !sub_hi || !sub_dice || !sub_idx || !ctrl) return -1;
+  if (!aligned16(lo) || !aligned16(hi) || !aligned16(sub_lo) || !aligned16(sub_hi)) return -1;
+  if ((((uintptr_t)dice) & 1u) != 0 || (((uintptr_t)sub_dice) & 1u) != 0) return -1;
+  k_gather_overflow<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, dice, overflow, n, m,
+                                                                        (uint4*)sub_lo, (uint4*)sub_hi, sub_dice, sub_idx, ctrl);
+  return launch_status();
+}
+
+int narde_scatter_choice(const int32_t* sub_choice, const float* sub_value, const int32_t* sub_idx, const int32_t* sub_counts_eff,
+                         const int32_t* sub_counts, int32_t m, int32_t cap, int32_t* choice, float* value, int32_t* ctrl,
+                         void* stream) {
+  if (m <= 0 || !sub_choice || !sub_idx || !choice || !ctrl) return -1;
+  k_scatter_choice<<<1, 1024, 0, (cudaStream_t)stream>>>(sub_choice, sub_value, sub_idx, sub_counts_eff, sub_counts, m, cap, choice,
+                                                         value, ctrl);
   return launch_status();
 }
 

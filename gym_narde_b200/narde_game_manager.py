@@ -370,7 +370,8 @@ class NardeGameManager:
             lo = torch.frombuffer(bytearray(node.lo), dtype=torch.uint8).reshape(1, 16).cuda()
             hi = torch.frombuffer(bytearray(node.hi), dtype=torch.uint8).reshape(1, 16).cuda()
             return ai_model.forward_states(lo, hi)[0].float().cpu()
-        obs = torch.as_tensor(np.asarray(self.env._get_obs(), dtype=np.float32)).unsqueeze(0).to(device)
+        env = getattr(self.env, "unwrapped", self.env)      # make() may have wrapped the env (TimeLimit)
+        obs = torch.as_tensor(np.asarray(env._get_obs(), dtype=np.float32)).unsqueeze(0).to(device)
         with torch.no_grad():
             return ai_model.forward(obs)[0].float().cpu()
 

@@ -210,6 +210,32 @@ int narde_afterstates(const void *lo, const void *hi, const uint64_t *actions, c
                       const int64_t *offsets, int64_t n, int32_t cap, void *as_lo, void *as_hi,
                       int32_t *row_env, void *stream);
 
+/* The same rows with the offsets computed on the device in the same launch (no host-side prefix sum): offsets
+ * (may be NULL) receives the exclusive prefix sums of min(counts, cap), *rows_out (may be NULL) the total number of
+ * rows.  scratch: NARDE_AFTERSTATE_SCRATCH_WORDS(n) u64 words, zero before the first call; every call leaves them
+ * ready for the next one (calls sharing a scratch buffer must be stream-ordered).
+ * rows_cap > 0 bounds the row buffers: rows at or beyond rows_cap are not written, *rows_out is clipped to it, and
+ * counts_eff (may be NULL; [n] i32) receives min(counts, cap) for environments whose rows all fit and 0 otherwise. */
+#define NARDE_AFTERSTATE_SCRATCH_WORDS(n) (((n) + 127) / 128 + 4)
+int narde_afterstates_scan(const void *lo, const void *hi, const uint64_t *actions, const int32_t *counts,
+                           int64_t n, int32_t cap, int64_t *offsets, int64_t *rows_out, void *as_lo, void *as_hi,
+                           int32_t *row_env, uint64_t *scratch, int64_t rows_cap, int32_t *counts_eff, void *stream);
+
+/* Environments whose legal list exceeds the stored capacity (overflow[i] != 0, as narde_enumerate_fast reports it) are
+ * copied -- state planes, dice, env index -- into a side batch of m slots, to be enumerated again with a large capacity
+ * (DQNAgent.act, train_deepq_pytorch.py:430-507, looks at every legal move, not at the first `cap`).  Unused slots become
+ * finished games (no legal action).  ctrl: 4 i32 words, zero before the first call: [0] overflowing envs of this call
+ * (cleared by narde_scatter_choice), [2] running total of envs that did not fit into m slots.
+ * narde_scatter_choice writes choice[sub_idx[s]] = sub_choice[s] (and value, if given) for the gathered slots; a slot
+ * with sub_counts_eff[s] == 0 (no afterstate rows: row pool exhausted) is skipped, and it as well as a slot with
+ * sub_counts[s] > cap (list longer than the side capacity) adds one to ctrl[2]. */
+int narde_gather_overflow(const void *lo, const void *hi, const uint8_t *dice, const uint8_t *overflow, int64_t n,
+                          int32_t m, void *sub_lo, void *sub_hi, uint8_t *sub_dice, int32_t *sub_idx, int32_t *ctrl,
+                          void *stream);
+int narde_scatter_choice(const int32_t *sub_choice, const float *sub_value, const int32_t *sub_idx,
+                         const int32_t *sub_counts_eff, const int32_t *sub_counts, int32_t m, int32_t cap,
+                         int32_t *choice, float *value, int32_t *ctrl, void *stream);
+
 /* Greedy policy over each environment's segment of afterstate scores: idx_out[i] = argmax_k
  * score[offsets[i] + k] (mode 0), or argmin when BLACK is to move (mode 1: the net scores positions for
  * WHITE).  best_out (may be NULL): the chosen score.  Ties: lowest index; empty segment: 0. */

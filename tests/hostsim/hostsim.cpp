@@ -143,32 +143,34 @@ int hs_enumerate_fast(const void* lo, const void* hi, const uint8_t* dice, int64
 
 static int64_t g_small_batch = 16384;
 extern "C" void hs_set_small_batch(int64_t v) { g_small_batch = v; }
+static int g_tile = 64;   // large-batch tile, as in narde_kernels.cu: 64 envs on 128 threads (default) or 128 on 128
+extern "C" void hs_set_tile(int v) { g_tile = v; }
 
 // CTA-cooperative step (narde_block.cuh) emulated phase by phase: every phase runs for all tids
 // of a block before the next one starts, which is what __syncthreads() guarantees on the GPU.
-template <int BLK, bool DEFER>
+template <int BLK, bool DEFER, int NT = BLK>
 static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs& A, float* obs198, int64_t* stats) {
-  typedef BlockStep<BLK, DEFER> BS;
-  static BlockShared<BLK> sh;
+  typedef BlockStep<BLK, DEFER, NT> BS;
+  static BlockShared<BLK, NT> sh;
   for (int64_t row0 = 0; row0 < n; row0 += BLK) {
-    for (int t = 0; t < BLK; t++) {
-      bool valid = row0 + t < n;
+    for (int t = 0; t < NT; t++) {
+      bool valid = t < BLK && row0 + t < n;
       State s;
       if (valid) s = load_state(lo, hi, row0 + t);
       BS::ph_load(t, sh, valid, s, row0 + t, A);
     }
     // NOTE: phases fused between two barriers on the GPU are emulated in DESCENDING tid order as
     // well as ascending elsewhere, so that a read-after-write hazard inside a fused pair shows up
-    for (int t = 0; t < BLK; t++) BS::ph_scan_serial(t, sh, 0x3u);
-    for (int t = BLK - 1; t >= 0; t--) BS::ph_item_bases(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_rows(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_scan_serial(t, sh, 0x2u);
-    for (int t = 0; t < BLK; t++) BS::ph_l2_bases(t, sh);
-    for (int t = BLK - 1; t >= 0; t--) BS::ph_count(t, sh);
-    for (int t = 0; t < BLK; t++) { BS::ph_env_totals(t, sh); if (DEFER) BS::ph_defer_push(t, sh, row0 + t < n, row0 + t, A); }
-    for (int t = 0; t < BLK; t++) BS::ph_scan_serial(t, sh, 0xFu);
-    for (int t = BLK - 1; t >= 0; t--) BS::ph_env_bases(t, sh);
-    for (int t = 0; t < BLK; t++) BS::ph_emit(t, sh, row0, A);
+    for (int t = 0; t < NT; t++) BS::ph_scan_serial(t, sh, 0x3u);
+    for (int t = NT - 1; t >= 0; t--) BS::ph_item_bases(t, sh);
+    for (int t = 0; t < NT; t++) BS::ph_rows(t, sh);
+    for (int t = 0; t < NT; t++) BS::ph_scan_serial(t, sh, 0x2u);
+    for (int t = 0; t < NT; t++) BS::ph_l2_bases(t, sh);
+    for (int t = NT - 1; t >= 0; t--) BS::ph_count(t, sh);
+    for (int t = 0; t < NT; t++) { BS::ph_env_totals(t, sh); if (DEFER) BS::ph_defer_push(t, sh, t < BLK && row0 + t < n, row0 + t, A); }
+    for (int t = 0; t < NT; t++) BS::ph_scan_serial(t, sh, 0xFu);
+    for (int t = NT - 1; t >= 0; t--) BS::ph_env_bases(t, sh);
+    for (int t = 0; t < NT; t++) BS::ph_emit(t, sh, row0, A);
     for (int t = 0; t < BLK; t++) {
       bool valid = row0 + t < n;
       StepFullLocal L;
@@ -243,6 +245,11 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
       step_full_v2_host<32, true>(lo, hi, n, A, obs198, stats);
     else
       step_full_v2_host<32, false>(lo, hi, n, A, obs198, stats);
+  } else if (g_tile == 64) {
+    if (workspace)
+      step_full_v2_host<64, true, 128>(lo, hi, n, A, obs198, stats);
+    else
+      step_full_v2_host<64, false, 128>(lo, hi, n, A, obs198, stats);
   } else if (workspace) {
     step_full_v2_host<128, true>(lo, hi, n, A, obs198, stats);
   } else {

@@ -51,6 +51,8 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert lib.narde_mlp_forward_states(None, None, 4, None, None, None, None) == -1
     assert lib.narde_mlp_score_states(None, None, 4, None, None, None, None, None) == -1
     assert lib.narde_afterstates(None, None, None, None, None, 4, 8, None, None, None, None) == -1
+    assert lib.narde_afterstates_scan(None, None, None, None, 0, 8, None, None, None, None, None, None, 0, None, None) == 0
+    assert lib.narde_afterstates_scan(None, None, None, None, 4, 8, None, None, None, None, None, None, 0, None, None) == -1
     assert lib.narde_segment_argmax(None, None, None, None, 4, 8, 0, None, None, None) == -1
     assert lib.narde_mlp_forward(None, -3, None, None, None, None) == -1
     assert lib.narde_mlp_forward_move2(None, 0, None, None, None, None, None, None) == 0

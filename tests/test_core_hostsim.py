@@ -120,15 +120,20 @@ def _v1_v2_equal(hostsim, lo, hi, **kw):
 
 
 def test_block_kernel_tile_128_equals_per_thread_body(hostsim):
-    """The library uses 32-env one-warp CTAs for batches <= 16384 and 128-env CTAs above; force the 128-env
-    tile on small inputs so that both are checked here (the other tests run the 32-env tile)."""
+    """The library uses 32-env one-warp CTAs for batches <= 16384 and, above, 64-env CTAs of 128 threads (two threads
+    per env in the item phases; NARDE_TILE=128 selects the older 128-env / 128-thread tile); force both large tiles on
+    small inputs so that all three are checked here (the other tests run the 32-env tile)."""
     import ctypes as C
     hostsim.lib.hs_set_small_batch(C.c_int64(0))
     try:
-        test_block_kernel_equals_per_thread_body(hostsim)
-        P.check_step_full_lockstep(hostsim, 200, 120, 0xBEEF)
+        for tile in (64, 128):
+            hostsim.lib.hs_set_tile(C.c_int(tile))
+            test_block_kernel_equals_per_thread_body(hostsim)
+            P.check_step_full_lockstep(hostsim, 200, 120, 0xBEEF)
+            P.check_step_full_lockstep(hostsim, 67, 60, 0xF00D + tile, cap=4)
     finally:
         hostsim.lib.hs_set_small_batch(C.c_int64(16384))
+        hostsim.lib.hs_set_tile(C.c_int(64))
 
 
 def test_block_kernel_equals_per_thread_body(hostsim):

@@ -53,7 +53,7 @@ def test_actor_choice_is_segment_argmax_and_step_plays_it():
     n, cap = 2048, 64
     for mode in ("max", "white_value"):
         env = VecNardeEnv(n, seed=9, max_actions=cap)
-        actor = AfterstateActor(env, mlp, mode=mode)
+        actor = AfterstateActor(env, mlp, mode=mode, overflow_slots=0)   # the first pass alone (stored lists only)
         env.reset()
         for t in range(60):
             turn = env.hi[:, 10].view(torch.int8).clone()          # +1 WHITE / -1 BLACK to move
@@ -100,3 +100,98 @@ def test_actor_graph_replay_equals_eager_turns():
         assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[0].reward, envs[1].reward)
         assert torch.equal(envs[0].chosen, envs[1].chosen)
     assert envs[0].episode_stats() == envs[1].episode_stats()
+
+
+def test_afterstates_scan_equals_host_prefix_sum_version():
+    """narde_afterstates_scan (offsets by an in-kernel decoupled look-back scan, rows dealt to threads) against
+    narde_afterstates fed with torch's exclusive prefix sum: offsets, row count, rows and row->env map, at ragged
+    sizes around the 128-env tile, with one scratch buffer reused across calls of different sizes."""
+    import ctypes as C
+    import torch
+    from gym_narde_b200 import VecNardeEnv, _cabi
+    lib = _cabi.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    scratch = torch.zeros(4096 // 128 + 5, dtype=torch.int64, device="cuda")
+    for n, cap, steps in ((1, 8, 3), (127, 16, 10), (129, 64, 25), (3000, 24, 40), (4096, 64, 60)):
+        env = VecNardeEnv(n, seed=77 + n, max_actions=cap)
+        env.reset()
+        for _ in range(steps):
+            env.step()
+        acts, counts, _ = env.get_valid_actions()
+        c = counts.clamp(max=cap).long()
+        off_ref = torch.cumsum(c, 0) - c
+        K = int(c.sum().item())
+        ref_lo = torch.zeros((K + 1, 16), dtype=torch.uint8, device="cuda")
+        ref_hi = torch.zeros_like(ref_lo)
+        ref_env = torch.full((K + 1,), -1, dtype=torch.int32, device="cuda")
+        assert lib.narde_afterstates(P(env.lo), P(env.hi), P(acts), P(counts), P(off_ref), n, cap, P(ref_lo), P(ref_hi),
+                                     P(ref_env), st) == 0
+        for rep in range(2):           # the scratch words are left ready for the next call
+            lo2, hi2 = torch.zeros_like(ref_lo), torch.zeros_like(ref_hi)
+            env2 = torch.full_like(ref_env, -1)
+            off = torch.full((n,), -7, dtype=torch.int64, device="cuda")
+            rows = torch.zeros(1, dtype=torch.int64, device="cuda")
+            assert lib.narde_afterstates_scan(P(env.lo), P(env.hi), P(acts), P(counts), n, cap, P(off), P(rows), P(lo2),
+                                              P(hi2), P(env2), P(scratch), 0, None, st) == 0
+            assert int(rows.item()) == K
+            assert torch.equal(off, off_ref)
+            assert torch.equal(lo2, ref_lo) and torch.equal(hi2, ref_hi) and torch.equal(env2, ref_env)
+
+
+def test_actor_scores_every_legal_action_beyond_the_stored_capacity():
+    """the greedy choice must look at EVERY legal action (DQNAgent.act, train_deepq_pytorch.py:430-507), not
+    at the first env.max_actions.  With a tiny stored capacity most envs overflow; the actor's choice (main pass +
+    side-batch pass) must equal the arg-max over the complete list enumerated with a capacity that holds everything."""
+    import ctypes as C
+    import torch
+    from gym_narde_b200 import VecNardeEnv, AfterstateMLP, AfterstateActor, _cabi
+    fn, head = _net()
+    mlp = AfterstateMLP.from_module(fn, head)
+    lib = _cabi.load()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    n, cap, big = 1536, 8, 2048
+    for mode in ("max", "white_value"):
+        env = VecNardeEnv(n, seed=31, max_actions=cap)
+        actor = AfterstateActor(env, mlp, mode=mode, overflow_slots=n, overflow_cap=big, overflow_rows=400 * n)
+        env.reset()
+        acts_b = torch.zeros((n, big), dtype=torch.int64, device="cuda")
+        cnt_b = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ws = torch.zeros(_cabi.workspace_ints(n), dtype=torch.int32, device="cuda")
+        overflowed = beyond = 0
+        for t in range(70):
+            turn = env.hi[:, 10].view(torch.int8).clone().float()
+            choice, dice = actor.choose()
+            _cabi.enumerate_actions_fast(env.lo, env.hi, dice, acts_b, cnt_b, None, ws)
+            c = cnt_b.long()
+            assert int(c.max().item()) <= big
+            off = torch.cumsum(c, 0) - c
+            K = int(c.sum().item())
+            lo2 = torch.zeros((K + 1, 16), dtype=torch.uint8, device="cuda")
+            hi2 = torch.zeros_like(lo2)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            assert lib.narde_afterstates(P(env.lo), P(env.hi), P(acts_b), P(cnt_b), P(off), n, big, P(lo2), P(hi2), None, st) == 0
+            sc = mlp.score_states(lo2[:K].contiguous(), hi2[:K].contiguous())
+            dense = torch.full((n, int(c.max().item()) + 1), float("-inf"), device="cuda")
+            col = torch.arange(dense.shape[1], device="cuda")[None, :]
+            mask = col < c[:, None]
+            dense[mask] = sc
+            if mode == "white_value":
+                dense = torch.where(mask, dense * turn[:, None], dense)
+            want = dense.argmax(1)
+            live = c > 0
+            assert torch.equal(choice.long()[live], want[live]), (mode, t)
+            overflowed += int((c > cap).sum().item())
+            beyond += int((want[live] >= cap).sum().item())
+            chosen_act = acts_b[torch.arange(n, device="cuda"), choice.long()].clone()
+            env.step(choice, dice=dice)
+            assert torch.equal(env.chosen[live], chosen_act[live])     # the step plays it although it was never stored
+        assert overflowed > 10000 and beyond > 3000, (overflowed, beyond)
+        assert actor.uncovered_envs() == 0
+    # a side batch that is too small: nothing breaks, the misses are counted
+    env = VecNardeEnv(n, seed=31, max_actions=cap)
+    actor = AfterstateActor(env, mlp, overflow_slots=16, overflow_cap=32, overflow_rows=256)
+    env.reset()
+    for t in range(30):
+        actor.step()
+    assert actor.uncovered_envs() > 0

@@ -37,7 +37,12 @@ rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if len(r) > 3 and r[0] == "Address"][0]
 hdr = rows[hi]
 sa, ie, te = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
-samp = [(int(r[0], 16), int(r[sa]), int(r[ie]), int(r[te])) for r in rows[hi + 1:] if r[sa].isdigit()]
+samp = []
+for r in rows[hi + 1:]:          # the first launch of the report only (a report may hold several)
+    if len(r) <= te or not r[0].startswith("0x"):
+        break
+    if r[sa].isdigit():
+        samp.append((int(r[0], 16), int(r[sa]), int(r[ie]), int(r[te])))
 base = samp[0][0]
 agg = collections.defaultdict(lambda: [0, 0, 0])
 tot, toti = sum(s[1] for s in samp), sum(s[2] for s in samp)
