@@ -720,7 +720,15 @@ struct BlockStep {
   // hand-over of order-dependent doubles turns: the list is complete once every CTA is past this
   // phase, which is when the exact kernel (a programmatic dependent launch) may start
   static NHD void ph_defer_push(int tid, const Sh& sh, bool valid, int64_t i, const StepFullArgs& A) {
-    if (valid && sh.defer[tid]) A.defer_list[gl_fetch_add(A.defer_count, 1)] = (int32_t)i;
+    // entry = env index + 1: a zero word is "not published yet" (the exact kernel consumes entries while the main
+    // kernel is still producing them and puts the zero back)
+    if (valid && sh.defer[tid]) {
+#if defined(__CUDA_ARCH__)
+      *reinterpret_cast<volatile int32_t*>(A.defer_list + gl_fetch_add(A.defer_count, 1)) = (int32_t)i + 1;
+#else
+      A.defer_list[gl_fetch_add(A.defer_count, 1)] = (int32_t)i + 1;
+#endif
+    }
   }
   static NHD void ph_env_bases(int tid, Sh& sh) {
     if (NT == BLK || tid < BLK) sh.ebase[tid] = sh.kind[tid] == K_ND ? sh.base[2][tid] : sh.base[3][tid];

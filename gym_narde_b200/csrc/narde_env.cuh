@@ -91,6 +91,11 @@ struct StepFullArgs {
   // kernel acquires `arrivals == n_primary` before it reads the list
   int32_t* arrivals;
   int32_t n_primary;
+  // large batches (several waves of main CTAs): the main kernel triggers its dependent at its very START, so the exact
+  // kernel's CTAs become resident as soon as the last main CTA has been dispatched, run the solver once on a built-in
+  // position (its code executes once per CTA: cold, it is bound by instruction fetch) and then wait for the list
+  int32_t early_trigger;
+  int64_t list_cap;  // entries the list can hold (= n): CTAs of the exact kernel beyond it have no entry to wait for
   int32_t* last_count;  // diagnostic: number of deferred envs of the completed call (F_DEVICE_ADVANCE clears the counter)
   // optional second destination of the state planes (16-byte lanes like lo / hi): pinned host memory of a host-side
   // consumer, for which the 32-byte record IS the observation (gym_narde_b200.expand_obs198 decodes it to Box(198))

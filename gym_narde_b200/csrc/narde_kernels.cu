@@ -26,10 +26,12 @@ constexpr int kThreads = 128;
 // envs (= threads) per CTA of the fused step: 128 for large batches; one-warp CTAs of 32 envs when the batch
 // cannot fill the machine otherwise (4096 envs: 128 CTAs instead of 32; measured 0.081 -> 0.053 ms/step)
 int g_variant = 0;
-int g_tile = 64;  // envs per CTA of the large-batch fused step: 64 (two threads per env) or 128 (NARDE_TILE in the environment: A/B timing)
+bool g_early = true;  // NARDE_LATE_TRIGGER=1 in the environment: the dependent is triggered after the count phase for every batch size (A/B timing)
+int g_tile = 128;  // envs per CTA of the large-batch fused step: 128 (a thread per env) or 64 on 128 threads (NARDE_TILE=64 in the environment; measured equal within noise: the step is bound by the CTA's chain of phases, not by resident warps)
 int64_t kSmallBatch = 16384;  // (NARDE_SMALL_BATCH in the environment overrides it: A/B timing of the two tiles)
 constexpr int kDeferredThreads = 128;  // exact-doubles kernel: four warps per CTA, one env per warp at a time (7 KB of shared memory each)
 constexpr int kDeferredGrid = 148 * 8;  // 8 CTAs per SM (64 registers, 27 KB)
+constexpr int kDeferredGridEarly = 148 * 4;  // early-trigger launches: these CTAs sit beside the main kernel's last wave
 
 __device__ __forceinline__ State ld_state(const uint4* __restrict__ lo, const uint4* __restrict__ hi, int64_t i) {
   uint4 a = lo[i], b = hi[i];
@@ -59,45 +61,45 @@ __device__ __forceinline__ void write_obs198_cta(const State* sm, const float4* 
                                                  float* __restrict__ obs, const uint32_t* skip = nullptr,
                                                  int tid = (int)threadIdx.x, int nthreads = (int)blockDim.x) {
   float* base = obs + row0 * 198;
-  const int items = rows * 24;
   // rows are 792 B: in a 16-byte aligned row the WHITE block (4 floats per point from offset 0) is made of
   // aligned 16-byte lanes and the BLACK block (from offset 392 B) of 8-byte ones; in the next row it is the
-  // other way round -- one 16-byte and two 8-byte stores per (env, point) instead of four 8-byte stores
-  const bool even_aligned = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0);
-  for (int g = tid; g < items; g += nthreads) {
-    int e = g / 24, pt = g - e * 24;
-    if (skip && skip[e]) continue;  // row written by the deferred kernel
-    int v = sm[e].point(pt);
-    float4 fw = lut[v > 0 ? v : 0], fb = lut[v < 0 ? -v : 0];
-    float* rw = base + e * 198 + 4 * pt;
-    float* rb = rw + 98;
-    if (((e & 1) == 0) == even_aligned) {
-      *reinterpret_cast<float4*>(rw) = fw;
-      reinterpret_cast<float2*>(rb)[0] = make_float2(fb.x, fb.y);
-      reinterpret_cast<float2*>(rb)[1] = make_float2(fb.z, fb.w);
-    } else {
-      reinterpret_cast<float2*>(rw)[0] = make_float2(fw.x, fw.y);
-      reinterpret_cast<float2*>(rw)[1] = make_float2(fw.z, fw.w);
-      *reinterpret_cast<float4*>(rb) = fb;
+  // other way round -- one 16-byte and two 8-byte stores per (env, point) instead of four 8-byte stores.
+  // A thread keeps ONE point (24 threads per env; its state word and byte shift are loop constants) and takes, per
+  // trip, one row of each alignment, so the warp never diverges on the store pattern and there is no division in
+  // the loop (the item loop it replaces spent 51 instructions per (env, point): 17 % of the kernel's instructions).
+  const int ngrp = nthreads / 24, grp = tid / 24, pt = tid - grp * 24;
+  if (grp < ngrp) {
+    const int wi = pt >> 2, shf = (pt & 3) * 8;
+    const int pa = ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) ? 0 : 1;  // parity of the 16-byte aligned rows
+    for (int j = grp; 2 * j < rows; j += ngrp) {
+      const int eA = 2 * j + pa, eB = 2 * j + 1 - pa;
+      if (eA < rows && !(skip && skip[eA])) {  // (skip: row written by the deferred kernel)
+        const int v = (int)(int8_t)(sm[eA].w[wi] >> shf);
+        const float4 fw = lut[v > 0 ? v : 0], fb = lut[v < 0 ? -v : 0];
+        float* rw = base + eA * 198 + 4 * pt;
+        float* rb = rw + 98;
+        *reinterpret_cast<float4*>(rw) = fw;
+        reinterpret_cast<float2*>(rb)[0] = make_float2(fb.x, fb.y);
+        reinterpret_cast<float2*>(rb)[1] = make_float2(fb.z, fb.w);
+      }
+      if (eB < rows && !(skip && skip[eB])) {
+        const int v = (int)(int8_t)(sm[eB].w[wi] >> shf);
+        const float4 fw = lut[v > 0 ? v : 0], fb = lut[v < 0 ? -v : 0];
+        float* rw = base + eB * 198 + 4 * pt;
+        float* rb = rw + 98;
+        reinterpret_cast<float2*>(rw)[0] = make_float2(fw.x, fw.y);
+        reinterpret_cast<float2*>(rw)[1] = make_float2(fw.z, fw.w);
+        *reinterpret_cast<float4*>(rb) = fb;
+      }
     }
   }
-  for (int g = tid; g < rows * 3; g += nthreads) {
-    int e = g / 3, k = g - e * 3;
+  for (int e = tid; e < rows; e += nthreads) {  // bars (always empty: no hitting, narde.py:71), off / 15, side to move
     if (skip && skip[e]) continue;
     const State& s = sm[e];
-    float2 v;
-    int at;
-    if (k == 0) {  // WHITE bar (always empty: no hitting, narde.py:71) and off / 15
-      v = make_float2(0.0f, off15(s.off_w()));
-      at = 96;
-    } else if (k == 1) {
-      v = make_float2(0.0f, off15(s.off_b()));
-      at = 194;
-    } else {
-      v = s.turn() == 1 ? make_float2(1.0f, 0.0f) : make_float2(0.0f, 1.0f);
-      at = 196;
-    }
-    *reinterpret_cast<float2*>(base + e * 198 + at) = v;
+    float* r = base + e * 198;
+    *reinterpret_cast<float2*>(r + 96) = make_float2(0.0f, off15(s.off_w()));
+    *reinterpret_cast<float2*>(r + 194) = make_float2(0.0f, off15(s.off_b()));
+    *reinterpret_cast<float2*>(r + 196) = s.turn() == 1 ? make_float2(1.0f, 0.0f) : make_float2(0.0f, 1.0f);
   }
 }
 
@@ -249,6 +251,9 @@ __global__ void __launch_bounds__(NT, MINB) k_step_full_v2(uint4* lo, uint4* hi,
   State s;
   PHASE_MARK(0);
   GT_MARK(blockIdx.x, 10);
+  // Programmatic dependent launch, large batches: the exact kernel may become resident once every main CTA has
+  // STARTED (it then warms its code up and waits for the list, see k_step_deferred)
+  if (DEFER && A.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // The caller's action words of this CTA (BLK x 4 B, contiguous) come in as ONE bulk asynchronous copy into
   // shared memory.  When the buffer is pinned host memory (zero-copy step_host) that is one PCIe read of 512 B
   // per CTA instead of a 32-byte read per warp sector: the host step was bound by the NUMBER of small reads.
@@ -289,16 +294,16 @@ __global__ void __launch_bounds__(NT, MINB) k_step_full_v2(uint4* lo, uint4* hi,
   BS::ph_env_totals(tid, sh);
   if (DEFER) {
     BS::ph_defer_push(tid, sh, valid, i, A);
-    __threadfence();
+    if (valid && sh.defer[tid]) __threadfence();  // (only a thread that pushed an entry: a fence per thread cost 1.8 % of the samples)
   }
   __syncthreads();
   // Publication of this CTA's list entries: the barrier above orders every thread's pushes before thread 0's
   // release-add; k_step_deferred acquires "all main CTAs have arrived" before it reads the list (the visibility
   // of a primary grid's writes is otherwise only guaranteed after griddepcontrol.wait, i.e. after its completion).
   if (DEFER && tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(A.arrivals) : "memory");
-  // Programmatic dependent launch: k_step_deferred may start as soon as every CTA is past this point,
-  // i.e. while the action lists and Box(198) rows of the other envs are still being written.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Programmatic dependent launch, small batches (one wave): k_step_deferred may start as soon as every CTA is past
+  // this point, i.e. while the action lists and Box(198) rows of the other envs are still being written.
+  if (!A.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   BS::ph_scan_serial(tid, sh, 0xFu);
   __syncthreads();
   BS::ph_env_bases(tid, sh);
@@ -435,44 +440,84 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
   };
   __shared__ Smem sm;
   __shared__ float4 lut[16];
-  __shared__ int32_t s_last;
+  __shared__ int32_t s_last, s_entry;
   obs_lut_init(lut);
   const int tid = threadIdx.x;
   GT_MARK(3072 + blockIdx.x, 0);
   // Launched as a programmatic dependent of k_step_full_v2: this grid starts once every main CTA has executed its
-  // trigger, which each does AFTER its release-add to `arrivals` -- so the acquire below never really waits, it
-  // makes the list entries of all main CTAs formally visible here although the main grid is still running.
+  // trigger -- at the CTA's start for large batches, after its release-add to `arrivals` (end of the count phase) for
+  // one-wave batches -- while the main grid is still running.  "arrivals == n_primary" (acquire) means: every main CTA
+  // has pushed its entries, the list is complete.
+  // The list is consumed WHILE it is produced.  With the early trigger (large batches) this grid is resident as soon as
+  // the last main CTA has been dispatched, most entries are already there (every main CTA of the earlier waves is past
+  // its count phase) and the rest arrive while the last wave runs: CTA b takes entry b the moment it is published --
+  // an entry is the env index + 1, a zero word means "not yet" -- instead of waiting for the complete list, so the
+  // ~18 us an order-dependent turn takes (a latency-bound chain of ~4000 dependent instructions) overlap the main
+  // kernel's last wave instead of following it.  Every consumed entry is zeroed again for the next call.
+  volatile int32_t* list = reinterpret_cast<volatile int32_t*>(A.defer_list);
+  TeamExec ex;
+  ex.tid = tid;
+  ex.cta = true;
+  {
+    const int q = (int)blockIdx.x;
+    if (tid == 0) {
+      int32_t v = 0, seen = 0;
+      while (q < A.list_cap) {
+        v = list[q];
+        if (v != 0) break;
+        if (seen >= A.n_primary) break;  // the list was complete before that read of the entry: there is no entry q
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(A.arrivals) : "memory");
+        if (seen < A.n_primary) __nanosleep(100);
+      }
+      if (v != 0) list[q] = 0;
+      s_entry = v;
+    }
+    __syncthreads();
+    const int32_t v = s_entry;
+    GT_MARK(3072 + blockIdx.x, 1);
+    if (v != 0) {
+#ifdef NARDE_DEBUG_HOOKS
+      ex.clk = (g_dbg_clk && q < 1024) ? g_dbg_clk + (size_t)(2048 + q) * 16 : nullptr;
+      if (g_dbg_flags & 4) { /* timing experiment only (wrong results): the deferred envs are not solved */ } else
+#endif
+      exact_env<BLK>(ex, sm.cta, lut, lo, hi, (int64_t)v - 1, A, obs198, stats);
+    }
+  }
+  // entries beyond the first gridDim.x (long lists: the doubles-heavy enumeration microbench) need the complete list
   if (tid == 0) {
     int32_t seen;
-    do {
+    for (;;) {
       asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(A.arrivals) : "memory");
-    } while (seen < A.n_primary);
+      if (seen >= A.n_primary) break;
+      __nanosleep(100);
+    }
   }
   __syncthreads();
-  GT_MARK(3072 + blockIdx.x, 1);
   int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
+  const int G = (int)gridDim.x;
+  if (n_def > G) {
+    if (n_def <= 3 * G) {  // a few more: the CTA as a team again
+      for (int q = G + (int)blockIdx.x; q < n_def; q += G) {
+        const int32_t v = list[q];
+        __syncthreads();
+        if (tid == 0) list[q] = 0;
 #ifdef NARDE_DEBUG_HOOKS
-  if (g_dbg_flags & 4) n_def = 0;  // timing experiment only (wrong results): the deferred envs are not solved
+        ex.clk = (g_dbg_clk && q < 1024) ? g_dbg_clk + (size_t)(2048 + q) * 16 : nullptr;
 #endif
-  const volatile int32_t* list = reinterpret_cast<const volatile int32_t*>(A.defer_list);
-  TeamExec ex;
-  if (n_def <= 2 * (int)gridDim.x) {  // consecutive CTAs sit on different SMs: a short list spreads over all of them
-    ex.tid = tid;
-    ex.cta = true;
-    for (int q = blockIdx.x; q < n_def; q += gridDim.x) {
+        exact_env<BLK>(ex, sm.cta, lut, lo, hi, (int64_t)v - 1, A, obs198, stats);
+      }
+    } else {               // throughput-bound: one env per warp
+      ex.tid = tid & 31;
+      ex.cta = false;
+      for (int q = G + (tid >> 5) * G + (int)blockIdx.x; q < n_def; q += G * (BLK / 32)) {
+        const int32_t v = list[q];
+        __syncwarp();
+        if ((tid & 31) == 0) list[q] = 0;
 #ifdef NARDE_DEBUG_HOOKS
-      ex.clk = (g_dbg_clk && q < 1024) ? g_dbg_clk + (size_t)(2048 + q) * 16 : nullptr;
+        ex.clk = (g_dbg_clk && q < 1024) ? g_dbg_clk + (size_t)(2048 + q) * 16 : nullptr;
 #endif
-      exact_env<BLK>(ex, sm.cta, lut, lo, hi, list[q], A, obs198, stats);
-    }
-  } else {
-    ex.tid = tid & 31;
-    ex.cta = false;
-    for (int q = (tid >> 5) * (int)gridDim.x + (int)blockIdx.x; q < n_def; q += (int)gridDim.x * (BLK / 32)) {
-#ifdef NARDE_DEBUG_HOOKS
-      ex.clk = (g_dbg_clk && q < 1024) ? g_dbg_clk + (size_t)(2048 + q) * 16 : nullptr;
-#endif
-      exact_env<32>(ex, sm.warp[tid >> 5], lut, lo, hi, list[q], A, obs198, stats);
+        exact_env<32>(ex, sm.warp[tid >> 5], lut, lo, hi, (int64_t)v - 1, A, obs198, stats);
+      }
     }
   }
   GT_MARK(3072 + blockIdx.x, 2);
@@ -849,7 +894,9 @@ int narde_abi_version(void) {
     v = getenv("NARDE_SMALL_BATCH");
     if (v) kSmallBatch = atoll(v);
     v = getenv("NARDE_TILE");
-    if (v && atoi(v) == 128) g_tile = 128;
+    if (v && (atoi(v) == 128 || atoi(v) == 64)) g_tile = atoi(v);
+    v = getenv("NARDE_LATE_TRIGGER");
+    if (v && v[0] == '1') g_early = false;
     v = getenv("NARDE_VARIANT");
     if (v) g_variant = atoi(v);
     env_read = true;
@@ -958,6 +1005,8 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
   A.ticket = nullptr;
   A.arrivals = nullptr;
   A.n_primary = 0;
+  A.early_trigger = 0;
+  A.list_cap = n;
   A.last_count = nullptr;
   A.mirror_lo = mirror_lo;
   A.mirror_hi = mirror_hi;
@@ -978,6 +1027,7 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
     A.last_count = workspace + 3;
     A.defer_list = workspace + NARDE_WORKSPACE_HEADER;
     A.n_primary = (int32_t)(n <= kSmallBatch ? (n + 31) / 32 : (n + g_tile - 1) / g_tile);
+    A.early_trigger = (g_use_pdl && g_early && n > kSmallBatch) ? 1 : 0;
     if (dev_advance) {  // the three counters are zero on entry and again on exit
       A.ticket = workspace + 1;
     } else {
@@ -1023,7 +1073,7 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
   if (workspace) {
     if (g_use_pdl) {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(kDeferredGrid);
+      cfg.gridDim = dim3(A.early_trigger && n <= 524288 ? kDeferredGridEarly : kDeferredGrid);
       cfg.blockDim = dim3(kDeferredThreads);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = (cudaStream_t)stream;

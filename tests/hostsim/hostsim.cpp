@@ -109,7 +109,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
                  int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
-  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.mirror_lo = A.mirror_hi = nullptr;
+  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.early_trigger = 0; A.list_cap = n; A.mirror_lo = A.mirror_hi = nullptr;
   A.last_count = nullptr;
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
@@ -143,7 +143,7 @@ int hs_enumerate_fast(const void* lo, const void* hi, const uint8_t* dice, int64
 
 static int64_t g_small_batch = 16384;
 extern "C" void hs_set_small_batch(int64_t v) { g_small_batch = v; }
-static int g_tile = 64;   // large-batch tile, as in narde_kernels.cu: 64 envs on 128 threads (default) or 128 on 128
+static int g_tile = 128;   // large-batch tile, as in narde_kernels.cu: 128 envs on 128 threads (default) or 64 on 128
 extern "C" void hs_set_tile(int v) { g_tile = v; }
 
 // CTA-cooperative step (narde_block.cuh) emulated phase by phase: every phase runs for all tids
@@ -206,7 +206,7 @@ static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float*
   static ExactSharedT<NT> sh;
   HostTeamExec<NT> ex;
   for (int q = 0; q < A.defer_count[0]; q++) {
-    int64_t i = A.defer_list[q];
+    int64_t i = A.defer_list[q] - 1;   // entries are env index + 1 (0 = not published, narde_block.cuh ph_defer_push)
     State s = load_state(lo, hi, i);
     ES::solve(ex, sh, s, i, A);
     StepFullLocal L;
@@ -231,7 +231,7 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
                     int32_t flags, int32_t max_episode_steps, int32_t* workspace, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
-  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.mirror_lo = A.mirror_hi = nullptr;
+  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.early_trigger = 0; A.list_cap = n; A.mirror_lo = A.mirror_hi = nullptr;
   A.last_count = nullptr;
   if (workspace) {
     for (int k = 0; k < 8; k++) workspace[k] = 0;   // NARDE_WORKSPACE_INTS layout (include/narde_b200.h)

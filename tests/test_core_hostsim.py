@@ -120,8 +120,8 @@ def _v1_v2_equal(hostsim, lo, hi, **kw):
 
 
 def test_block_kernel_tile_128_equals_per_thread_body(hostsim):
-    """The library uses 32-env one-warp CTAs for batches <= 16384 and, above, 64-env CTAs of 128 threads (two threads
-    per env in the item phases; NARDE_TILE=128 selects the older 128-env / 128-thread tile); force both large tiles on
+    """The library uses 32-env one-warp CTAs for batches <= 16384 and 128-env CTAs above (NARDE_TILE=64 selects the
+    64-env / 128-thread tile: two threads per env in the item phases); force both large tiles on
     small inputs so that all three are checked here (the other tests run the 32-env tile)."""
     import ctypes as C
     hostsim.lib.hs_set_small_batch(C.c_int64(0))
@@ -133,7 +133,7 @@ def test_block_kernel_tile_128_equals_per_thread_body(hostsim):
             P.check_step_full_lockstep(hostsim, 67, 60, 0xF00D + tile, cap=4)
     finally:
         hostsim.lib.hs_set_small_batch(C.c_int64(16384))
-        hostsim.lib.hs_set_tile(C.c_int(64))
+        hostsim.lib.hs_set_tile(C.c_int(128))
 
 
 def test_block_kernel_equals_per_thread_body(hostsim):

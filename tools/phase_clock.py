@@ -12,7 +12,7 @@ env = VecNardeEnv(E, seed=0x5EED, max_actions=64)
 env.reset()
 for _ in range(300):
     env.step()
-TILE = 128 if os.environ.get('NARDE_TILE') == '128' else 64   # envs per main CTA (the library reads the same variable)
+TILE = 64 if os.environ.get('NARDE_TILE') == '64' else 128   # envs per main CTA (the library reads the same variable)
 nb = min((E + TILE - 1) // TILE, 2048)
 buf = torch.zeros((max(nb, 2048) + 1024, 16), dtype=torch.int64, device="cuda")
 lib = _cabi.load()
