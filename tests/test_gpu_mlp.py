@@ -8,8 +8,9 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-ABS_TOL = 2e-2          # |q_kernel - q_fp32| on Q-values of magnitude ~0.1-0.5
-ARGMAX_AGREEMENT = 0.97  # bf16 rounding flips near-ties; reported, not hidden
+ABS_TOL = 5e-3          # |q_kernel - q_fp32| on Q-values of magnitude ~0.1-0.5 (measured 7e-4; SURVEY 7.10 asks <= 1e-2)
+ARGMAX_AGREEMENT = 0.95  # floor only: bf16 rounding flips near-ties among 576 random-init Q-values; the measured figure is
+                         # printed by __graft_entry__.smoke(), and every flip must be a near-tie (checked below)
 
 
 def _reference_net():
@@ -39,8 +40,12 @@ def test_mlp_matches_fp32_reference_on_real_observations():
         err = (q - ref).abs().max().item()
         assert err < ABS_TOL, (rows, err)
         if rows == 4096:
-            agree = (q.argmax(1) == ref.argmax(1)).float().mean().item()
+            am, rm = q.argmax(1), ref.argmax(1)
+            agree = (am == rm).float().mean().item()
             assert agree > ARGMAX_AGREEMENT, agree
+            # where the arg-max differs, the fp32 net itself has the two candidates within the kernel's error
+            gap = ref.gather(1, rm[:, None]) - ref.gather(1, am[:, None])
+            assert gap.max().item() < 2 * ABS_TOL, gap.max().item()
     # exactness of the data path: with bf16-representable weights/inputs the only error is accumulation order
     torch.manual_seed(1)
     xb = torch.randint(0, 2, (512, 198), device="cuda").float()
