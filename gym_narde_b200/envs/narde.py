@@ -8,6 +8,8 @@ reference's own tests run unchanged.  The fields live on the host exactly as in 
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from .. import _cabi
@@ -21,31 +23,52 @@ def rotate_board(board):
 
 
 class _Dev:
-    """Lazily allocated n=1 device buffers shared by all Narde facades of the process."""
+    """Lazily allocated n=1 buffers shared by all Narde facades of the process.
+
+    They live in PINNED HOST memory, which CUDA maps into the device address space: the kernels read the packed state /
+    dice / codes and write their results straight over PCIe (the zero-copy I/O VecNardeEnv.step_host uses), so a facade
+    call is one kernel launch and one stream synchronisation -- no host<->device copy operations (a call used to be 3
+    H2D copies, a launch and 2 synchronous D2H copies)."""
     _inst = None
 
     def __init__(self):
         torch = _cabi.require_cuda()
         _cabi.load()
-        dev = torch.device("cuda")
         self.torch = torch
-        self.lo = torch.zeros((1, 16), dtype=torch.uint8, device=dev)
-        self.hi = torch.zeros((1, 16), dtype=torch.uint8, device=dev)
-        self.dice4 = torch.zeros((1, 4), dtype=torch.uint8, device=dev)
-        self.dice2 = torch.zeros((1, 2), dtype=torch.uint8, device=dev)
-        self.moves = torch.zeros((1, _cabi.MAX_HALF_MOVES, 2), dtype=torch.uint8, device=dev)
-        self.counts = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.codes = torch.zeros((1, 2), dtype=torch.int32, device=dev)
-        self.obs24 = torch.zeros((1, 24), dtype=torch.int32, device=dev)
-        self.obs198 = torch.zeros((1, 198), dtype=torch.float32, device=dev)
-        self.rew_i = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.rew_f = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.done = torch.zeros(1, dtype=torch.uint8, device=dev)
-        self.act = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.actions = torch.zeros((1, 4096), dtype=torch.int64, device=dev)
-        self.overflow = torch.zeros(1, dtype=torch.uint8, device=dev)
-        self.board8 = torch.zeros((1, 24), dtype=torch.int8, device=dev)
-        self.flag = torch.zeros(1, dtype=torch.uint8, device=dev)
+        z = lambda shape, dtype: torch.zeros(shape, dtype=dtype).pin_memory()
+        self.lo = z((1, 16), torch.uint8)
+        self.hi = z((1, 16), torch.uint8)
+        self.dice4 = z((1, 4), torch.uint8)
+        self.dice2 = z((1, 2), torch.uint8)
+        self.moves = z((1, _cabi.MAX_HALF_MOVES, 2), torch.uint8)
+        self.counts = z(1, torch.int32)
+        self.codes = z((1, 2), torch.int32)
+        self.obs24 = z((1, 24), torch.int32)
+        self.obs198 = z((1, 198), torch.float32)
+        self.rew_i = z(1, torch.int32)
+        self.rew_f = z(1, torch.float32)
+        self.done = z(1, torch.uint8)
+        self.act = z(1, torch.int64)
+        self.actions = z((1, 4096), torch.int64)
+        self.overflow = z(1, torch.uint8)
+        self.board8 = z((1, 24), torch.int8)
+        self.flag = z(1, torch.uint8)
+        # numpy views and raw pointers of the hot single-env calls (packing through generic [n,16] array code and
+        # re-validating every tensor per call cost more than the kernel: 98 -> see tools/facade_latency.py)
+        self.lo_i8 = self.lo.numpy().view(np.int8)[0]
+        self.hi_i8 = self.hi.numpy().view(np.int8)[0]
+        self.hi_u8 = self.hi.numpy()[0]
+        self.np = {k: getattr(self, k).numpy() for k in ("dice4", "dice2", "moves", "counts", "codes", "obs24", "rew_i", "done")}
+        self.p = {k: C.c_void_p(getattr(self, k).data_ptr()) for k in
+                  ("lo", "hi", "dice4", "dice2", "moves", "counts", "codes", "obs24", "rew_i", "done")}
+        self.lib = _cabi.load()
+
+    def stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def sync(self):
+        """Wait for the kernels enqueued so far: their results are then in the (host) buffers."""
+        self.torch.cuda.current_stream().synchronize()
 
     @classmethod
     def get(cls):
@@ -55,24 +78,32 @@ class _Dev:
 
 
 def upload_game(dev, game, turn):
-    lo, hi = S.pack_states(np.asarray(game.board, dtype=np.int64), game.borne_off_white, game.borne_off_black,
-                           turn, bool(game.first_turn_white), bool(game.first_turn_black))
-    dev.lo.copy_(dev.torch.from_numpy(lo))
-    dev.hi.copy_(dev.torch.from_numpy(hi))
+    """The state record (gym_narde_b200/state.py layout) of one game, written straight into the pinned planes."""
+    board = np.asarray(game.board)
+    dev.lo_i8[:] = board[:16]
+    dev.hi_i8[:8] = board[16:]
+    h = dev.hi_u8
+    h[8] = game.borne_off_white
+    h[9] = game.borne_off_black
+    dev.hi_i8[10] = turn
+    h[11] = (S.FLAG_FIRST_W if game.first_turn_white else 0) | (S.FLAG_FIRST_B if game.first_turn_black else 0)
+    h[12:16] = 0
 
 
 def download_game(dev, game):
-    u = S.unpack_states(dev.lo.cpu().numpy(), dev.hi.cpu().numpy())
-    board = u["board"][0].astype(np.int32)
+    dev.sync()
     try:
-        game.board[:] = board  # keep the caller's array object alive when possible
+        game.board[:16] = dev.lo_i8  # keep the caller's array object alive when possible
+        game.board[16:] = dev.hi_i8[:8]
     except Exception:
-        game.board = board
-    game.borne_off_white = int(u["off_w"][0])
-    game.borne_off_black = int(u["off_b"][0])
-    game.first_turn_white = bool(u["first_w"][0])
-    game.first_turn_black = bool(u["first_b"][0])
-    return u
+        game.board = np.concatenate([dev.lo_i8, dev.hi_i8[:8]]).astype(np.int32)
+    h = dev.hi_u8
+    flags = int(h[11])
+    game.borne_off_white = int(h[8])
+    game.borne_off_black = int(h[9])
+    game.first_turn_white = bool(flags & S.FLAG_FIRST_W)
+    game.first_turn_black = bool(flags & S.FLAG_FIRST_B)
+    return {"turn": [int(dev.hi_i8[10])], "done": [bool(flags & S.FLAG_DONE)]}
 
 
 class Narde:
@@ -91,7 +122,8 @@ class Narde:
         dev = _Dev.get()
         upload_game(dev, self, 1 if current_player == 1 else -1)
         _cabi.obs24(dev.lo, dev.hi, dev.obs24)
-        return dev.obs24.cpu().numpy()[0].astype(np.int32)
+        dev.sync()
+        return dev.obs24.numpy()[0].astype(np.int32)
 
     def get_valid_moves(self, roll, current_player=1):
         """gym_narde/envs/narde.py:58-92 (narde_half_moves kernel): ordered list of (from, to|'off')."""
@@ -100,13 +132,16 @@ class Narde:
             raise ValueError("roll must hold 1..4 dice in 1..6")
         dev = _Dev.get()
         upload_game(dev, self, 1 if current_player == 1 else -1)
-        d4 = np.zeros((1, 4), dtype=np.uint8)
-        d4[0, :len(roll)] = roll
-        dev.dice4.copy_(dev.torch.from_numpy(d4))
-        _cabi.half_moves(dev.lo, dev.hi, dev.dice4, dev.moves, dev.counts)
-        n = int(dev.counts.cpu()[0])
-        mv = dev.moves.cpu().numpy()[0, :n]
-        return [(int(f), 'off' if int(t) == S.OFF else int(t)) for f, t in mv]
+        d4 = dev.np["dice4"][0]
+        d4[:] = 0
+        d4[:len(roll)] = roll
+        p = dev.p
+        rc = dev.lib.narde_half_moves(p["lo"], p["hi"], p["dice4"], 1, 0, p["moves"], p["counts"], dev.stream())
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_half_moves failed: %d" % rc)
+        dev.sync()
+        n = int(dev.np["counts"][0])
+        return [(f, 'off' if t == S.OFF else t) for f, t in dev.np["moves"][0, :n].tolist()]
 
     def execute_rotated_move(self, move, current_player):
         """gym_narde/envs/narde.py:36-56 (narde_apply_actions kernel, half-move only)."""
@@ -123,7 +158,8 @@ class Narde:
         b = np.clip(np.asarray(board, dtype=np.int64), -127, 127).astype(np.int8).reshape(1, 24)
         dev.board8.copy_(dev.torch.from_numpy(b))
         _cabi.violates_block_rule(dev.board8, dev.flag)
-        return bool(dev.flag.cpu()[0])
+        dev.sync()
+        return bool(dev.flag.numpy()[0])
 
     def validate_move(self, move, roll, current_player=1):
         """gym_narde/envs/narde.py:186-192."""
@@ -137,6 +173,7 @@ class Narde:
         upload_game(dev, self, 1 if current_player == 1 else -1)
         dev.dice2.copy_(dev.torch.tensor([[abs(d1), abs(d2)]], dtype=dev.torch.uint8))
         _cabi.enumerate_actions(dev.lo, dev.hi, dev.dice2, dev.actions, dev.counts, dev.overflow)
-        n = min(int(dev.counts.cpu()[0]), dev.actions.shape[1])
-        acts = dev.actions.cpu().numpy()[0, :n].view(np.uint64)
+        dev.sync()
+        n = min(int(dev.counts.numpy()[0]), dev.actions.shape[1])
+        acts = dev.actions.numpy()[0, :n].view(np.uint64).copy()
         return [tuple(S.decode_action(a)) for a in acts]

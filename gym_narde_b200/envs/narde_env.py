@@ -90,9 +90,11 @@ class NardeEnv(_Base):
         upload_game(dev, self.game, self.current_player)
         if self.rules == "reference":
             _cabi.obs24(dev.lo, dev.hi, dev.obs24)  # narde_env.py:24-25
-            return dev.obs24.cpu().numpy()[0].astype(np.int32)
+            dev.sync()
+            return dev.obs24.numpy()[0].astype(np.int32)
         _cabi.obs198(dev.lo, dev.hi, dev.obs198)
-        return dev.obs198.cpu().numpy()[0].copy()
+        dev.sync()
+        return dev.obs198.numpy()[0].copy()
 
     # ---- reset (narde_env.py:105-120) ----------------------------------------------------
     def reset(self, *, seed=None, options=None):
@@ -120,15 +122,18 @@ class NardeEnv(_Base):
         dev = _Dev.get()
         t = dev.torch
         upload_game(dev, self.game, self.current_player)
-        dev.dice2.copy_(t.tensor([dice], dtype=t.uint8))
-        c1, c2 = int(action[0]), int(action[1])
-        dev.codes.copy_(t.tensor([[c1, c2]], dtype=t.int32))
-        _cabi.step_ref(dev.lo, dev.hi, dev.dice2, dev.codes, dev.obs24, dev.rew_i, dev.done, max_episode_steps=0)
-        u = download_game(dev, self.game)
+        dev.np["dice2"][0, :] = dice
+        dev.np["codes"][0, :] = (int(action[0]), int(action[1]))
+        p = dev.p
+        rc = dev.lib.narde_step_ref(p["lo"], p["hi"], p["dice2"], p["codes"], 1, 0, p["obs24"], p["rew_i"], p["done"], None,
+                                    dev.stream())
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_step_ref failed: %d" % rc)
+        u = download_game(dev, self.game)          # (synchronises: every output of the kernel is in host memory)
         self.current_player = int(u["turn"][0])
-        obs = dev.obs24.cpu().numpy()[0].astype(np.int32)
-        reward = int(dev.rew_i.cpu()[0])
-        done = bool(int(dev.done.cpu()[0]))
+        obs = dev.np["obs24"][0].astype(np.int32)
+        reward = int(dev.np["rew_i"][0])
+        done = bool(int(dev.np["done"][0]))
         self.last_roll = tuple(dice)
         return obs, reward, done, False, {}
 
@@ -170,8 +175,8 @@ class NardeEnv(_Base):
         u = download_game(dev, self.game)
         self.current_player = int(u["turn"][0])
         self.last_roll = None
-        obs = dev.obs198.cpu().numpy()[0].copy()
-        return obs, float(dev.rew_f.cpu()[0]), bool(int(dev.done.cpu()[0])), False, {}
+        obs = dev.obs198.numpy()[0].copy()
+        return obs, float(dev.rew_f.numpy()[0]), bool(int(dev.done.numpy()[0])), False, {}
 
     # ---- misc (narde_env.py:122-141) -----------------------------------------------------
     def render(self):
