@@ -521,13 +521,11 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
     }
   }
   GT_MARK(3072 + blockIdx.x, 2);
-  // stream order: this grid must not complete before its primary has (the next step follows it)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  GT_MARK(3072 + blockIdx.x, 3);
   // F_DEVICE_ADVANCE: the step's own bookkeeping instead of a memset and a counter kernel in front of every step
-  // (each is a node of the step's CUDA graph, ~2 us).  Every CTA of this grid is done with the list and has read the
-  // step index before it arrives here, and the primary grid is complete: the last arrival clears the list and its
-  // header for the next step and publishes the new step index.
+  // (each is a node of the step's CUDA graph, ~2 us).  Every CTA of this grid is done with the list when it arrives
+  // here, and every main CTA has read the step index (first thing it does) and is past its last access to the list
+  // header (arrivals == n_primary was observed above): the last arrival clears the header for the next step and
+  // publishes the new step index -- while the main grid may still be writing its action lists and Box(198) rows.
   if (A.ticket) {
     __syncthreads();
     if (tid == 0) {
@@ -546,6 +544,10 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
       }
     }
   }
+  GT_MARK(3072 + blockIdx.x, 3);
+  // stream order: this grid must not complete before its primary has (the next step follows it); nothing is left to
+  // do after it
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   GT_MARK(3072 + blockIdx.x, 4);
 }
 
