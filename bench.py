@@ -366,6 +366,17 @@ def run_cuda_arm(args):
         env.step()
         stored += int(env.counts.clamp(max=args.cap).sum().item())
     A_stored = stored / (32.0 * E)
+    # side figure: the same turns back to back in ONE device interval, no L2 flush (what a pipeline of steps sees: the
+    # launch latency and the exact kernel's last microseconds hide behind the next turn; a turn writes ~126 MB of
+    # outputs per GPU on top of the previous turn's, as much as the L2 holds)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_b2b = 256
+    t0.record()
+    for _ in range(n_b2b):
+        env.step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms_b2b = t0.elapsed_time(t1) / n_b2b
 
     # ---- end-to-end arm: host action choices in (pinned) -> step -> reward/done out (pinned) ----
     # uniformly random u32 fractions (fraction=True), FRESH every turn from a pinned pool the "host policy" filled
@@ -583,6 +594,9 @@ def run_cuda_arm(args):
             line["cross_rank_shard_check"] = cross
         if cfg5 is not None:
             line["config5_afterstate_scoring"] = cfg5
+        line["back_to_back"] = {"ms_per_turn": ms_b2b, "value_rank0": E / (ms_b2b * 1e-3), "turns": n_b2b,
+                                "note": "rank 0: 256 graph-replayed turns in one CUDA-event interval, L2 NOT flushed (side figure; "
+                                        "`value` is the flushed, individually timed one)"}
         if cfg3 is not None:
             cfg3.pop("_sample", None)
             line["config3_enumeration_microbench"] = cfg3

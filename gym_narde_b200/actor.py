@@ -64,7 +64,8 @@ class AfterstateActor:
         self._scan_ws = t.zeros((n + 127) // 128 + 4, dtype=t.int64, device=dev)   # NARDE_AFTERSTATE_SCRATCH_WORDS(n)
         self.choice = t.zeros(n, dtype=t.int32, device=dev)
         self.value = t.zeros(n, dtype=t.float32, device=dev)
-        self.dice = t.zeros((n, 2), dtype=t.uint8, device=dev)
+        self.dice = env.dice                                        # the turn's dice (written by the enumeration)
+        self.act_override = t.zeros(n, dtype=t.int64, device=dev)   # chosen actions beyond the stored lists (side batch)
         self.lib = _cabi.load()
         m = max(256, n // 16) if overflow_slots is None else int(overflow_slots)
         self.side = None
@@ -124,7 +125,8 @@ class AfterstateActor:
             raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
         rc = self.lib.narde_scatter_choice(P(sb.choice.data_ptr()), P(sb.value.data_ptr()), P(sb.idx.data_ptr()),
                                            P(sb.counts_eff.data_ptr()), P(sb.counts.data_ptr()), sb.m, sb.cap,
-                                           P(self.choice.data_ptr()), P(self.value.data_ptr()), P(sb.ctrl.data_ptr()), st)
+                                           P(self.choice.data_ptr()), P(self.value.data_ptr()), P(sb.ctrl.data_ptr()),
+                                           P(sb.actions.data_ptr()), P(self.act_override.data_ptr()), st)
         if rc != 0:
             raise _cabi.NardeCudaError("narde_scatter_choice failed: %d" % rc)
 
@@ -135,7 +137,7 @@ class AfterstateActor:
     def choose(self):
         """roll -> enumerate -> afterstates -> score -> greedy index.  Returns (choice [N] int32, dice [N,2])."""
         env = self.env
-        self.dice.copy_(env.roll())
+        env.roll()                        # (writes env.dice, which self.dice is)
         actions, counts, _ = env.get_valid_actions(self.dice)
         self.afterstates(actions, counts)
         self.mlp.score_states(self.as_lo, self.as_hi, out=self.scores, rows_dev=self.rows_dev)
@@ -148,10 +150,28 @@ class AfterstateActor:
         self._overflow_pass(self.dice)
         return self.choice, self.dice
 
+    def _play_chosen(self):
+        """narde_step_chosen: the lists of this turn are in env.actions / env.counts and the choice is made -- apply it and
+        complete the turn (reward, termination, auto-reset, statistics, Box(198)) without enumerating the position again."""
+        env, P = self.env, C.c_void_p
+        flags = (_cabi.REWARD_MOVER12 if env.reward_mode == "mover12" else 0) | (_cabi.AUTORESET if env.autoreset else 0)
+        rc = self.lib.narde_step_chosen(P(env.lo.data_ptr()), P(env.hi.data_ptr()), env.num_envs, env.env_base, env.seed, 0,
+                                        P(self.dice.data_ptr()), P(self.choice.data_ptr()), P(env.actions.data_ptr()), self.cap,
+                                        P(env.counts.data_ptr()), P(self.act_override.data_ptr()), P(env.chosen.data_ptr()),
+                                        P(env.obs.data_ptr()), P(env.reward.data_ptr()), P(env.done.data_ptr()),
+                                        P(env.trunc.data_ptr()), P(env.stats.data_ptr()), flags, env.max_episode_steps,
+                                        P(env._step_dev.data_ptr()), self._stream())
+        if rc != 0:
+            raise _cabi.NardeCudaError("narde_step_chosen failed: %d" % rc)
+
     def step(self):
         """One greedy lock-step turn for all envs; returns VecNardeEnv.step's tuple."""
-        choice, dice = self.choose()
-        return self.env.step(choice, dice=dice)
+        env = self.env
+        self.choose()
+        env.step_count += 1
+        env._step_dev.fill_(env.step_count)
+        self._play_chosen()
+        return env.obs, env.reward, env.terminated, env.truncated, env.info
 
     # -- the same turn as ONE CUDA-graph replay ---------------------------------------------------
     def _enqueue_turn(self):
@@ -173,11 +193,7 @@ class AfterstateActor:
         if rc != 0:
             raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
         self._overflow_pass(self.dice)
-        _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, action_idx=self.choice,
-                        actions=env.actions if env.write_actions else None, counts=env.counts, dice_out=env.dice,
-                        chosen=env.chosen, obs198=env.obs, reward=env.reward, done=env.done, stats=env.stats,
-                        flags=flags, max_episode_steps=env.max_episode_steps, truncated=env.trunc,
-                        workspace=env._workspaces[0], step_dev=env._step_dev)
+        self._play_chosen()
 
     def step_graph(self):
         """step() as one CUDA-graph replay (captured on first use; needs the env built with chunks=1)."""

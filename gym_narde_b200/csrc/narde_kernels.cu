@@ -207,6 +207,74 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
   write_obs198_cta(sm, lut, rows, row0, obs198);
 }
 
+// The turn when the action is already known (the greedy actor: the lists were enumerated and scored a moment ago):
+// apply choice[i] of the stored list -- or act_override[i] when it is not 0 (an action beyond the stored capacity,
+// found by the side-batch pass; consumed and cleared here) -- then exactly the fused step's completion: termination,
+// reward, player switch, truncation, auto-reset, outputs, statistics, Box(198).  A thread per env, no enumeration:
+// the second full pass over the position that narde_step_full(action_idx) makes is not needed.
+__global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, int64_t n, StepFullArgs A_in,
+                                                         const uint64_t* actions, const int32_t* counts, uint64_t* act_override,
+                                                         float* obs198, int64_t* stats) {
+  StepFullArgs A = A_in;
+  if (A.step_dev) A.step = *A.step_dev;
+  __shared__ State sm[kThreads];
+  __shared__ float4 lut[16];
+  obs_lut_init(lut);
+  const int64_t row0 = (int64_t)blockIdx.x * blockDim.x, i = row0 + threadIdx.x;
+  StepFullLocal L;
+  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
+  if (i < n) {
+    State s = ld_state(lo, hi, i);
+    if (s.flags() & FLAG_DONE) {  // a finished game without auto-reset stays as it is (BlockStep::ph_finish, K_DONE)
+      if (A.chosen) A.chosen[i] = ACT_EMPTY;
+      if (A.reward) A.reward[i] = 0.0f;
+      if (A.done) A.done[i] = 1;
+      if (A.truncated) A.truncated[i] = 0;
+    } else {
+      const int count = counts[i];
+      uint64_t act = ACT_EMPTY;
+      if (count > 0) {
+        int idx = A.action_idx[i];
+        idx = idx < 0 ? 0 : idx < count ? idx : count - 1;
+        const uint64_t over = act_override ? act_override[i] : 0ull;
+        act = over ? over : actions[i * (int64_t)A.cap + (idx < A.cap ? idx : A.cap - 1)];
+      }
+      if (act_override && act_override[i]) act_override[i] = 0ull;
+      const uint16_t d2 = reinterpret_cast<const uint16_t*>(A.dice_in)[i];
+      StepFullArgs B = A;
+      B.counts = nullptr;    // counts / dice / lists are the enumeration's outputs and stay as they are
+      B.dice_out = nullptr;
+      complete_env(s, i, B, s.turn(), (uint32_t)count, act, d2 & 0xFF, d2 >> 8, L);
+      L.overflow = count > A.cap ? 1 : 0;
+      st_state(lo, hi, i, s);
+    }
+    sm[threadIdx.x] = s;
+  }
+  if (stats) {
+    unsigned full = 0xFFFFFFFFu;
+    int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
+    int mx = L.count, ov = L.overflow;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(full, v[k], o);
+      mx = max(mx, __shfl_xor_sync(full, mx, o));
+      ov += __shfl_xor_sync(full, ov, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++)
+        if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
+      if (mx) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)mx);
+      if (ov) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), (unsigned long long)ov);
+    }
+  }
+  if (!obs198) return;
+  __syncthreads();
+  const int rows = (int)min((int64_t)blockDim.x, n - row0);
+  write_obs198_cta(sm, lut, rows, row0, obs198);
+}
+
 // Debug aid (NARDE_DEBUG_HOOKS builds only): per-CTA phase timestamps (clock64) when a buffer was registered
 // through narde_debug_set_clock_buffer; [block][16] u64.
 #ifdef NARDE_DEBUG_HOOKS
@@ -763,7 +831,8 @@ __global__ void __launch_bounds__(kThreads) k_gather_overflow(const uint4* lo, c
 }
 __global__ void __launch_bounds__(1024) k_scatter_choice(const int32_t* sub_choice, const float* sub_value, const int32_t* sub_idx,
                                                         const int32_t* sub_counts_eff, const int32_t* sub_counts, int m, int cap,
-                                                        int32_t* choice, float* value, int32_t* ctrl) {
+                                                        int32_t* choice, float* value, int32_t* ctrl,
+                                                        const uint64_t* sub_actions, uint64_t* act_out) {
   const int seen = ctrl[0];
   const int used = seen < m ? seen : m;
   int missed = 0;
@@ -777,6 +846,8 @@ __global__ void __launch_bounds__(1024) k_scatter_choice(const int32_t* sub_choi
     if (sub_counts && sub_counts[sl] > cap) missed++;  // longer than the side batch's capacity: best of the first `cap`
     choice[i] = sub_choice[sl];
     if (value && sub_value) value[i] = sub_value[sl];
+    // the action itself, for narde_step_chosen: an index beyond the main batch's stored list cannot be looked up there
+    if (act_out && sub_actions) act_out[i] = sub_actions[(int64_t)sl * cap + sub_choice[sl]];
   }
   if (missed) atomicAdd(&ctrl[2], missed);
   __syncthreads();
@@ -1151,10 +1222,37 @@ int narde_gather_overflow(const void* lo, const void* hi, const uint8_t* dice, c
 
 int narde_scatter_choice(const int32_t* sub_choice, const float* sub_value, const int32_t* sub_idx, const int32_t* sub_counts_eff,
                          const int32_t* sub_counts, int32_t m, int32_t cap, int32_t* choice, float* value, int32_t* ctrl,
-                         void* stream) {
+                         const uint64_t* sub_actions, uint64_t* act_out, void* stream) {
   if (m <= 0 || !sub_choice || !sub_idx || !choice || !ctrl) return -1;
   k_scatter_choice<<<1, 1024, 0, (cudaStream_t)stream>>>(sub_choice, sub_value, sub_idx, sub_counts_eff, sub_counts, m, cap, choice,
-                                                         value, ctrl);
+                                                         value, ctrl, sub_actions, act_out);
+  return launch_status();
+}
+
+int narde_step_chosen(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step, const uint8_t* dice,
+                      const int32_t* choice, const uint64_t* actions, int32_t cap, const int32_t* counts, uint64_t* act_override,
+                      uint64_t* chosen, float* obs198, float* reward, uint8_t* done, uint8_t* truncated, int64_t* stats,
+                      int32_t flags, int32_t max_episode_steps, const uint64_t* step_dev, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || cap <= 0 || !lo || !hi || !dice || !choice || !actions || !counts || !aligned16(lo) || !aligned16(hi)) return -1;
+  if ((((uintptr_t)dice) & 1u) != 0 || (obs198 && (((uintptr_t)obs198) & 7u) != 0)) return -1;
+  if (flags & ~(NARDE_REWARD_MOVER12 | NARDE_AUTORESET)) return -1;
+  StepFullArgs A = {};
+  A.env_base = env_base;
+  A.seed = seed;
+  A.step = step;
+  A.dice_in = dice;
+  A.action_idx = choice;
+  A.cap = cap;
+  A.chosen = chosen;
+  A.reward = reward;
+  A.done = done;
+  A.truncated = truncated;
+  A.flags = flags;
+  A.max_episode_steps = max_episode_steps;
+  A.step_dev = step_dev;
+  k_step_chosen<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((uint4*)lo, (uint4*)hi, n, A, actions, counts, act_override,
+                                                                   obs198, stats);
   return launch_status();
 }
 

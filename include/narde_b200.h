@@ -228,13 +228,28 @@ int narde_afterstates_scan(const void *lo, const void *hi, const uint64_t *actio
  * (cleared by narde_scatter_choice), [2] running total of envs that did not fit into m slots.
  * narde_scatter_choice writes choice[sub_idx[s]] = sub_choice[s] (and value, if given) for the gathered slots; a slot
  * with sub_counts_eff[s] == 0 (no afterstate rows: row pool exhausted) is skipped, and it as well as a slot with
- * sub_counts[s] > cap (list longer than the side capacity) adds one to ctrl[2]. */
+ * sub_counts[s] > cap (list longer than the side capacity) adds one to ctrl[2].  sub_actions ([m, cap] u64) and
+ * act_out ([n] u64), both optional: act_out[sub_idx[s]] = the chosen action itself. */
 int narde_gather_overflow(const void *lo, const void *hi, const uint8_t *dice, const uint8_t *overflow, int64_t n,
                           int32_t m, void *sub_lo, void *sub_hi, uint8_t *sub_dice, int32_t *sub_idx, int32_t *ctrl,
                           void *stream);
 int narde_scatter_choice(const int32_t *sub_choice, const float *sub_value, const int32_t *sub_idx,
                          const int32_t *sub_counts_eff, const int32_t *sub_counts, int32_t m, int32_t cap,
-                         int32_t *choice, float *value, int32_t *ctrl, void *stream);
+                         int32_t *choice, float *value, int32_t *ctrl, const uint64_t *sub_actions,
+                         uint64_t *act_out, void *stream);
+
+/* The turn of narde_step_full(action_idx = choice) when the legal lists of this very turn are already in
+ * actions / counts (narde_enumerate_fast or narde_step_full(NARDE_ENUMERATE_ONLY) with the same dice): no second
+ * enumeration -- env i plays actions[i*cap + clamp(choice[i])], or act_override[i] when that word is not 0 (the
+ * action of an index beyond the stored capacity, as narde_scatter_choice's act_out delivers it; the word is
+ * cleared again) -- then termination / reward / player switch / truncation / auto-reset / statistics / Box(198)
+ * exactly as narde_step_full.  dice: [n,2] u8, the turn's dice (episode bookkeeping only).  flags:
+ * NARDE_REWARD_MOVER12 | NARDE_AUTORESET.  counts, dice and the lists are not written. */
+int narde_step_chosen(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
+                      const uint8_t *dice, const int32_t *choice, const uint64_t *actions, int32_t cap,
+                      const int32_t *counts, uint64_t *act_override, uint64_t *chosen, float *obs198, float *reward,
+                      uint8_t *done, uint8_t *truncated, int64_t *stats, int32_t flags, int32_t max_episode_steps,
+                      const uint64_t *step_dev, void *stream);
 
 /* Greedy policy over each environment's segment of afterstate scores: idx_out[i] = argmax_k
  * score[offsets[i] + k] (mode 0), or argmin when BLACK is to move (mode 1: the net scores positions for

@@ -195,3 +195,34 @@ def test_actor_scores_every_legal_action_beyond_the_stored_capacity():
     for t in range(30):
         actor.step()
     assert actor.uncovered_envs() > 0
+
+
+def test_step_chosen_equals_fused_step_with_the_same_choice():
+    """narde_step_chosen (what AfterstateActor.step plays: apply the chosen action, complete the turn, no second
+    enumeration) against narde_step_full(action_idx=choice, dice) on a twin env: states, Box(198), reward, terminated /
+    truncated, chosen action and episode statistics, through auto-resets, truncation and choices beyond the stored lists."""
+    import torch
+    from gym_narde_b200 import VecNardeEnv, AfterstateMLP, AfterstateActor
+    fn, head = _net()
+    mlp = AfterstateMLP.from_module(fn, head)
+    n = 3000
+    for cap, mode, max_steps in ((64, "max", 1000), (6, "white_value", 40)):
+        a = VecNardeEnv(n, seed=5, max_actions=cap, max_episode_steps=max_steps)
+        b = VecNardeEnv(n, seed=5, max_actions=cap, max_episode_steps=max_steps, graph=False)
+        actor = AfterstateActor(a, mlp, mode=mode, overflow_slots=n, overflow_cap=2048, overflow_rows=300 * n)
+        a.reset()
+        b.reset()
+        beyond = 0
+        for t in range(150):
+            actor.step()
+            beyond += int((actor.choice >= cap).sum().item())
+            b.step(actor.choice.clone(), dice=a.dice.clone())
+            assert torch.equal(a.lo, b.lo) and torch.equal(a.hi, b.hi), (cap, t)
+            assert torch.equal(a.obs, b.obs) and torch.equal(a.reward, b.reward), (cap, t)
+            assert torch.equal(a.done, b.done) and torch.equal(a.trunc, b.trunc), (cap, t)
+            assert torch.equal(a.chosen, b.chosen) and torch.equal(a.counts, b.counts), (cap, t)
+        assert a.episode_stats() == b.episode_stats()
+        assert a.episode_stats()["episodes"] > 0
+        if cap == 6:
+            assert beyond > 1000          # actions that were never stored in the main batch's lists were played
+        assert int(actor.act_override.abs().sum().item()) == 0   # every override was consumed
