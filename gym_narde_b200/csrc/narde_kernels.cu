@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, 
 // through narde_debug_set_clock_buffer; [block][16] u64.
 #ifdef NARDE_DEBUG_HOOKS
 __device__ unsigned long long* g_dbg_clk = nullptr;
+__device__ unsigned g_dbg_stagger_ns = 0;
 #define PHASE_MARK(k)                                                                  \
   do {                                                                                 \
     if (g_dbg_clk && threadIdx.x == 0) g_dbg_clk[(size_t)blockIdx.x * 16 + (k)] = clock64(); \
@@ -322,6 +323,11 @@ __global__ void __launch_bounds__(NT, MINB) k_step_full_v2(uint4* lo, uint4* hi,
   // Programmatic dependent launch, large batches: the exact kernel may become resident once every main CTA has
   // STARTED (it then warms its code up and waits for the list, see k_step_deferred)
   if (DEFER && A.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef NARDE_DEBUG_HOOKS
+  // timing experiment: de-phase the first wave (its CTAs start together and stay in lock-step: every phase of every CTA
+  // hits the same unit at the same time); slot k of an SM starts k * g_dbg_stagger_ns later
+  if (g_dbg_stagger_ns && blockIdx.x < 148 * 5) __nanosleep((blockIdx.x / 148) * g_dbg_stagger_ns);
+#endif
   // The caller's action words of this CTA (BLK x 4 B, contiguous) come in as ONE bulk asynchronous copy into
   // shared memory.  When the buffer is pinned host memory (zero-copy step_host) that is one PCIe read of 512 B
   // per CTA instead of a 32-byte read per warp sector: the host step was bound by the NUMBER of small reads.
@@ -1304,6 +1310,8 @@ int narde_advance_counter(uint64_t* counter, void* stream) {
 
 #ifdef NARDE_DEBUG_HOOKS
 int narde_debug_set_flags(int flags) { return (int)cudaMemcpyToSymbol(narde::g_dbg_flags, &flags, sizeof(flags)); }
+
+int narde_debug_set_stagger(unsigned ns) { return (int)cudaMemcpyToSymbol(g_dbg_stagger_ns, &ns, sizeof(ns)); }
 
 int narde_debug_set_clock_buffer(void* devptr) {
   unsigned long long* p = (unsigned long long*)devptr;

@@ -21,6 +21,9 @@ buf = torch.zeros((3072 + 2048, 16), dtype=torch.int64, device="cuda")
 lib = _cabi.load()
 lib.narde_debug_set_clock_buffer.argtypes = [C.c_void_p]
 lib.narde_debug_set_flags(flags)
+if len(sys.argv) > 3:
+    lib.narde_debug_set_stagger.argtypes = [C.c_uint]
+    lib.narde_debug_set_stagger(int(sys.argv[3]))          # ns between the start of an SM's CTA slots (first wave)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 rows = []
 for it in range(12):
