@@ -68,6 +68,7 @@ class AfterstateActor:
         self.act_override = t.zeros(n, dtype=t.int64, device=dev)   # chosen actions beyond the stored lists (side batch)
         self.lib = _cabi.load()
         m = max(256, n // 16) if overflow_slots is None else int(overflow_slots)
+        m = -(-m // 128) * 128            # whole tiles of the side batch's kernels
         self.side = None
         if m > 0:
             self.side = sb = _SideBatch(t, dev, m, int(overflow_cap))

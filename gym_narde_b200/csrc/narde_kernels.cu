@@ -241,10 +241,8 @@ __global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, 
       }
       if (act_override && act_override[i]) act_override[i] = 0ull;
       const uint16_t d2 = reinterpret_cast<const uint16_t*>(A.dice_in)[i];
-      StepFullArgs B = A;
-      B.counts = nullptr;    // counts / dice / lists are the enumeration's outputs and stay as they are
-      B.dice_out = nullptr;
-      complete_env(s, i, B, s.turn(), (uint32_t)count, act, d2 & 0xFF, d2 >> 8, L);
+      // (A.counts / A.dice_out are NULL: counts, dice and lists are the enumeration's outputs and stay as they are)
+      complete_env(s, i, A, s.turn(), (uint32_t)count, act, d2 & 0xFF, d2 >> 8, L);
       L.overflow = count > A.cap ? 1 : 0;
       st_state(lo, hi, i, s);
     }
@@ -803,9 +801,14 @@ __global__ void __launch_bounds__(kThreads) k_gather_overflow(const uint4* lo, c
                                                              uint4* sub_hi, uint8_t* sub_dice, int32_t* sub_idx, int32_t* ctrl) {
   __shared__ int s_last;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // The k-th gathered env goes to slot (k mod T) * 32 + k / T, T = m / 32: consecutive entries land in different 32-slot
+  // tiles, so the few hundred long lists are spread over all CTAs of the side batch's kernels instead of filling the
+  // first ones (contiguous slots: 136 + 140 us for the side enumeration and its afterstate rows; spread: see DESIGN 9).
+  const int T = m >> 5;
   if (i < n && overflow[i]) {
-    const int slot = atomicAdd(&ctrl[0], 1);
-    if (slot < m) {
+    const int seq = atomicAdd(&ctrl[0], 1);
+    if (seq < m) {
+      const int slot = (seq % T) * 32 + seq / T;
       sub_lo[slot] = lo[i];
       sub_hi[slot] = hi[i];
       reinterpret_cast<uint16_t*>(sub_dice)[slot] = reinterpret_cast<const uint16_t*>(dice)[i];
@@ -825,7 +828,8 @@ __global__ void __launch_bounds__(kThreads) k_gather_overflow(const uint4* lo, c
   for (int k = 0; k < 6; k++) fin.w[k] = 0;
   fin.set_meta(15, 0, 1, FLAG_DONE);
   fin.aux = 0;
-  for (int sl = (seen < m ? seen : m) + (int)threadIdx.x; sl < m; sl += (int)blockDim.x) {
+  for (int sl = (int)threadIdx.x; sl < m; sl += (int)blockDim.x) {
+    if ((sl & 31) * T + (sl >> 5) < seen) continue;  // a gathered env sits here
     st_state(sub_lo, sub_hi, sl, fin);
     reinterpret_cast<uint16_t*>(sub_dice)[sl] = 0x0101;
     sub_idx[sl] = -1;
@@ -839,12 +843,10 @@ __global__ void __launch_bounds__(1024) k_scatter_choice(const int32_t* sub_choi
                                                         const int32_t* sub_counts_eff, const int32_t* sub_counts, int m, int cap,
                                                         int32_t* choice, float* value, int32_t* ctrl,
                                                         const uint64_t* sub_actions, uint64_t* act_out) {
-  const int seen = ctrl[0];
-  const int used = seen < m ? seen : m;
   int missed = 0;
-  for (int sl = threadIdx.x; sl < used; sl += blockDim.x) {
+  for (int sl = threadIdx.x; sl < m; sl += blockDim.x) {
     const int32_t i = sub_idx[sl];
-    if (i < 0) continue;
+    if (i < 0) continue;  // an unused slot (a finished game put there by the gather)
     if (sub_counts_eff && sub_counts_eff[sl] == 0) {  // its rows did not fit the row pool: the first pass's choice stands
       missed++;
       continue;
@@ -1218,7 +1220,7 @@ int narde_afterstates_scan(const void* lo, const void* hi, const uint64_t* actio
 int narde_gather_overflow(const void* lo, const void* hi, const uint8_t* dice, const uint8_t* overflow, int64_t n, int32_t m,
                           void* sub_lo, void* sub_hi, uint8_t* sub_dice, int32_t* sub_idx, int32_t* ctrl, void* stream) {
   if (n == 0) return 0;
-  if (n < 0 || m <= 0 || !lo || !hi || !dice || !overflow || !sub_lo || !sub_hi || !sub_dice || !sub_idx || !ctrl) return -1;
+  if (n < 0 || m <= 0 || (m & 31) != 0 || !lo || !hi || !dice || !overflow || !sub_lo || !sub_hi || !sub_dice || !sub_idx || !ctrl) return -1;
   if (!aligned16(lo) || !aligned16(hi) || !aligned16(sub_lo) || !aligned16(sub_hi)) return -1;
   if ((((uintptr_t)dice) & 1u) != 0 || (((uintptr_t)sub_dice) & 1u) != 0) return -1;
   k_gather_overflow<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)lo, (const uint4*)hi, dice, overflow, n, m,

@@ -222,7 +222,8 @@ int narde_afterstates_scan(const void *lo, const void *hi, const uint64_t *actio
                            int32_t *row_env, uint64_t *scratch, int64_t rows_cap, int32_t *counts_eff, void *stream);
 
 /* Environments whose legal list exceeds the stored capacity (overflow[i] != 0, as narde_enumerate_fast reports it) are
- * copied -- state planes, dice, env index -- into a side batch of m slots, to be enumerated again with a large capacity
+ * copied -- state planes, dice, env index -- into a side batch of m slots (m a multiple of 32; consecutive entries are
+ * dealt to different 32-slot tiles so that the long lists spread over the CTAs), to be enumerated again with a large capacity
  * (DQNAgent.act, train_deepq_pytorch.py:430-507, looks at every legal move, not at the first `cap`).  Unused slots become
  * finished games (no legal action).  ctrl: 4 i32 words, zero before the first call: [0] overflowing envs of this call
  * (cleared by narde_scatter_choice), [2] running total of envs that did not fit into m slots.

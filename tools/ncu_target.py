@@ -11,7 +11,7 @@ import torch
 from gym_narde_b200 import VecNardeEnv
 
 what = sys.argv[1] if len(sys.argv) > 1 else "step"
-E = int(sys.argv[2]) if len(sys.argv) > 2 else (131072 if what == "step" else 65536)
+E = int(sys.argv[2]) if len(sys.argv) > 2 else (131072 if what == "step" else 65536)   # what: step | actor | actor_graph | c3
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 300
 torch.cuda.set_device(0)
 if what == "c3":
@@ -49,6 +49,6 @@ else:
     head = nn.Linear(256, 576).cuda()
     actor = AfterstateActor(env, AfterstateMLP.from_module(fn, head))
     for _ in range(4):
-        actor.step()
+        actor.step_graph() if what == "actor_graph" else actor.step()
     torch.cuda.synchronize()
     print("actor done", env.episode_stats())
