@@ -530,7 +530,11 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
   TeamExec ex;
   ex.tid = tid;
   ex.cta = true;
-  {
+  // (huge batches -- the 1 M-position enumeration -- have lists of tens of thousands of entries: throughput-bound, a warp
+  // per env for all of them once the list is complete, no CTA-per-entry round first; decided by the batch size so that
+  // every CTA decides the same)
+  const bool stream_entries = A.list_cap <= 524288;
+  if (stream_entries) {
     const int q = (int)blockIdx.x;
     if (tid == 0) {
       int32_t v = 0, seen = 0;
@@ -567,9 +571,10 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
   __syncthreads();
   int n_def = *reinterpret_cast<volatile const int32_t*>(A.defer_count);
   const int G = (int)gridDim.x;
-  if (n_def > G) {
-    if (n_def <= 3 * G) {  // a few more: the CTA as a team again
-      for (int q = G + (int)blockIdx.x; q < n_def; q += G) {
+  const int first = stream_entries ? G : 0;  // entries [0, first) were taken above
+  if (n_def > first) {
+    if (n_def <= first + 2 * G) {  // a few more: the CTA as a team again
+      for (int q = first + (int)blockIdx.x; q < n_def; q += G) {
         const int32_t v = list[q];
         __syncthreads();
         if (tid == 0) list[q] = 0;
@@ -581,7 +586,7 @@ __global__ void __launch_bounds__(BLK, 8) k_step_deferred(uint4* lo, uint4* hi, 
     } else {               // throughput-bound: one env per warp
       ex.tid = tid & 31;
       ex.cta = false;
-      for (int q = G + (tid >> 5) * G + (int)blockIdx.x; q < n_def; q += G * (BLK / 32)) {
+      for (int q = first + (tid >> 5) * G + (int)blockIdx.x; q < n_def; q += G * (BLK / 32)) {
         const int32_t v = list[q];
         __syncwarp();
         if ((tid & 31) == 0) list[q] = 0;
