@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libnarde_b200.so")
 if os.environ.get("NARDE_B200_DEBUG_HOOKS") == "1":   # measurement tools only (tools/*.py): the -DNARDE_DEBUG_HOOKS build
     LIB_PATH = os.path.join(_HERE, "libnarde_b200_debug.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 # flags / bits (include/narde_b200.h)
 REWARD_MOVER12 = 1
 AUTORESET = 2
@@ -24,9 +24,9 @@ PACK_RESULT = 128
 DEVICE_ADVANCE = 256
 HALF_MOVES_ONLY = 4
 MAX_HALF_MOVES = 96
-NUM_STATS = 8
+NUM_STATS = 9
 STAT_NAMES = ("episodes", "white_wins", "black_wins", "mars", "episode_steps", "legal_actions",
-              "max_actions", "overflows")
+              "max_actions", "overflows", "clamped_actions")
 
 
 

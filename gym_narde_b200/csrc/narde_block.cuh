@@ -862,7 +862,7 @@ struct BlockStep {
   // ---- phase 8: per-env completion: rare sequential cases, apply, outputs ------------------
   static NHD void ph_finish(int tid, Sh& sh, bool valid, int64_t i, const StepFullArgs& A, StepFullLocal& L) {
     L.count = 0;
-    L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
+    L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = 0;
     if (!valid) return;
     uint8_t kind = sh.kind[tid];
     if (kind == K_DONE) {
@@ -932,6 +932,7 @@ struct BlockStep {
       }
     }
     complete_env(s, i, A, player, count, act, sh.d1[tid], sh.d2[tid], L);
+    L.clamped = index_was_clamped(A, sh.rnd[tid], count);  // (sh.rnd holds the caller's word when action_idx was given)
     sh.st[tid] = s;
   }
 };

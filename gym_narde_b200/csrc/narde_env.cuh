@@ -123,11 +123,19 @@ NHD uint32_t pick_action_index(const StepFullArgs& A, int64_t i, uint32_t rnd, u
 struct StepFullLocal {  // per-env contributions to the stats vector
   int count;
   int finished, white_win, black_win, mars, ep_len, overflow;
+  int clamped;  // the caller's action index was out of range (set by the kernels after complete_env)
 };
+// SURVEY 8b "Errors": an out-of-range index never raises (the reference's step forfeits silently, narde_env.py:63);
+// it is clamped and counted
+NHD int index_was_clamped(const StepFullArgs& A, uint32_t word, uint32_t count) {
+  if (!A.action_idx || (A.flags & F_ACTION_FRACTION) || count == 0) return 0;
+  const int32_t v = (int32_t)word;
+  return (v < 0 || v >= (int32_t)count) ? 1 : 0;
+}
 
 NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal& L) {
   L.count = 0;
-  L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
+  L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = 0;
   uint32_t env = (uint32_t)(A.env_base + i);
   if (s.flags() & FLAG_DONE) {  // only reachable without auto-reset: a finished env idles
     if (A.counts) A.counts[i] = 0;
@@ -166,6 +174,7 @@ NHD void step_full_env(State& s, int64_t i, const StepFullArgs& A, StepFullLocal
   uint64_t act = ACT_EMPTY;
   if (count > 0) {
     int idx = (int)pick_action_index(A, i, rnd.z, (uint32_t)count);
+    L.clamped = A.action_idx ? index_was_clamped(A, (uint32_t)A.action_idx[i], (uint32_t)count) : 0;
     if (slice && idx < A.cap) {
       act = slice[idx];
     } else {  // not stored: enumerate again and pick the idx-th

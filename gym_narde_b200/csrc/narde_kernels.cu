@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
   int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
   int64_t i = row0 + threadIdx.x;
   StepFullLocal L;
-  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
+  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = 0;
   if (i < n) {
     State s = ld_state(lo, hi, i);
     step_full_env(s, i, A, L);
@@ -183,13 +183,14 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
     // warp-level reduction, one atomic per warp per slot that is non-zero
     unsigned full = 0xFFFFFFFFu;
     int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
-    int mx = L.count, ov = L.overflow;
+    int mx = L.count, ov = L.overflow, cl = L.clamped;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
       for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(full, v[k], o);
       mx = max(mx, __shfl_xor_sync(full, mx, o));
       ov += __shfl_xor_sync(full, ov, o);
+      cl += __shfl_xor_sync(full, cl, o);
     }
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
         if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
       if (mx) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)mx);
       if (ov) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), (unsigned long long)ov);
+      if (cl) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_CLAMPED_ACTIONS), (unsigned long long)cl);
     }
   }
   if (!obs198) return;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, 
   obs_lut_init(lut);
   const int64_t row0 = (int64_t)blockIdx.x * blockDim.x, i = row0 + threadIdx.x;
   StepFullLocal L;
-  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = 0;
+  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = 0;
   if (i < n) {
     State s = ld_state(lo, hi, i);
     if (s.flags() & FLAG_DONE) {  // a finished game without auto-reset stays as it is (BlockStep::ph_finish, K_DONE)
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, 
       // (A.counts / A.dice_out are NULL: counts, dice and lists are the enumeration's outputs and stay as they are)
       complete_env(s, i, A, s.turn(), (uint32_t)count, act, d2 & 0xFF, d2 >> 8, L);
       L.overflow = count > A.cap ? 1 : 0;
+      L.clamped = index_was_clamped(A, (uint32_t)A.action_idx[i], (uint32_t)count);
       st_state(lo, hi, i, s);
     }
     sm[threadIdx.x] = s;
@@ -251,13 +254,14 @@ __global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, 
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
     int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
-    int mx = L.count, ov = L.overflow;
+    int mx = L.count, ov = L.overflow, cl = L.clamped;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
       for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(full, v[k], o);
       mx = max(mx, __shfl_xor_sync(full, mx, o));
       ov += __shfl_xor_sync(full, ov, o);
+      cl += __shfl_xor_sync(full, cl, o);
     }
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -265,6 +269,7 @@ __global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, 
         if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
       if (mx) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)mx);
       if (ov) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), (unsigned long long)ov);
+      if (cl) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_CLAMPED_ACTIONS), (unsigned long long)cl);
     }
   }
   if (!obs198) return;
@@ -407,13 +412,14 @@ __global__ void __launch_bounds__(NT, MINB) k_step_full_v2(uint4* lo, uint4* hi,
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
     int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
-    int mx = L.count, ov = L.overflow;
+    int mx = L.count, ov = L.overflow, cl = L.clamped;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
       for (int k = 0; k < 6; k++) v[k] += __shfl_xor_sync(full, v[k], o);
       mx = max(mx, __shfl_xor_sync(full, mx, o));
       ov += __shfl_xor_sync(full, ov, o);
+      cl += __shfl_xor_sync(full, cl, o);
     }
     if ((tid & 31) == 0) {
 #pragma unroll
@@ -421,6 +427,7 @@ __global__ void __launch_bounds__(NT, MINB) k_step_full_v2(uint4* lo, uint4* hi,
         if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
       if (mx) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)mx);
       if (ov) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), (unsigned long long)ov);
+      if (cl) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_CLAMPED_ACTIONS), (unsigned long long)cl);
     }
   }
   if (!obs198) return;
@@ -480,6 +487,7 @@ __device__ __forceinline__ void exact_env(TeamExec& ex, ShT& sh, const float4* l
       }
     }
     complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L, false);
+    L.clamped = A.action_idx ? index_was_clamped(A, (uint32_t)A.action_idx[i], sh.count) : 0;
     sh.st = st;
     if (!(A.flags & F_ENUMERATE_ONLY)) {
       st_state(lo, hi, i, st);
@@ -491,6 +499,7 @@ __device__ __forceinline__ void exact_env(TeamExec& ex, ShT& sh, const float4* l
         if (v[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + k), (unsigned long long)v[k]);
       if (L.count) atomicMax(reinterpret_cast<long long*>(stats + NARDE_STAT_MAX_ACTIONS), (long long)L.count);
       if (L.overflow) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_OVERFLOWS), 1ull);
+      if (L.clamped) atomicAdd(reinterpret_cast<unsigned long long*>(stats + NARDE_STAT_CLAMPED_ACTIONS), 1ull);
     }
   }
   ex.run([](int) {});

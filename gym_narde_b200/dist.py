@@ -53,7 +53,7 @@ def broadcast_policy(tensors, src=0, group=None):
 
 
 def merge_stats(all_stats):
-    """[world, 8] -> dict of job-wide totals (slot 6, max_actions, is a max not a sum)."""
+    """[world, NUM_STATS] -> dict of job-wide totals (slot 6, max_actions, is a max not a sum)."""
     from . import _cabi
 
     tot = all_stats.sum(0).tolist()

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NARDE_ABI_VERSION 3
+#define NARDE_ABI_VERSION 4
 #define NARDE_MAX_HALF_MOVES 96 /* 4 dice x 24 points */
 /* int32 words of the optional `workspace` of narde_step_full / narde_enumerate_fast for n environments (the caller
  * zero-fills it once): header [0] number of deferred envs of the call (cleared again by a NARDE_DEVICE_ADVANCE call),
@@ -75,7 +75,8 @@ extern "C" {
 #define NARDE_STAT_LEGAL_ACTIONS 5 /* sum of legal turn actions over all stepped envs */
 #define NARDE_STAT_MAX_ACTIONS 6
 #define NARDE_STAT_OVERFLOWS 7
-#define NARDE_NUM_STATS 8
+#define NARDE_STAT_CLAMPED_ACTIONS 8 /* env turns whose caller-given action index was out of range and got clamped */
+#define NARDE_NUM_STATS 9
 
 int narde_abi_version(void);
 

@@ -121,6 +121,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
       stats[4] += L.ep_len; stats[5] += L.count;
       if (L.count > stats[6]) stats[6] = L.count;
       stats[7] += L.overflow;
+      stats[8] += L.clamped;   // NARDE_STAT_CLAMPED_ACTIONS
     }
     if (obs198)
       for (int k = 0; k < 99; k++) obs198_pair(s, k, obs198 + 198 * i + 2 * k, obs198 + 198 * i + 2 * k + 1);
@@ -182,6 +183,7 @@ static void step_full_v2_host(void* lo, void* hi, int64_t n, const StepFullArgs&
         stats[4] += L.ep_len; stats[5] += L.count;
         if (L.count > stats[6]) stats[6] = L.count;
         stats[7] += L.overflow;
+        stats[8] += L.clamped;   // NARDE_STAT_CLAMPED_ACTIONS
       }
       if (obs198)
         for (int k = 0; k < 99; k++)
@@ -212,12 +214,14 @@ static void step_deferred_host(void* lo, void* hi, const StepFullArgs& A, float*
     StepFullLocal L;
     State st = sh.st;
     complete_env(st, i, A, sh.player, sh.count, sh.chosen, sh.d1, sh.d2, L);
+    L.clamped = A.action_idx ? index_was_clamped(A, (uint32_t)A.action_idx[i], sh.count) : 0;
     store_state(lo, hi, i, st);
     if (stats) {
       stats[0] += L.finished; stats[1] += L.white_win; stats[2] += L.black_win; stats[3] += L.mars;
       stats[4] += L.ep_len; stats[5] += L.count;
       if (L.count > stats[6]) stats[6] = L.count;
       stats[7] += L.overflow;
+      stats[8] += L.clamped;   // NARDE_STAT_CLAMPED_ACTIONS
     }
     if (obs198)
       for (int k = 0; k < 99; k++) obs198_pair(st, k, obs198 + 198 * i + 2 * k, obs198 + 198 * i + 2 * k + 1);

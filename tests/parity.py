@@ -284,7 +284,7 @@ def check_step_full_lockstep(backend, n, T, seed, env_base=77, cap=32, flags=2, 
         out = backend.step_full(lo, hi, env_base=env_base, seed=seed, step=t + 1, cap=cap, action_idx=given,
                                 flags=flags | (32 if action_mode == "fraction" else 0))
         u = S.unpack_states(lo, hi)
-        exp_stats = np.zeros(8, np.int64)
+        exp_stats = np.zeros(9, np.int64)
         for i, e in enumerate(envs):
             if idle[i]:
                 assert out["done"][i] & 1 and out["counts"][i] == 0 and out["reward"][i] == 0
@@ -308,6 +308,8 @@ def check_step_full_lockstep(backend, n, T, seed, env_base=77, cap=32, flags=2, 
             exp_stats[5] += nact
             exp_stats[6] = max(exp_stats[6], nact)
             exp_stats[7] += nact > cap
+            if nact and action_mode == "index":
+                exp_stats[8] += int(given[i]) < 0 or int(given[i]) >= nact      # NARDE_STAT_CLAMPED_ACTIONS
             if nact:
                 assert act_moves(out["chosen"][i]) == list(map(tuple, acts[idx]["moves"]))
                 k = min(nact, cap)
@@ -328,7 +330,7 @@ def check_step_full_lockstep(backend, n, T, seed, env_base=77, cap=32, flags=2, 
             assert (obs == out["obs198"][i]).all(), (t, i)
             assert e.state_tuple() == (tuple(u["board"][i]), u["off_w"][i], u["off_b"][i], int(u["first_w"][i]),
                                        int(u["first_b"][i]), u["turn"][i]), (t, i)
-        for k in (0, 1, 2, 3, 5, 6, 7):
+        for k in (0, 1, 2, 3, 5, 6, 7, 8):
             assert exp_stats[k] == out["stats"][k], (t, k, exp_stats, out["stats"])
     return episodes
 

@@ -114,7 +114,7 @@ class HostSim:
             "reward": np.zeros(n, np.float32),
             "done": np.zeros(n, np.uint8),
             "trunc": np.zeros(n, np.uint8),
-            "stats": np.zeros(8, np.int64),
+            "stats": np.zeros(9, np.int64),
         }
         v1 = self.per_thread or (flags & 8)
         ws = np.zeros(n + 8, np.int32) if (self.defer and not v1) else None
@@ -235,7 +235,7 @@ class CudaBackend:
         obs = t.zeros((n, 198), dtype=t.float32, device=self.dev) if want_obs else None
         rew = t.zeros(n, dtype=t.float32, device=self.dev)
         done = t.zeros(n, dtype=t.uint8, device=self.dev)
-        stats = t.zeros(8, dtype=t.int64, device=self.dev)
+        stats = t.zeros(9, dtype=t.int64, device=self.dev)
         trunc = t.zeros(n, dtype=t.uint8, device=self.dev)
         ws = t.zeros(n + 8, dtype=t.int32, device=self.dev) if (getattr(self, "defer", True) and not (flags & 8)) else None
         if getattr(self, "per_thread", False):

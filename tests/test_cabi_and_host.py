@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     nm = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r"\bT (narde_[A-Za-z0-9_]+)$", nm, flags=re.M))
     assert exported == declared, exported ^ declared
-    assert lib.narde_abi_version() == _cabi.ABI_VERSION == 3 and lib.narde_build_arch() == b"sm_100a"
+    assert lib.narde_abi_version() == _cabi.ABI_VERSION == 4 and lib.narde_build_arch() == b"sm_100a"
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

@@ -116,7 +116,7 @@ def test_benchmark_config_131072_envs_300_graph_replayed_steps_vs_oracle():
     assert turns == n * T
     assert rec.obs_ok, "a Box(198) batch differed from the rows re-derived from the state planes"
     got = env.stats.cpu().numpy()
-    assert (got == stats).all(), (got, stats)
+    assert (got[:8] == stats).all() and got[8] == 0, (got, stats)      # (slot 8: clamped caller indices -- none here)
     assert stats[0] > 2 * n and stats[7] > 0        # every env finished games on the way; the capacity overflowed somewhere
     print("benchmark-config parity: %d env turns bit-equal to the oracle; stats %s" % (turns, stats.tolist()))
 
@@ -162,7 +162,7 @@ def test_truncation_and_small_tile_graph_replay_vs_oracle():
             rec.record(env.reward, env.done, env.trunc)
         turns, stats = rec.compare(77, 9, chunk=4096)
         assert turns == n * T and rec.obs_ok
-        assert (env.stats.cpu().numpy() == stats).all()
+        assert (env.stats.cpu().numpy()[:8] == stats).all()
         assert int(rec.done.bitwise_and(2).ne(0).sum().item()) > n   # truncations happened
 
 

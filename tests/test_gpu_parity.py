@@ -234,7 +234,7 @@ def test_device_advance_mode_equals_host_stepped_calls():
                         counts=torch.zeros(n, dtype=torch.int32, device=dev), dice=torch.zeros((n, 2), dtype=torch.uint8, device=dev),
                         chosen=torch.zeros(n, dtype=torch.int64, device=dev), obs=torch.zeros((n, 198), device=dev),
                         rew=torch.zeros(n, device=dev), done=torch.zeros(n, dtype=torch.uint8, device=dev),
-                        stats=torch.zeros(8, dtype=torch.int64, device=dev))
+                        stats=torch.zeros(9, dtype=torch.int64, device=dev))
 
         def call(b, step, flags, ws, step_dev):
             _cabi.step_full(b["lo"], b["hi"], 7, 0xD1CE, step, actions=b["actions"], counts=b["counts"], dice_out=b["dice"],
