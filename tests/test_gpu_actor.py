@@ -112,8 +112,9 @@ def test_afterstates_scan_equals_host_prefix_sum_version():
     lib = _cabi.load()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda t: C.c_void_p(t.data_ptr())
-    scratch = torch.zeros(4096 // 128 + 5, dtype=torch.int64, device="cuda")
-    for n, cap, steps in ((1, 8, 3), (127, 16, 10), (129, 64, 25), (3000, 24, 40), (4096, 64, 60)):
+    scratch = torch.zeros(131072 // 128 + 5, dtype=torch.int64, device="cuda")
+    # (131 072 envs: 1024 tiles, more than are resident at once -- the look-back really waits on other CTAs)
+    for n, cap, steps in ((1, 8, 3), (127, 16, 10), (129, 64, 25), (3000, 24, 40), (4096, 64, 60), (131072, 12, 45)):
         env = VecNardeEnv(n, seed=77 + n, max_actions=cap)
         env.reset()
         for _ in range(steps):
