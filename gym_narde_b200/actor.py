@@ -37,13 +37,14 @@ class _SideBatch:
 
 
 class AfterstateActor:
-    def __init__(self, env, mlp, mode="max", overflow_slots=None, overflow_cap=2048, overflow_rows=None):
+    def __init__(self, env, mlp, mode="max", overflow_slots=None, overflow_cap=3072, overflow_rows=None):
         """env: VecNardeEnv(rules="full"); mlp: AfterstateMLP; mode: "max" (the mover maximises the score)
         or "white_value" (the net scores positions for WHITE: WHITE maximises, BLACK minimises).
 
         Every legal action is scored, as DQNAgent.act does (train_deepq_pytorch.py:430-507): environments whose list
         is longer than env.max_actions (doubles turns, up to ~1300 actions; 0.5-1 % of the envs in self-play) get a
-        second pass with capacity `overflow_cap` in a side batch of `overflow_slots` environments (default N/16, at
+        second pass with capacity `overflow_cap` (default 3072 >= C(18, 4) = 3060, the number of 4-multisets of 15 sources:
+        every doubles turn fits; 2018 legal turns have been seen in self-play) in a side batch of `overflow_slots` environments (default N/16, at
         least 256) sharing `overflow_rows` afterstate rows (default 192 per slot).  Environments that do not fit --
         more overflowing envs than slots, a list longer than overflow_cap, or the row pool exhausted -- are counted in
         `uncovered_envs()` and keep the choice among their first max_actions actions; overflow_slots=0 switches the
