@@ -540,12 +540,21 @@ def run_cuda_arm(args):
         bytes_per_unit = 871 + 8 * A_stored                  # B_step(A), A = list entries actually stored
         kernel_ms = total_ms / (K * R)                       # rank-0 kernels of one turn (main + programmatic dependent)
         achieved = E * bytes_per_unit / (kernel_ms * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, ncu_counters = None, None, None
         cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("r02") and f.endswith("_step_full_v2.json"))
         if cands:                                            # ncu --set full of this round's kernel on this workload
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))["launches"][0].get("dram_bytes_per_launch")
+                prof = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))["launches"][0]
+                traffic = prof.get("dram_bytes_per_launch")
                 traffic_src = "ncu --set full, profiles/%s (per launch)" % cands[-1]
+                pm = prof.get("metrics", {})
+                num = lambda k: float(str(pm.get(k, "nan")).split()[0])
+                ncu_counters = {"issue_slots_busy_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                "active_threads_per_warp_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                                "warp_instructions_per_launch": num("smsp__inst_executed.sum"),
+                                "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                                "stall_cycles_per_issue": prof.get("warp_stalls_per_issue"),
+                                "source": "profiles/%s (the committed capture of this kernel; not re-measured in this run)" % cands[-1]}
             except Exception:
                 traffic = None
         line = {
@@ -561,7 +570,8 @@ def run_cuda_arm(args):
                        "parallelism": "env-sharded x%d, no data-path collective" % world},
             "roofline": {"bound": "hbm", "kernel": "k_step_full_v2<128,true> + its programmatic dependent k_step_deferred (order-dependent doubles turns, overlaps the tail), timed together as one turn", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms, "launches_timed": K * R},
+                         "algorithmic_bytes_per_env_step": bytes_per_unit, "kernel_ms": kernel_ms, "launches_timed": K * R,
+                         "ncu_counters": ncu_counters},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E * R, "d2h_bytes_per_step": 6 * E * R,
                     "ms_per_step": total_e2e_max / K, "ms_per_turn": total_e2e_max / (K * R), "observation": "Box(198) stays in HBM (device-resident policy); see e2e_with_obs",
                     "note": "VecNardeEnv.step_host(fraction=True, actions=pool row), zero-copy, one CUDA-graph replay per turn: every CTA of the fused step bulk-copies its envs' int32 action choices (fresh u32 fractions of the legal list, pinned pool) from host memory into shared memory, and reward f32 / done u8 / truncated u8 are written by the kernel straight into pinned host memory"},
