@@ -1161,6 +1161,8 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
       k_step_full_v2<128, true, 128, 8><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
     else if (g_variant == 2)
       k_step_full_v2<128, true, 256, 4><<<g, 256, 0, st>>>(plo, phi, n, A, obs198, stats);
+    else if (g_variant == 3)  // 128-register budget (110-113 used), 4 CTAs per SM: 1 us faster in the timeline probe, 7 us SLOWER in bench.py
+      k_step_full_v2<128, true, 128, 4><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
 #endif
     else
       k_step_full_v2<128, true, 128, 5><<<g, 128, 0, st>>>(plo, phi, n, A, obs198, stats);
