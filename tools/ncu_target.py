@@ -29,6 +29,23 @@ if what == "c3":
     torch.cuda.synchronize()
     print("c3 done; deferred", int(ws[0].item()))
     sys.exit(0)
+if what == "mlp":      # the tcgen05 scorer alone: 350 208 packed states of a self-play batch, three launches
+    import torch.nn as nn
+    from gym_narde_b200 import AfterstateMLP
+    env = VecNardeEnv(43776, seed=3)
+    env.reset()
+    for _ in range(40):
+        env.step()
+    lo, hi = env.lo.repeat(8, 1).contiguous(), env.hi.repeat(8, 1).contiguous()
+    torch.manual_seed(0)
+    fn = nn.Sequential(nn.Linear(198, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU()).cuda()
+    mlp = AfterstateMLP.from_module(fn, nn.Linear(256, 576).cuda())
+    out = torch.zeros(lo.shape[0], dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        mlp.score_states(lo, hi, out=out)
+    torch.cuda.synchronize()
+    print("mlp done", lo.shape[0], float(out.mean()))
+    sys.exit(0)
 env = VecNardeEnv(E, seed=0x5EED, max_actions=64, graph=False)
 env.reset()
 for _ in range(B):
