@@ -853,12 +853,12 @@ __global__ void __launch_bounds__(kThreads) k_gather_overflow(const uint4* lo, c
     if (seen > m) ctrl[2] += seen - m;
   }
 }
-__global__ void __launch_bounds__(1024) k_scatter_choice(const int32_t* sub_choice, const float* sub_value, const int32_t* sub_idx,
+__global__ void __launch_bounds__(256) k_scatter_choice(const int32_t* sub_choice, const float* sub_value, const int32_t* sub_idx,
                                                         const int32_t* sub_counts_eff, const int32_t* sub_counts, int m, int cap,
                                                         int32_t* choice, float* value, int32_t* ctrl,
                                                         const uint64_t* sub_actions, uint64_t* act_out) {
   int missed = 0;
-  for (int sl = threadIdx.x; sl < m; sl += blockDim.x) {
+  for (int sl = blockIdx.x * blockDim.x + threadIdx.x; sl < m; sl += gridDim.x * blockDim.x) {
     const int32_t i = sub_idx[sl];
     if (i < 0) continue;  // an unused slot (a finished game put there by the gather)
     if (sub_counts_eff && sub_counts_eff[sl] == 0) {  // its rows did not fit the row pool: the first pass's choice stands
@@ -872,8 +872,47 @@ __global__ void __launch_bounds__(1024) k_scatter_choice(const int32_t* sub_choi
     if (act_out && sub_actions) act_out[i] = sub_actions[(int64_t)sl * cap + sub_choice[sl]];
   }
   if (missed) atomicAdd(&ctrl[2], missed);
-  __syncthreads();
-  if (threadIdx.x == 0) ctrl[0] = 0;  // ready for the next turn's gather
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl[0] = 0;  // ready for the next turn's gather (nothing here reads it)
+}
+
+// The same for long segments (the side batch: lists of hundreds to thousands of actions): a warp per env, lanes stride over
+// the segment (coalesced), the (value, index) pairs reduced by shuffles -- a thread per env walks such a segment alone.
+__global__ void __launch_bounds__(kThreads) k_segment_argmax_warp(const float* score, const int64_t* offsets, const int32_t* counts,
+                                                                 const uint4* hi, int64_t n, int cap, int mode, int32_t* idx_out,
+                                                                 float* best_out) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;  // (whole warps leave together)
+  int c = counts[i];
+  c = c < cap ? c : cap;
+  const int64_t base = offsets[i];
+  float sign = 1.0f;
+  if (mode == 1) {
+    const uint32_t meta = hi[i].z;
+    if ((int)(int8_t)((meta >> 16) & 0xFF) != 1) sign = -1.0f;
+  }
+  float best = 0.0f;
+  int best_k = 0x7FFFFFFF;
+  for (int k = lane; k < c; k += 32) {
+    const float v = sign * score[base + k];
+    if (best_k == 0x7FFFFFFF || v > best) {  // strictly greater: the lowest index of a lane's maximum stays
+      best = v;
+      best_k = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_down_sync(0xFFFFFFFFu, best, o);
+    const int ok = __shfl_down_sync(0xFFFFFFFFu, best_k, o);
+    if (ok != 0x7FFFFFFF && (best_k == 0x7FFFFFFF || ov > best || (ov == best && ok < best_k))) {
+      best = ov;
+      best_k = ok;
+    }
+  }
+  if (lane == 0) {
+    idx_out[i] = c ? best_k : 0;
+    if (best_out) best_out[i] = c ? sign * best : 0.0f;
+  }
 }
 
 // Greedy choice per env over its segment of afterstate scores: mode 0 = maximise; mode 1 = WHITE
@@ -1248,8 +1287,8 @@ int narde_scatter_choice(const int32_t* sub_choice, const float* sub_value, cons
                          const int32_t* sub_counts, int32_t m, int32_t cap, int32_t* choice, float* value, int32_t* ctrl,
                          const uint64_t* sub_actions, uint64_t* act_out, void* stream) {
   if (m <= 0 || !sub_choice || !sub_idx || !choice || !ctrl) return -1;
-  k_scatter_choice<<<1, 1024, 0, (cudaStream_t)stream>>>(sub_choice, sub_value, sub_idx, sub_counts_eff, sub_counts, m, cap, choice,
-                                                         value, ctrl, sub_actions, act_out);
+  k_scatter_choice<<<(m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sub_choice, sub_value, sub_idx, sub_counts_eff, sub_counts, m,
+                                                                      cap, choice, value, ctrl, sub_actions, act_out);
   return launch_status();
 }
 
@@ -1284,8 +1323,12 @@ int narde_segment_argmax(const float* score, const int64_t* offsets, const int32
                          int32_t cap, int32_t mode, int32_t* idx_out, float* best_out, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || cap <= 0 || !score || !offsets || !counts || !hi || !idx_out || !aligned16(hi)) return -1;
-  k_segment_argmax<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(score, offsets, counts, (const uint4*)hi, n, cap, mode,
-                                                                       idx_out, best_out);
+  if (cap > 128)  // long segments: a warp per env
+    k_segment_argmax_warp<<<grid_for(n * 32), kThreads, 0, (cudaStream_t)stream>>>(score, offsets, counts, (const uint4*)hi, n, cap,
+                                                                                   mode, idx_out, best_out);
+  else
+    k_segment_argmax<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(score, offsets, counts, (const uint4*)hi, n, cap, mode,
+                                                                         idx_out, best_out);
   return launch_status();
 }
 
