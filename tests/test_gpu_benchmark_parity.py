@@ -198,6 +198,15 @@ def test_step_host_packed_observation_is_lossless():
             assert (host_rows == env.obs.cpu().numpy()).all(), (n, t)
             dev_rows = gym_narde_b200.expand_obs198(env.lo, env.hi)
             assert torch.equal(dev_rows, env.obs)
+        twin = VecNardeEnv(n, seed=21, max_actions=64, env_base=17)      # the form bench.py's e2e_with_obs times: + one result byte
+        twin.load_state_dict(env.state_dict())
+        for t in range(6):
+            io = env.step_host(fraction=True, actions=rows[t % 4], obs="packed", packed=True)
+            twin.step(rows[t % 4].cuda(), fraction=True)
+            torch.cuda.synchronize()
+            assert torch.equal(io["lo"], twin.lo.cpu()) and torch.equal(io["hi"], twin.hi.cpu()), (n, t)
+            want = twin.done.cpu() | (twin.trunc.cpu() << 1) | (twin.reward.cpu().to(torch.uint8) << 2)
+            assert torch.equal(io["result"], want), (n, t)
 
 
 def test_config3_synthetic_positions_vs_oracle():

@@ -15,7 +15,9 @@ def timed(fn, n=100):
     torch.cuda.synchronize()
     t = sorted(x.elapsed_time(y) for x, y in ev)
     return "mean %.4f p50 %.4f min %.4f" % (sum(t) / n, t[n // 2], t[0])
-for name, kw in (("device random step", None), ("step_host dma_in=True", {"dma_in": True}), ("step_host dma_in=False", {"dma_in": False})):
+for name, kw in (("device random step", None), ("step_host dma_in=True", {"dma_in": True}), ("step_host dma_in=False", {"dma_in": False}),
+                 ("step_host packed result", {"packed": True}), ("step_host obs=packed", {"obs": "packed"}),
+                 ("step_host packed result + obs", {"packed": True, "obs": "packed"})):
     env = VecNardeEnv(E, seed=0x5EED, max_actions=64)
     env.reset()
     for _ in range(300):
