@@ -408,9 +408,10 @@ def run_cuda_arm(args):
         # the same, and the OBSERVATION crosses PCIe too, in its packed form (32-byte state records written by the
         # kernel into pinned host memory; gym_narde_b200.expand_obs198 decodes them to Box(198) rows on the host)
         e2e_t[0] += 1
-        # (packed=True: reward / terminated / truncated travel as ONE byte per env instead of three arrays -- with the
-        # state records crossing as well, three more streams of partial-line PCIe writes cost 14 us per turn)
-        env.step_host(fraction=True, actions=h_pool[e2e_t[0] % POOL], obs="packed", packed=True)
+        # (obs="compact": observation and result in ONE 20-byte record per env -- 24 points of 5 bits, off counts, side to
+        # move, flags, terminated / truncated / reward bits, steps -- 2.6 MB per turn instead of 4.2 MB of planes plus
+        # three result arrays: the posted PCIe writes end before the kernel does)
+        env.step_host(fraction=True, actions=h_pool[e2e_t[0] % POOL], obs="compact")
 
     for _ in range(max(W, POOL + 1)):          # one graph per pool buffer is captured on first use: all of them now
         e2e_step()
@@ -578,10 +579,10 @@ def run_cuda_arm(args):
                     "ms_per_step": total_e2e_max / K, "ms_per_turn": total_e2e_max / (K * R), "observation": "Box(198) stays in HBM (device-resident policy); see e2e_with_obs",
                     "note": "VecNardeEnv.step_host(fraction=True, actions=pool row), zero-copy, one CUDA-graph replay per turn: every CTA of the fused step bulk-copies its envs' int32 action choices (fresh u32 fractions of the legal list, pinned pool) from host memory into shared memory, and reward f32 / done u8 / truncated u8 are written by the kernel straight into pinned host memory"},
             "e2e_with_obs": {"value": units / (total_e2e_pobs_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * E * R,
-                             "d2h_bytes_per_step": 33 * E * R, "ms_per_turn": total_e2e_pobs_max / (K * R),
+                             "d2h_bytes_per_step": 20 * E * R, "ms_per_turn": total_e2e_pobs_max / (K * R),
                              "frac_of_value": (units / (total_e2e_pobs_max * 1e-3)) / value,
-                             "observation": "packed: the 32-byte state record of every env (a lossless encoding of Box(198); gym_narde_b200.expand_obs198 decodes it) is written by the kernel into pinned host memory",
-                             "note": "step_host(fraction=True, obs='packed', packed=True): actions in + packed observation + one result byte per env (bit 0 terminated, bit 1 truncated, bits 2-3 the reward) out, all through pinned host memory, no copy operations"},
+                             "observation": "compact: one 20-byte record per env (the state -- a lossless encoding of Box(198) -- and the turn's result bits; gym_narde_b200.state.unpack_compact + expand_obs198 decode it) is written by the kernel into pinned host memory",
+                             "note": "step_host(fraction=True, obs='compact'): actions in, observation + terminated / truncated / reward out in one record per env, all through pinned host memory, no copy operations (the 32-byte planes + one result byte, obs='packed', packed=True: 0.122 ms per turn)"},
             "e2e_explicit_copies": {"value": world * E * k_side / (sum(ms_e2e_copies) * 1e-3), "unit": UNIT, "ms_per_turn": sum(ms_e2e_copies) / k_side,
                                     "note": "the same turn with cudaMemcpyAsync H2D / D2H around VecNardeEnv.step (rank 0's time)"},
             "e2e_pipelined": {"value": world * E / (ms_pipe_max * 1e-3), "unit": UNIT, "ms_per_turn": ms_pipe_max,

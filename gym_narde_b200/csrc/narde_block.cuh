@@ -862,7 +862,7 @@ struct BlockStep {
   // ---- phase 8: per-env completion: rare sequential cases, apply, outputs ------------------
   static NHD void ph_finish(int tid, Sh& sh, bool valid, int64_t i, const StepFullArgs& A, StepFullLocal& L) {
     L.count = 0;
-    L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = 0;
+    L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = L.result = 0;
     if (!valid) return;
     uint8_t kind = sh.kind[tid];
     if (kind == K_DONE) {
@@ -872,6 +872,7 @@ struct BlockStep {
       if (A.reward) A.reward[i] = 0.0f;
       if (A.done) A.done[i] = (A.flags & F_ENUMERATE_ONLY) ? 0 : 1;
       if (A.truncated) A.truncated[i] = 0;
+      L.result = DONE_TERMINATED;  // a finished game without auto-reset stays terminated
       return;
     }
     if (sh.defer[tid]) return;  // handed to the exact CTA-per-env kernel (ph_defer_push); left untouched here

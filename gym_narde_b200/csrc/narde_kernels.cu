@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) k_step_full(uint4* lo, uint4* hi, in
   int64_t row0 = (int64_t)blockIdx.x * blockDim.x;
   int64_t i = row0 + threadIdx.x;
   StepFullLocal L;
-  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = 0;
+  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = L.result = 0;
   if (i < n) {
     State s = ld_state(lo, hi, i);
     step_full_env(s, i, A, L);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) k_step_chosen(uint4* lo, uint4* hi, 
   obs_lut_init(lut);
   const int64_t row0 = (int64_t)blockIdx.x * blockDim.x, i = row0 + threadIdx.x;
   StepFullLocal L;
-  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = 0;
+  L.count = L.finished = L.white_win = L.black_win = L.mars = L.ep_len = L.overflow = L.clamped = L.result = 0;
   if (i < n) {
     State s = ld_state(lo, hi, i);
     if (s.flags() & FLAG_DONE) {  // a finished game without auto-reset stays as it is (BlockStep::ph_finish, K_DONE)
@@ -409,6 +409,23 @@ __global__ void __launch_bounds__(NT, MINB) k_step_full_v2(uint4* lo, uint4* hi,
     st_state(lo, hi, i, sh.st[tid]);
     if (A.mirror_lo) st_state((uint4*)A.mirror_lo, (uint4*)A.mirror_hi, i, sh.st[tid]);  // posted PCIe writes (zero-copy)
   }
+  if (A.mirror_compact && !(A.flags & F_ENUMERATE_ONLY)) {
+    // the 20-byte host records of this CTA, packed into shared memory (the scan scratch is dead by now) and written as
+    // contiguous words: a warp's store is 128 contiguous bytes of (pinned host) memory; records of deferred envs are
+    // the exact kernel's to write
+    uint32_t* stg = &sh.part[0][0];
+    static_assert(sizeof(sh.part) + sizeof(sh.base) >= 5 * BLK * sizeof(uint32_t), "staging area of the compact records");
+    if (valid && !sh.defer[tid]) {
+      uint32_t r[5];
+      pack_compact(sh.st[tid], L.result, r);
+#pragma unroll
+      for (int k = 0; k < 5; k++) stg[tid * 5 + k] = r[k];
+    }
+    __syncthreads();
+    const int nrec = (int)min((int64_t)BLK, n - row0);
+    for (int w = tid; w < nrec * 5; w += NT)
+      if (!sh.defer[w / 5]) A.mirror_compact[row0 * 5 + w] = stg[w];
+  }
   if (stats) {
     unsigned full = 0xFFFFFFFFu;
     int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
@@ -492,6 +509,11 @@ __device__ __forceinline__ void exact_env(TeamExec& ex, ShT& sh, const float4* l
     if (!(A.flags & F_ENUMERATE_ONLY)) {
       st_state(lo, hi, i, st);
       if (A.mirror_lo) st_state((uint4*)A.mirror_lo, (uint4*)A.mirror_hi, i, st);
+      if (A.mirror_compact) {
+        uint32_t r[5];
+        pack_compact(st, L.result, r);
+        for (int k = 0; k < 5; k++) A.mirror_compact[i * 5 + k] = r[k];
+      }
     }
     if (stats) {
       int v[6] = {L.finished, L.white_win, L.black_win, L.mars, L.ep_len, L.count};
@@ -1112,8 +1134,11 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
                            uint8_t* truncated, int64_t* stats, int32_t flags, int32_t max_episode_steps, int32_t* workspace,
                            const uint64_t* step_dev, void* mirror_lo, void* mirror_hi, void* stream) {
   if (n == 0) return 0;
-  if ((mirror_lo == nullptr) != (mirror_hi == nullptr) || !aligned16(mirror_lo) || !aligned16(mirror_hi)) return -1;
+  // mirror_lo with mirror_hi: the two state planes; mirror_lo alone: the compact 20-byte records
+  if ((mirror_hi && !mirror_lo) || !aligned16(mirror_lo) || !aligned16(mirror_hi)) return -1;
   if (mirror_lo && (flags & NARDE_ENUMERATE_ONLY)) return -1;
+  const bool compact = mirror_lo && !mirror_hi;
+  if (compact && (flags & NARDE_PER_THREAD_KERNEL)) return -1;
   if (n < 0 || cap < 0 || !lo || !hi || !aligned16(lo) || !aligned16(hi)) return -1;
   if (obs198 && (((uintptr_t)obs198) & 7u) != 0) return -1;
   if (n == 0) return 0;
@@ -1142,8 +1167,9 @@ int narde_step_full_mirror(void* lo, void* hi, int64_t n, int64_t env_base, uint
   A.early_trigger = 0;
   A.list_cap = n;
   A.last_count = nullptr;
-  A.mirror_lo = mirror_lo;
+  A.mirror_lo = compact ? nullptr : mirror_lo;
   A.mirror_hi = mirror_hi;
+  A.mirror_compact = compact ? reinterpret_cast<uint32_t*>(mirror_lo) : nullptr;
   const bool dev_advance = (flags & NARDE_DEVICE_ADVANCE) != 0;
   if (dev_advance && (!workspace || !step_dev || (flags & (NARDE_PER_THREAD_KERNEL | NARDE_ENUMERATE_ONLY)))) return -1;
   if (flags & NARDE_PER_THREAD_KERNEL) {

@@ -87,6 +87,41 @@ def rotate_board(board):
     return np.concatenate((-board[..., 12:], -board[..., :12]), axis=-1)
 
 
+COMPACT_RECORD_BYTES = 20   # NARDE_COMPACT_RECORD_BYTES (include/narde_b200.h)
+
+
+def unpack_compact(rec):
+    """Decode the compact host records VecNardeEnv.step_host(obs="compact") receives ([n,20] uint8; layout in
+    include/narde_b200.h) -> (lo, hi, result): the two [n,16] uint8 state planes exactly as the device holds them
+    (feed them to expand_obs198 / unpack_states) and the turn's result byte (bit 0 terminated, bit 1 truncated,
+    bits 2-3 the reward 0/1/2).  Numpy on the host: a decoder of the wire format, nothing in the product calls it."""
+    rec = np.ascontiguousarray(np.asarray(rec, dtype=np.uint8).reshape(-1, COMPACT_RECORD_BYTES))
+    n = rec.shape[0]
+    x = rec[:, :16].copy().view("<u8")                     # [n,2]
+    x0, x1 = x[:, 0], x[:, 1]
+    m60 = np.uint64((1 << 60) - 1)
+    a = x0 & m60
+    b = ((x0 >> np.uint64(60)) | (x1 << np.uint64(4))) & m60
+    pts = np.empty((n, 24), np.int16)
+    for p in range(12):
+        pts[:, p] = ((a >> np.uint64(5 * p)) & np.uint64(31)).astype(np.int16)
+        pts[:, p + 12] = ((b >> np.uint64(5 * p)) & np.uint64(31)).astype(np.int16)
+    pts = ((pts ^ 16) - 16).astype(np.int8)                # 5-bit two's complement
+    w4 = rec[:, 16:20].copy().view("<u4")[:, 0]
+    lo = np.zeros((n, 16), np.uint8)
+    hi = np.zeros((n, 16), np.uint8)
+    lo[:, :] = pts[:, :16].view(np.uint8)
+    hi[:, :8] = pts[:, 16:].view(np.uint8)
+    hi[:, 8] = ((x1 >> np.uint64(56)) & np.uint64(15)).astype(np.uint8)
+    hi[:, 9] = ((x1 >> np.uint64(60)) & np.uint64(15)).astype(np.uint8)
+    hi[:, 10] = np.where(w4 & 1, 1, -1).astype(np.int8).view(np.uint8)
+    hi[:, 11] = ((w4 >> 1) & 7).astype(np.uint8)
+    steps = (w4 >> 8) & 0xFFFF
+    hi[:, 12] = (steps & 0xFF).astype(np.uint8)
+    hi[:, 13] = (steps >> 8).astype(np.uint8)
+    return lo, hi, ((w4 >> 4) & 15).astype(np.uint8)
+
+
 _OBS_LUT = None
 
 

@@ -237,7 +237,9 @@ class VecNardeEnv:
                          "result": t.zeros(n, dtype=t.uint8).pin_memory(),
                          # obs="packed": the state planes after the turn, the 32-byte encoding of Box(198)
                          "lo": t.zeros((n, 16), dtype=t.uint8).pin_memory(),
-                         "hi": t.zeros((n, 16), dtype=t.uint8).pin_memory()}
+                         "hi": t.zeros((n, 16), dtype=t.uint8).pin_memory(),
+                         # obs="compact": one 20-byte record per env (state + result bits, include/narde_b200.h)
+                         "rec": t.zeros((n, 20), dtype=t.uint8).pin_memory()}
             self._hio_graphs = {}
         return self._hio
 
@@ -258,7 +260,12 @@ class VecNardeEnv:
         obs="packed": the OBSERVATION crosses to the host as well, in its packed form -- the kernel also writes every
         env's 32-byte state record (after the turn, after an auto-reset) into host_io()["lo"] / ["hi"]; Box(198) is a
         function of exactly those bytes (gym_narde_b200.expand_obs198(lo, hi) gives the float32 [N,198] rows, bit-equal
-        to the device's), so 32 B per env cross PCIe instead of 792."""
+        to the device's), so 32 B per env cross PCIe instead of 792.
+        obs="compact": observation AND result in ONE 20-byte record per env in host_io()["rec"] (24 points of 5 bits, off
+        counts, side to move, flags, terminated / truncated / reward bits, episode steps;
+        gym_narde_b200.state.unpack_compact(rec) -> the same lo / hi planes and the result byte); reward / done /
+        truncated / result are not written separately.  2.6 MB instead of 4.3 MB per 131 072 envs: the posted PCIe
+        writes end before the kernel does."""
         t = self.torch
         if self.rules != "full":
             raise ValueError("step_host needs rules='full'")
@@ -270,8 +277,9 @@ class VecNardeEnv:
         src = io["actions"] if actions is None else actions
         if not (src.is_pinned() and src.dtype == t.int32 and src.is_contiguous() and src.numel() == self.num_envs):
             raise _cabi.NardeCudaError("step_host actions must be a pinned contiguous int32 [N] host tensor")
-        if obs not in (None, "packed"):
-            raise ValueError("obs must be None (Box(198) stays on the device) or 'packed'")
+        if obs not in (None, "packed", "compact"):
+            raise ValueError("obs must be None (Box(198) stays on the device), 'packed' or 'compact'")
+        compact = obs == "compact"
         if len(self._chunks) != 1:
             raise _cabi.NardeCudaError("step_host needs an unchunked env (chunks=1)")
         key = (src.data_ptr(), bool(fraction), bool(packed), bool(dma_in), obs)
@@ -296,11 +304,12 @@ class VecNardeEnv:
                 _cabi.step_full(self.lo, self.hi, self.env_base, self.seed, 0, action_idx=self.action_in if dma_in else src,
                                 actions=self.actions if self.write_actions else None, counts=self.counts,
                                 dice_out=self.dice, chosen=self.chosen, obs198=self.obs,
-                                reward=None if packed else io["reward"], done=io["result"] if packed else io["done"],
+                                reward=None if (packed or compact) else io["reward"],
+                                done=None if compact else (io["result"] if packed else io["done"]),
                                 stats=self.stats, flags=flags, max_episode_steps=self.max_episode_steps,
-                                truncated=None if packed else io["truncated"],
+                                truncated=None if (packed or compact) else io["truncated"],
                                 workspace=self._ws_adv if adv else self._workspaces[0], step_dev=self._step_dev,
-                                mirror_lo=io["lo"] if obs == "packed" else None,
+                                mirror_lo=io["lo"] if obs == "packed" else (io["rec"] if compact else None),
                                 mirror_hi=io["hi"] if obs == "packed" else None)
             self._hio_graphs[key] = (g, src)
         g.replay()

@@ -146,6 +146,14 @@ int narde_step_full(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t se
  * pinned HOST memory) receive every environment's state after the turn as well.  For a host-side consumer the
  * 32-byte record is a lossless encoding of the Box(198) observation (README.md:44-102 is a function of board, off
  * counts and side to move): 32 B per env cross PCIe instead of 792 (gym_narde_b200.expand_obs198 decodes it). */
+/* mirror_hi == NULL with mirror_lo != NULL selects the COMPACT host record instead: mirror_lo is [n] records of
+ * NARDE_COMPACT_RECORD_BYTES = 20 bytes (five little-endian u32 words): bits 0..119 the 24 points, 5 bits each, two's
+ * complement (+white / -black, absolute frame, point 0 first); bits 120..123 off_white, 124..127 off_black; word 4:
+ * bit 0 side to move (1 = WHITE), bits 1..3 the state flags (first_w, first_b, done), bits 4..7 the turn's result
+ * (terminated, truncated, reward 0..2 in two bits -- the NARDE_PACK_RESULT byte), bits 8..23 episode steps.  13 B less
+ * per env across PCIe than planes + result byte: the posted writes end before the kernel does
+ * (gym_narde_b200.state.unpack_compact decodes it; VecNardeEnv.step_host(obs="compact")). */
+#define NARDE_COMPACT_RECORD_BYTES 20
 int narde_step_full_mirror(void *lo, void *hi, int64_t n, int64_t env_base, uint64_t seed, uint64_t step,
                            const uint8_t *dice_in, const int32_t *action_idx, int32_t cap, uint64_t *actions,
                            int32_t *counts, uint8_t *dice_out, uint64_t *chosen, float *obs198, float *reward,

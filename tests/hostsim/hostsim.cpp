@@ -109,7 +109,7 @@ int hs_step_full(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t seed,
                  int32_t flags, int32_t max_episode_steps, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, actions, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
-  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.early_trigger = 0; A.list_cap = n; A.mirror_lo = A.mirror_hi = nullptr;
+  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.early_trigger = 0; A.list_cap = n; A.mirror_lo = A.mirror_hi = nullptr; A.mirror_compact = nullptr;
   A.last_count = nullptr;
   for (int64_t i = 0; i < n; i++) {
     State s = load_state(lo, hi, i);
@@ -235,7 +235,7 @@ int hs_step_full_v2(void* lo, void* hi, int64_t n, int64_t env_base, uint64_t se
                     int32_t flags, int32_t max_episode_steps, int32_t* workspace, void*) {
   StepFullArgs A = {env_base, seed, step, dice_in, action_idx, cap, cap > 0 ? actions : nullptr, counts, dice_out,
                     chosen, reward, done, truncated, flags, max_episode_steps, nullptr, nullptr, nullptr};
-  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.early_trigger = 0; A.list_cap = n; A.mirror_lo = A.mirror_hi = nullptr;
+  A.ticket = nullptr; A.arrivals = nullptr; A.n_primary = 0; A.early_trigger = 0; A.list_cap = n; A.mirror_lo = A.mirror_hi = nullptr; A.mirror_compact = nullptr;
   A.last_count = nullptr;
   if (workspace) {
     for (int k = 0; k < 8; k++) workspace[k] = 0;   // NARDE_WORKSPACE_INTS layout (include/narde_b200.h)

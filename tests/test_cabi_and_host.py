@@ -113,3 +113,34 @@ def test_expand_obs198_on_the_host_equals_the_oracle():
     for i in range(lo.shape[0]):
         ref = O.obs198(u["board"][i], int(u["off_w"][i]), int(u["off_b"][i]), int(u["turn"][i]))
         assert (ref == got[i]).all(), i
+
+
+def test_compact_record_decoder_round_trip():
+    """gym_narde_b200.state.unpack_compact against a numpy restatement of the packing the kernels do
+    (narde_env.cuh pack_compact; layout in include/narde_b200.h): random legal-range states survive the round trip."""
+    import numpy as np
+    from gym_narde_b200 import state as S
+    rng = np.random.default_rng(5)
+    n = 4000
+    boards = rng.integers(-15, 16, (n, 24))
+    off_w, off_b = rng.integers(0, 16, n), rng.integers(0, 16, n)
+    turn = rng.choice([-1, 1], n)
+    fw, fb, dn = rng.integers(0, 2, n).astype(bool), rng.integers(0, 2, n).astype(bool), rng.integers(0, 2, n).astype(bool)
+    steps = rng.integers(0, 1 << 16, n)
+    result = rng.integers(0, 12, n)
+    lo, hi = S.pack_states(boards, off_w, off_b, turn, fw, fb, dn, steps)
+    a = np.zeros(n, np.uint64)
+    b = np.zeros(n, np.uint64)
+    for p in range(12):
+        a |= (boards[:, p].astype(np.int64) & 31).astype(np.uint64) << np.uint64(5 * p)
+        b |= (boards[:, p + 12].astype(np.int64) & 31).astype(np.uint64) << np.uint64(5 * p)
+    x0 = a | (b << np.uint64(60))
+    x1 = (b >> np.uint64(4)) | (off_w.astype(np.uint64) << np.uint64(56)) | (off_b.astype(np.uint64) << np.uint64(60))
+    w4 = ((turn == 1).astype(np.uint32) | (hi[:, 11].astype(np.uint32) << 1) | (result.astype(np.uint32) << 4)
+          | (steps.astype(np.uint32) << 8))
+    rec = np.zeros((n, 20), np.uint8)
+    rec[:, 0:8] = x0.view(np.uint8).reshape(n, 8)
+    rec[:, 8:16] = x1.view(np.uint8).reshape(n, 8)
+    rec[:, 16:20] = w4.astype("<u4").view(np.uint8).reshape(n, 4)
+    lo2, hi2, res = S.unpack_compact(rec)
+    assert (lo2 == lo).all() and (hi2 == hi).all() and (res == result).all()

@@ -207,6 +207,15 @@ def test_step_host_packed_observation_is_lossless():
             assert torch.equal(io["lo"], twin.lo.cpu()) and torch.equal(io["hi"], twin.hi.cpu()), (n, t)
             want = twin.done.cpu() | (twin.trunc.cpu() << 1) | (twin.reward.cpu().to(torch.uint8) << 2)
             assert torch.equal(io["result"], want), (n, t)
+        for t in range(8):                                               # obs="compact": one 20-byte record per env
+            io = env.step_host(fraction=True, actions=rows[t % 4], obs="compact")
+            twin.step(rows[t % 4].cuda(), fraction=True)
+            torch.cuda.synchronize()
+            lo_h, hi_h, res = S.unpack_compact(io["rec"].numpy())
+            assert (lo_h == twin.lo.cpu().numpy()).all() and (hi_h == twin.hi.cpu().numpy()).all(), (n, t)
+            want = (twin.done.cpu() | (twin.trunc.cpu() << 1) | (twin.reward.cpu().to(torch.uint8) << 2)).numpy()
+            assert (res == want).all(), (n, t)
+            assert torch.equal(env.obs, twin.obs)
 
 
 def test_config3_synthetic_positions_vs_oracle():
