@@ -79,6 +79,7 @@ class AfterstateActor:
             sb.as_hi = t.zeros((rows, 16), dtype=t.uint8, device=dev)
             sb.scores = t.zeros(rows, dtype=t.float32, device=dev)
         self._graph = None
+        self._s2 = t.cuda.Stream(device=dev) if self.side is not None else None
         self._enum_ws = t.zeros(_cabi.workspace_ints(n), dtype=t.int32, device=dev)
 
     def _stream(self):
@@ -99,12 +100,21 @@ class AfterstateActor:
             raise _cabi.NardeCudaError("narde_afterstates_scan failed: %d" % rc)
         return self.offsets
 
-    def _overflow_pass(self, dice):
-        """Second pass (see __init__): gather -> enumerate with the large capacity -> afterstates -> score -> arg-max ->
-        scatter into self.choice / self.value.  Seven launches on a few thousand positions; no host synchronisation."""
-        sb, env, P = self.side, self.env, C.c_void_p
+    def _side_prepare(self, dice):
+        """Second pass, first half (see __init__): gather -> enumerate with the large capacity -> afterstate rows.  It only
+        needs the first pass's enumeration (overflow flags), so it runs on a side stream BESIDE the first pass's rows / scorer /
+        arg-max (small latency-bound kernels next to the one-CTA-per-SM scorer); fork / join with stream waits, which a
+        CUDA-graph capture records as a branch."""
+        sb, env, P, t = self.side, self.env, C.c_void_p, self.env.torch
         if sb is None:
             return
+        main = t.cuda.current_stream(env.device)
+        self._s2.wait_stream(main)
+        with t.cuda.stream(self._s2):
+            self._side_prepare_launches(dice)
+
+    def _side_prepare_launches(self, dice):
+        sb, env, P = self.side, self.env, C.c_void_p
         st = self._stream()
         rc = self.lib.narde_gather_overflow(P(env.lo.data_ptr()), P(env.hi.data_ptr()), P(dice.data_ptr()),
                                             P(env.overflow.data_ptr()), env.num_envs, sb.m, P(sb.lo.data_ptr()),
@@ -119,6 +129,15 @@ class AfterstateActor:
                                              None, P(sb.scan_ws.data_ptr()), sb.rows_cap, P(sb.counts_eff.data_ptr()), st)
         if rc != 0:
             raise _cabi.NardeCudaError("narde_afterstates_scan failed: %d" % rc)
+
+    def _side_finish(self):
+        """Second pass, second half (after the join): score the side batch's rows, arg-max, scatter into self.choice /
+        self.value / self.act_override."""
+        sb, env, P, t = self.side, self.env, C.c_void_p, self.env.torch
+        if sb is None:
+            return
+        t.cuda.current_stream(env.device).wait_stream(self._s2)
+        st = self._stream()
         self.mlp.score_states(sb.as_lo, sb.as_hi, out=sb.scores, rows_dev=sb.rows_dev)
         rc = self.lib.narde_segment_argmax(P(sb.scores.data_ptr()), P(sb.offsets.data_ptr()), P(sb.counts_eff.data_ptr()),
                                            P(sb.hi.data_ptr()), sb.m, sb.cap, self.mode, P(sb.choice.data_ptr()),
@@ -141,6 +160,7 @@ class AfterstateActor:
         env = self.env
         env.roll()                        # (writes env.dice, which self.dice is)
         actions, counts, _ = env.get_valid_actions(self.dice)
+        self._side_prepare(self.dice)
         self.afterstates(actions, counts)
         self.mlp.score_states(self.as_lo, self.as_hi, out=self.scores, rows_dev=self.rows_dev)
         rc = self.lib.narde_segment_argmax(C.c_void_p(self.scores.data_ptr()), C.c_void_p(self.offsets.data_ptr()),
@@ -149,7 +169,7 @@ class AfterstateActor:
                                            C.c_void_p(self.value.data_ptr()), self._stream())
         if rc != 0:
             raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
-        self._overflow_pass(self.dice)
+        self._side_finish()
         return self.choice, self.dice
 
     def _play_chosen(self):
@@ -186,6 +206,7 @@ class AfterstateActor:
         _cabi.step_full(env.lo, env.hi, env.env_base, env.seed, 0, actions=env.actions, counts=env.counts,
                         dice_out=self.dice, done=env.overflow, flags=_cabi.ENUMERATE_ONLY, workspace=self._enum_ws,
                         step_dev=env._step_dev)
+        self._side_prepare(self.dice)
         self.afterstates(env.actions, env.counts)
         self.mlp.score_states(self.as_lo, self.as_hi, out=self.scores, rows_dev=self.rows_dev)
         rc = self.lib.narde_segment_argmax(C.c_void_p(self.scores.data_ptr()), C.c_void_p(self.offsets.data_ptr()),
@@ -194,7 +215,7 @@ class AfterstateActor:
                                            C.c_void_p(self.value.data_ptr()), self._stream())
         if rc != 0:
             raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
-        self._overflow_pass(self.dice)
+        self._side_finish()
         self._play_chosen()
 
     def step_graph(self):
