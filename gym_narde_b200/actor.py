@@ -101,7 +101,7 @@ class AfterstateActor:
         return self.offsets
 
     def _side_prepare(self, dice):
-        """Second pass, first half (see __init__): gather -> enumerate with the large capacity -> afterstate rows.  It only
+        """Second pass (see __init__): gather -> enumerate with the large capacity -> afterstate rows -> score -> arg-max.  It only
         needs the first pass's enumeration (overflow flags), so it runs on a side stream BESIDE the first pass's rows / scorer /
         arg-max (small latency-bound kernels next to the one-CTA-per-SM scorer); fork / join with stream waits, which a
         CUDA-graph capture records as a branch."""
@@ -129,21 +129,23 @@ class AfterstateActor:
                                              None, P(sb.scan_ws.data_ptr()), sb.rows_cap, P(sb.counts_eff.data_ptr()), st)
         if rc != 0:
             raise _cabi.NardeCudaError("narde_afterstates_scan failed: %d" % rc)
-
-    def _side_finish(self):
-        """Second pass, second half (after the join): score the side batch's rows, arg-max, scatter into self.choice /
-        self.value / self.act_override."""
-        sb, env, P, t = self.side, self.env, C.c_void_p, self.env.torch
-        if sb is None:
-            return
-        t.cuda.current_stream(env.device).wait_stream(self._s2)
-        st = self._stream()
+        # (the scorer keeps no state between launches, so this one may be queued beside the first pass's: its CTAs get
+        # their SMs when those leave)
         self.mlp.score_states(sb.as_lo, sb.as_hi, out=sb.scores, rows_dev=sb.rows_dev)
         rc = self.lib.narde_segment_argmax(P(sb.scores.data_ptr()), P(sb.offsets.data_ptr()), P(sb.counts_eff.data_ptr()),
                                            P(sb.hi.data_ptr()), sb.m, sb.cap, self.mode, P(sb.choice.data_ptr()),
                                            P(sb.value.data_ptr()), st)
         if rc != 0:
             raise _cabi.NardeCudaError("narde_segment_argmax failed: %d" % rc)
+
+    def _side_finish(self):
+        """Second pass, after the join: scatter the side batch's choices into self.choice / self.value /
+        self.act_override."""
+        sb, env, P, t = self.side, self.env, C.c_void_p, self.env.torch
+        if sb is None:
+            return
+        t.cuda.current_stream(env.device).wait_stream(self._s2)
+        st = self._stream()
         rc = self.lib.narde_scatter_choice(P(sb.choice.data_ptr()), P(sb.value.data_ptr()), P(sb.idx.data_ptr()),
                                            P(sb.counts_eff.data_ptr()), P(sb.counts.data_ptr()), sb.m, sb.cap,
                                            P(self.choice.data_ptr()), P(self.value.data_ptr()), P(sb.ctrl.data_ptr()),
