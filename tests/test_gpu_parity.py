@@ -265,3 +265,26 @@ def test_device_advance_mode_equals_host_stepped_calls():
         call(b, 0, _cabi.DEVICE_ADVANCE, ws_b, None)
     with pytest.raises(_cabi.NardeCudaError):
         call(b, 0, _cabi.DEVICE_ADVANCE, ws_a[:n + 2], ctr)     # shorter than NARDE_WORKSPACE_INTS(n)
+
+
+@pytest.mark.gpu
+def test_chunked_multi_stream_step_equals_unchunked():
+    """VecNardeEnv(chunks=k): the step launched as k sub-batches on k streams (each with its own deferred-turn list,
+    early programmatic trigger and exact kernel) plays exactly the turns of the single launch."""
+    import torch
+    from gym_narde_b200 import VecNardeEnv
+    n = 70000
+    ref = VecNardeEnv(n, seed=41, max_actions=32, graph=False)
+    ref.reset()
+    others = [VecNardeEnv(n, seed=41, max_actions=32, chunks=k, graph=g) for k, g in ((2, False), (3, True))]
+    for e in others:
+        e.reset()
+    for t in range(90):
+        ref.step()
+        for e in others:
+            e.step()
+            assert torch.equal(ref.lo, e.lo) and torch.equal(ref.hi, e.hi), t
+            assert torch.equal(ref.obs, e.obs) and torch.equal(ref.reward, e.reward) and torch.equal(ref.done, e.done), t
+            assert torch.equal(ref.counts, e.counts) and torch.equal(ref.chosen, e.chosen), t
+    for e in others:
+        assert ref.episode_stats() == e.episode_stats()
